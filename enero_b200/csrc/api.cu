@@ -1,0 +1,699 @@
+// C-ABI glue (include/enero_b200.h): contexts, weights, device mirrors of the topology,
+// the signature-compatible GNN path, the fused decision batch and the device-resident
+// episode / Local-Search batch.  No CPU fallback: every entry point below that computes
+// launches the kernels in gnn_kernels.cuh / env_kernels.cuh or fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "enero_internal.h"
+#include "env_kernels.cuh"
+#include "gnn_kernels.cuh"
+
+using namespace enero;
+
+#define CUDA_TRY(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            enero_set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));               \
+            return ENERO_ERR_CUDA;                                                             \
+        }                                                                                      \
+    } while (0)
+#define TRY(expr) do { int _r = (expr); if (_r != ENERO_OK) return _r; } while (0)
+
+static int fail(int code, const std::string& m) { enero_set_error(m); return code; }
+
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return ENERO_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { enero_set_error(std::string("cudaMalloc: ") + cudaGetErrorString(e)); return ENERO_ERR_CUDA; }
+        cap = want;
+        return ENERO_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct enero_ctx {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    float* w[2] = {nullptr, nullptr};
+    int64_t launches = 0;
+    // scratch of the GNN engine
+    DevBuf h[2], A[2], util, nK, logits, probs, action, in_loads, in_sd, in_bw, ones;
+    DevBuf x_ls, x_gid, x_first, x_second, x_cnt, x_off, x_cur, x_slot, x_src, x_goff, x_err, x_out;
+    int occ_iter[2][2] = {{0, 0}, {0, 0}};   // [indexer][last] resident CTAs/SM of k_mp_iter
+};
+
+#define LAUNCH_CHECK(ctx)                                                     \
+    do { (ctx)->launches++; CUDA_TRY(cudaGetLastError()); } while (0)
+
+// ---------------------------------------------------------------------------------------
+extern "C" int enero_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" int enero_ctx_create(int device, enero_ctx** out) {
+    if (!out) return fail(ENERO_ERR_INVALID, "enero_ctx_create: null out");
+    int n = 0;
+    CUDA_TRY(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) return fail(ENERO_ERR_INVALID, "enero_ctx_create: no such CUDA device");
+    CUDA_TRY(cudaSetDevice(device));
+    auto* c = new enero_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    c->num_sms = prop.multiProcessorCount;
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CUDA_TRY(cudaMalloc(&c->w[i], sizeof(float) * (ENERO_NPARAMS + 3)));
+        CUDA_TRY(cudaMemset(c->w[i], 0, sizeof(float) * (ENERO_NPARAMS + 3)));
+    }
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_iter[0][0], k_mp_iter<IdxExplicit, false>, MP_TPB, 0));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_iter[0][1], k_mp_iter<IdxExplicit, true>, MP_TPB, 0));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_iter[1][0], k_mp_iter<IdxTopo, false>, MP_TPB, 0));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_iter[1][1], k_mp_iter<IdxTopo, true>, MP_TPB, 0));
+    *out = c;
+    return ENERO_OK;
+}
+
+extern "C" int enero_ctx_destroy(enero_ctx* c) {
+    if (!c) return ENERO_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (DevBuf* b : {&c->h[0], &c->h[1], &c->A[0], &c->A[1], &c->util, &c->nK, &c->logits, &c->probs, &c->action,
+                      &c->in_loads, &c->in_sd, &c->in_bw, &c->ones, &c->x_ls, &c->x_gid, &c->x_first, &c->x_second,
+                      &c->x_cnt, &c->x_off, &c->x_cur, &c->x_slot, &c->x_src, &c->x_goff, &c->x_err, &c->x_out})
+        b->release();
+    for (int i = 0; i < 2; ++i) cudaFree(c->w[i]);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return ENERO_OK;
+}
+
+extern "C" int enero_ctx_sync(enero_ctx* c) {
+    if (!c) return fail(ENERO_ERR_INVALID, "null ctx");
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return ENERO_OK;
+}
+extern "C" int64_t enero_ctx_launch_count(enero_ctx* c) { return c ? c->launches : -1; }
+extern "C" void* enero_ctx_stream(enero_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+extern "C" int enero_weights_upload(enero_ctx* c, int which, const float* flat) {
+    if (!c || !flat || which < 0 || which > 1) return fail(ENERO_ERR_INVALID, "enero_weights_upload: bad argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaMemcpyAsync(c->w[which], flat, sizeof(float) * ENERO_NPARAMS, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return ENERO_OK;
+}
+extern "C" int enero_weights_download(enero_ctx* c, int which, float* flat) {
+    if (!c || !flat || which < 0 || which > 1) return fail(ENERO_ERR_INVALID, "enero_weights_download: bad argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaMemcpyAsync(flat, c->w[which], sizeof(float) * ENERO_NPARAMS, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return ENERO_OK;
+}
+
+// ---- topology mirrors -------------------------------------------------------------------
+template <class T>
+static int upload_vec(T** dst, const std::vector<T>& v) {
+    CUDA_TRY(cudaMalloc(dst, std::max<size_t>(1, v.size()) * sizeof(T)));
+    if (!v.empty()) CUDA_TRY(cudaMemcpy(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return ENERO_OK;
+}
+static void topo_free_dev(enero_topo* t) {
+    if (t->dev_id < 0) return;
+    cudaSetDevice(t->dev_id);
+    TopoDev& d = t->dev;
+    cudaFree(d.cap); cudaFree(d.capf); cudaFree(d.in_off); cudaFree(d.in_first);
+    cudaFree(d.sp_off); cudaFree(d.sp_edge); cudaFree(d.mid_off); cudaFree(d.mids);
+    d = TopoDev();
+    t->dev_id = -1;
+}
+extern "C" int enero_topo_destroy(enero_topo* t) {
+    if (!t) return ENERO_OK;
+    topo_free_dev(t);
+    delete t;
+    return ENERO_OK;
+}
+extern "C" int enero_topo_upload(enero_ctx* c, enero_topo* t) {
+    if (!c || !t) return fail(ENERO_ERR_INVALID, "enero_topo_upload: null argument");
+    if (t->dev_id == c->device) return ENERO_OK;
+    topo_free_dev(t);
+    CUDA_TRY(cudaSetDevice(c->device));
+    TopoDev& d = t->dev;
+    d.N = t->N; d.E = t->E; d.P = t->P; d.K = t->K; d.Kmax = t->Kmax; d.off_f = t->off_f; d.off_s = t->off_s;
+    TRY(upload_vec(&d.cap, t->cap)); TRY(upload_vec(&d.capf, t->capf));
+    TRY(upload_vec(&d.in_off, t->in_off)); TRY(upload_vec(&d.in_first, t->in_first));
+    TRY(upload_vec(&d.sp_off, t->sp_off)); TRY(upload_vec(&d.sp_edge, t->sp_edge));
+    TRY(upload_vec(&d.mid_off, t->mid_off)); TRY(upload_vec(&d.mids, t->mids));
+    t->dev_id = c->device;
+    return ENERO_OK;
+}
+static TopoView view_of(const enero_topo* t) {
+    const TopoDev& d = t->dev;
+    return TopoView{d.N, d.E, d.Kmax, d.cap, d.capf, d.sp_off, d.sp_edge, d.mid_off, d.mids};
+}
+
+// ---- message passing driver ---------------------------------------------------------------
+template <class IDX>
+static int run_iterations(enero_ctx* c, const IDX& idx, int which, int T, int64_t rows, int idx_kind) {
+    const int64_t ntiles = (rows + MP_TPB - 1) / MP_TPB;
+    for (int it = 0; it < T; ++it) {
+        const bool last = (it == T - 1);
+        const int occ = std::max(1, c->occ_iter[idx_kind][last ? 1 : 0]);
+        const int grid = (int)std::min<int64_t>(ntiles, (int64_t)c->num_sms * occ);
+        const float* hin = c->h[it & 1].as<float>();
+        const float* Ain = c->A[it & 1].as<float>();
+        float* hout = c->h[(it + 1) & 1].as<float>();
+        float* Aout = c->A[(it + 1) & 1].as<float>();
+        if (last) k_mp_iter<IDX, true><<<grid, MP_TPB, 0, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles);
+        else k_mp_iter<IDX, false><<<grid, MP_TPB, 0, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles);
+        LAUNCH_CHECK(c);
+    }
+    return ENERO_OK;
+}
+
+static int ensure_rows(enero_ctx* c, int64_t rows) {
+    const size_t bytes = (size_t)rows * H * sizeof(float);
+    for (int i = 0; i < 2; ++i) { TRY(c->h[i].ensure(bytes)); TRY(c->A[i].ensure(bytes)); }
+    return ENERO_OK;
+}
+
+// ---- signature-compatible GNN forward ---------------------------------------------------------
+extern "C" int enero_gnn_forward(enero_ctx* c, int which, const float* link_state, const int32_t* graph_id,
+                                 const int32_t* first, const int32_t* second, int64_t n, int64_t p, int G,
+                                 int T, float* out, int ptr_kind) {
+    if (!c || !link_state || !out || (p > 0 && (!first || !second))) return fail(ENERO_ERR_INVALID, "enero_gnn_forward: null argument");
+    if (which < 0 || which > 1 || n < 1 || p < 0 || G < 1 || T < 1 || n > 0x7fffffff || p > 0x7fffffff)
+        return fail(ENERO_ERR_INVALID, "enero_gnn_forward: bad sizes");
+    if (!graph_id && G != 1) return fail(ENERO_ERR_INVALID, "enero_gnn_forward: graph_id == NULL means a single graph");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    TRY(ensure_rows(c, n));
+    const int* d_first = first; const int* d_second = second; const int* d_gid = graph_id;
+    float* d_out = out;
+    if (ptr_kind == ENERO_HOST) {
+        CUDA_TRY(cudaMemcpyAsync(c->h[0].p, link_state, (size_t)n * H * 4, cudaMemcpyHostToDevice, st));
+        TRY(c->x_first.ensure((size_t)std::max<int64_t>(1, p) * 4)); TRY(c->x_second.ensure((size_t)std::max<int64_t>(1, p) * 4));
+        if (p) {
+            CUDA_TRY(cudaMemcpyAsync(c->x_first.p, first, (size_t)p * 4, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(c->x_second.p, second, (size_t)p * 4, cudaMemcpyHostToDevice, st));
+        }
+        d_first = c->x_first.as<int>(); d_second = c->x_second.as<int>();
+        if (graph_id) {
+            TRY(c->x_gid.ensure((size_t)n * 4));
+            CUDA_TRY(cudaMemcpyAsync(c->x_gid.p, graph_id, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+            d_gid = c->x_gid.as<int>();
+        }
+        TRY(c->x_out.ensure((size_t)G * 4));
+        d_out = c->x_out.as<float>();
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(c->h[0].p, link_state, (size_t)n * H * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    // CSR by destination row, stable in pair order
+    TRY(c->x_cnt.ensure((size_t)(n + 1) * 4)); TRY(c->x_off.ensure((size_t)(n + 1) * 4)); TRY(c->x_cur.ensure((size_t)(n + 1) * 4));
+    TRY(c->x_slot.ensure((size_t)std::max<int64_t>(1, p) * 4)); TRY(c->x_src.ensure((size_t)std::max<int64_t>(1, p) * 4));
+    TRY(c->x_goff.ensure((size_t)(G + 1) * 4)); TRY(c->x_err.ensure(4));
+    CUDA_TRY(cudaMemsetAsync(c->x_cnt.p, 0, (size_t)(n + 1) * 4, st));
+    CUDA_TRY(cudaMemsetAsync(c->x_cur.p, 0, (size_t)(n + 1) * 4, st));
+    CUDA_TRY(cudaMemsetAsync(c->x_err.p, 0, 4, st));
+    const int gp = (int)std::min<int64_t>(4096, (std::max<int64_t>(p, 1) + 255) / 256);
+    const int gn = (int)std::min<int64_t>(4096, (n + 256) / 256);
+    if (p) { k_csr_count<<<gp, 256, 0, st>>>(d_second, p, n, c->x_cnt.as<int>(), c->x_err.as<int>()); LAUNCH_CHECK(c); }
+    k_scan_excl<<<1, 1024, 0, st>>>(c->x_cnt.as<int>(), n, c->x_off.as<int>()); LAUNCH_CHECK(c);
+    if (p) {
+        k_csr_fill<<<gp, 256, 0, st>>>(d_second, p, n, c->x_off.as<int>(), c->x_cur.as<int>(), c->x_slot.as<int>()); LAUNCH_CHECK(c);
+        k_csr_sort<<<gn, 256, 0, st>>>(d_first, n, c->x_off.as<int>(), c->x_slot.as<int>(), c->x_src.as<int>(), c->x_err.as<int>()); LAUNCH_CHECK(c);
+    }
+    if (d_gid) { k_graph_offsets<<<gn, 256, 0, st>>>(d_gid, n, G, c->x_goff.as<int>(), c->x_err.as<int>()); LAUNCH_CHECK(c); }
+    else { const int go[2] = {0, (int)n}; CUDA_TRY(cudaMemcpyAsync(c->x_goff.p, go, 8, cudaMemcpyHostToDevice, st)); CUDA_TRY(cudaStreamSynchronize(st)); }
+    k_transform0<<<(int)std::min<int64_t>((n + MP_TPB - 1) / MP_TPB, 8 * c->num_sms), MP_TPB, 0, st>>>(c->w[which], c->h[0].as<float>(), c->A[0].as<float>(), n);
+    LAUNCH_CHECK(c);
+    IdxExplicit idx{n, c->x_off.as<int>(), c->x_src.as<int>()};
+    TRY(run_iterations(c, idx, which, T, n, 0));
+    GraphsExplicit gr{G, c->x_goff.as<int>()};
+    k_readout<GraphsExplicit><<<(G + 3) / 4, 128, 0, st>>>(gr, c->w[which], c->h[T & 1].as<float>(), d_out); LAUNCH_CHECK(c);
+    int err = 0;
+    CUDA_TRY(cudaMemcpyAsync(&err, c->x_err.p, 4, cudaMemcpyDeviceToHost, st));
+    if (ptr_kind == ENERO_HOST) CUDA_TRY(cudaMemcpyAsync(out, d_out, (size_t)G * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (err == 1) return fail(ENERO_ERR_INVALID, "enero_gnn_forward: first/second index out of range [0, n)");
+    if (err == 2) return fail(ENERO_ERR_INVALID, "enero_gnn_forward: graph_id must be ascending in [0, n_graphs)");
+    return ENERO_OK;
+}
+
+// ---- fused decision batch (device pointers) -------------------------------------------------------
+// logits/probs [B,Kmax], nK/action [B]; skip: u8[B] or NULL
+static int decide_dev(enero_ctx* c, enero_topo* t, int B, const double* loads, const int* sd, const double* bw,
+                      const uint8_t* skip, float* logits, float* probs, int* nK, int* action, int T) {
+    const TopoDev& d = t->dev;
+    const int RPD = d.Kmax * d.E;
+    const int64_t rows = (int64_t)B * RPD;
+    cudaStream_t st = c->stream;
+    TRY(ensure_rows(c, rows));
+    TRY(c->util.ensure((size_t)B * d.E * 4));
+    TopoView tv = view_of(t);
+    CUDA_TRY(cudaMemsetAsync(logits, 0, (size_t)B * d.Kmax * 4, st));
+    k_decision_prep<<<(int)(((int64_t)B * d.E + 255) / 256), 256, 0, st>>>(tv, B, loads, sd, skip, nK, c->util.as<float>()); LAUNCH_CHECK(c);
+    k_features<<<(int)((rows + MP_TPB - 1) / MP_TPB), MP_TPB, 0, st>>>(tv, B, RPD, sd, bw, nK, c->util.as<float>(), c->w[ENERO_ACTOR],
+                                                                     c->h[0].as<float>(), c->A[0].as<float>()); LAUNCH_CHECK(c);
+    IdxTopo idx{rows, d.E, d.off_f, d.off_s, RPD, nK, d.in_off, d.in_first};
+    TRY(run_iterations(c, idx, ENERO_ACTOR, T, rows, 1));
+    GraphsTopo gr{B, d.Kmax, d.E, RPD, nK};
+    k_readout<GraphsTopo><<<(B * d.Kmax + 3) / 4, 128, 0, st>>>(gr, c->w[ENERO_ACTOR], c->h[T & 1].as<float>(), logits); LAUNCH_CHECK(c);
+    k_policy<<<(B + 3) / 4, 128, 0, st>>>(B, d.Kmax, nK, logits, probs, action); LAUNCH_CHECK(c);
+    return ENERO_OK;
+}
+
+static int value_dev(enero_ctx* c, enero_topo* t, int B, const double* loads, float* values, int T) {
+    const TopoDev& d = t->dev;
+    const int64_t rows = (int64_t)B * d.E;
+    cudaStream_t st = c->stream;
+    TRY(ensure_rows(c, rows));
+    TRY(c->util.ensure((size_t)B * d.E * 4));
+    TRY(c->nK.ensure((size_t)B * 4));
+    TRY(c->in_sd.ensure((size_t)B * 8));
+    CUDA_TRY(cudaMemsetAsync(c->in_sd.p, 0xFF, (size_t)B * 8, st));       // sd = -1: prep yields nK = 0 ...
+    TopoView tv = view_of(t);
+    k_decision_prep<<<(int)(((int64_t)B * d.E + 255) / 256), 256, 0, st>>>(tv, B, loads, c->in_sd.as<int>(), nullptr, c->nK.as<int>(), c->util.as<float>()); LAUNCH_CHECK(c);
+    // ... and the critic's "one graph per state" is nK = 1 everywhere
+    if (c->ones.cap < (size_t)B * 4) {
+        TRY(c->ones.ensure((size_t)B * 4));
+        std::vector<int> one((size_t)c->ones.cap / 4, 1);
+        CUDA_TRY(cudaMemcpyAsync(c->ones.p, one.data(), one.size() * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    k_features_critic<<<(int)((rows + MP_TPB - 1) / MP_TPB), MP_TPB, 0, st>>>(tv, B, c->util.as<float>(), c->w[ENERO_CRITIC],
+                                                                            c->h[0].as<float>(), c->A[0].as<float>()); LAUNCH_CHECK(c);
+    IdxTopo idx{rows, d.E, d.off_f, d.off_s, d.E, c->ones.as<int>(), d.in_off, d.in_first};
+    TRY(run_iterations(c, idx, ENERO_CRITIC, T, rows, 1));
+    GraphsTopo gr{B, 1, d.E, d.E, c->ones.as<int>()};
+    k_readout<GraphsTopo><<<(B + 3) / 4, 128, 0, st>>>(gr, c->w[ENERO_CRITIC], c->h[T & 1].as<float>(), values); LAUNCH_CHECK(c);
+    return ENERO_OK;
+}
+
+extern "C" int enero_decide_batch(enero_ctx* c, enero_topo* t, int B, const double* loads, const int32_t* sd,
+                                  const double* bw, float* logits, float* probs, int32_t* nK, int32_t* action,
+                                  int ptr_kind) {
+    if (!c || !t || !loads || !sd || !bw || B < 1) return fail(ENERO_ERR_INVALID, "enero_decide_batch: bad argument");
+    if (t->dev_id != c->device) return fail(ENERO_ERR_STATE, "enero_decide_batch: topology not uploaded to this device");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const int E = t->E, Kmax = t->Kmax;
+    TRY(c->logits.ensure((size_t)B * Kmax * 4)); TRY(c->probs.ensure((size_t)B * Kmax * 4));
+    TRY(c->nK.ensure((size_t)B * 4)); TRY(c->action.ensure((size_t)B * 4));
+    if (ptr_kind == ENERO_HOST) {
+        TRY(c->in_loads.ensure((size_t)B * E * 8)); TRY(c->in_sd.ensure((size_t)B * 8)); TRY(c->in_bw.ensure((size_t)B * 8));
+        CUDA_TRY(cudaMemcpyAsync(c->in_loads.p, loads, (size_t)B * E * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(c->in_sd.p, sd, (size_t)B * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(c->in_bw.p, bw, (size_t)B * 8, cudaMemcpyHostToDevice, st));
+        TRY(decide_dev(c, t, B, c->in_loads.as<double>(), c->in_sd.as<int>(), c->in_bw.as<double>(), nullptr,
+                       c->logits.as<float>(), c->probs.as<float>(), c->nK.as<int>(), c->action.as<int>(), 5));
+        if (logits) CUDA_TRY(cudaMemcpyAsync(logits, c->logits.p, (size_t)B * Kmax * 4, cudaMemcpyDeviceToHost, st));
+        if (probs) CUDA_TRY(cudaMemcpyAsync(probs, c->probs.p, (size_t)B * Kmax * 4, cudaMemcpyDeviceToHost, st));
+        if (nK) CUDA_TRY(cudaMemcpyAsync(nK, c->nK.p, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+        if (action) CUDA_TRY(cudaMemcpyAsync(action, c->action.p, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+    } else {
+        TRY(decide_dev(c, t, B, loads, sd, bw, nullptr, logits ? logits : c->logits.as<float>(),
+                       probs ? probs : c->probs.as<float>(), nK ? nK : c->nK.as<int>(),
+                       action ? action : c->action.as<int>(), 5));
+    }
+    return ENERO_OK;
+}
+
+extern "C" int enero_value_batch(enero_ctx* c, enero_topo* t, int B, const double* loads, float* values, int ptr_kind) {
+    if (!c || !t || !loads || !values || B < 1) return fail(ENERO_ERR_INVALID, "enero_value_batch: bad argument");
+    if (t->dev_id != c->device) return fail(ENERO_ERR_STATE, "enero_value_batch: topology not uploaded to this device");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    if (ptr_kind == ENERO_HOST) {
+        TRY(c->in_loads.ensure((size_t)B * t->E * 8)); TRY(c->logits.ensure((size_t)B * 4));
+        CUDA_TRY(cudaMemcpyAsync(c->in_loads.p, loads, (size_t)B * t->E * 8, cudaMemcpyHostToDevice, st));
+        TRY(value_dev(c, t, B, c->in_loads.as<double>(), c->logits.as<float>(), 5));
+        CUDA_TRY(cudaMemcpyAsync(values, c->logits.p, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+    } else {
+        TRY(value_dev(c, t, B, loads, values, 5));
+    }
+    return ENERO_OK;
+}
+
+// ---- device-resident episode batch ---------------------------------------------------------------
+struct enero_batch {
+    enero_ctx* c = nullptr; enero_topo* t = nullptr;
+    int B = 0, Dmax = 0, NN = 0; double pct = 0.15;
+    bool reset_done = false, policy_valid = false;
+    DevBuf tm, loads, mid_cur, elig, elig_len, it, cur, cur_bw, done, steps, max_uti, max_edge, best, best_step, ospf,
+        h_action, h_reward, h_max, last_reward, logits, probs, nK, action, values;
+    DevBuf ls_loads, ls_mid, ls_elig, ls_elig_len, ls_val, ls_nmoves, ls_moves, ls_move_val, ls_max_edge;
+    std::vector<int> h_elig, h_elig_len;           // host mirror of list_eligible_demands
+    std::vector<int> h_ls_elig, h_ls_elig_len; int ls_cap = 0;
+    int max_len = 0;
+};
+
+static EpisodeView ep_view(enero_batch* b) {
+    EpisodeView v;
+    v.B = b->B; v.Dmax = b->Dmax; v.tm = b->tm.as<double>(); v.loads = b->loads.as<double>(); v.mid_cur = b->mid_cur.as<int>();
+    v.elig = b->elig.as<int>(); v.elig_len = b->elig_len.as<int>(); v.it = b->it.as<int>(); v.cur = b->cur.as<int>();
+    v.cur_bw = b->cur_bw.as<double>(); v.done = b->done.as<uint8_t>(); v.steps = b->steps.as<int>();
+    v.max_uti = b->max_uti.as<double>(); v.max_edge = b->max_edge.as<int>(); v.best = b->best.as<double>();
+    v.best_step = b->best_step.as<int>(); v.ospf = b->ospf.as<double>(); v.h_action = b->h_action.as<int>();
+    v.h_reward = b->h_reward.as<double>(); v.h_max = b->h_max.as<double>(); v.last_reward = b->last_reward.as<double>();
+    return v;
+}
+
+extern "C" int enero_batch_create(enero_ctx* c, enero_topo* t, int B, double pct, enero_batch** out) {
+    if (!c || !t || !out || B < 1 || !(pct > 0)) return fail(ENERO_ERR_INVALID, "enero_batch_create: bad argument");
+    if (t->N < 3) return fail(ENERO_ERR_INVALID, "enero_batch_create: need N >= 3 (the finished episode's dummy demand is (1,2))");
+    TRY(enero_topo_upload(c, t));
+    CUDA_TRY(cudaSetDevice(c->device));
+    auto* b = new enero_batch();
+    b->c = c; b->t = t; b->B = B; b->pct = pct; b->NN = t->N * t->N;
+    b->Dmax = (int)std::ceil((double)(t->N * (t->N - 1)) * pct);       // environment16.py:199
+    const size_t BB = (size_t)B, D = (size_t)b->Dmax, NN = (size_t)b->NN, E = (size_t)t->E, K = (size_t)t->Kmax;
+    int r = ENERO_OK;
+    auto A = [&](DevBuf& buf, size_t bytes) { if (r == ENERO_OK) r = buf.ensure(std::max<size_t>(bytes, 16)); };
+    A(b->tm, BB * NN * 8); A(b->loads, BB * E * 8); A(b->mid_cur, BB * NN * 4); A(b->elig, BB * D * 4); A(b->elig_len, BB * 4);
+    A(b->it, BB * 4); A(b->cur, BB * 8); A(b->cur_bw, BB * 8); A(b->done, BB); A(b->steps, BB * 4); A(b->max_uti, BB * 8);
+    A(b->max_edge, BB * 4); A(b->best, BB * 8); A(b->best_step, BB * 4); A(b->ospf, BB * 8); A(b->h_action, BB * D * 4);
+    A(b->h_reward, BB * D * 8); A(b->h_max, BB * D * 8); A(b->last_reward, BB * 8); A(b->logits, BB * K * 4);
+    A(b->probs, BB * K * 4); A(b->nK, BB * 4); A(b->action, BB * 4); A(b->values, BB * 4);
+    A(b->ls_loads, BB * E * 8); A(b->ls_mid, BB * NN * 4); A(b->ls_val, BB * 8); A(b->ls_nmoves, BB * 4); A(b->ls_max_edge, BB * 4);
+    if (r != ENERO_OK) { delete b; return r; }
+    *out = b;
+    return ENERO_OK;
+}
+
+extern "C" int enero_batch_destroy(enero_batch* b) {
+    if (!b) return ENERO_OK;
+    cudaSetDevice(b->c->device);
+    cudaStreamSynchronize(b->c->stream);
+    for (DevBuf* x : {&b->tm, &b->loads, &b->mid_cur, &b->elig, &b->elig_len, &b->it, &b->cur, &b->cur_bw, &b->done, &b->steps,
+                      &b->max_uti, &b->max_edge, &b->best, &b->best_step, &b->ospf, &b->h_action, &b->h_reward, &b->h_max,
+                      &b->last_reward, &b->logits, &b->probs, &b->nK, &b->action, &b->values, &b->ls_loads, &b->ls_mid,
+                      &b->ls_elig, &b->ls_elig_len, &b->ls_val, &b->ls_nmoves, &b->ls_moves, &b->ls_move_val, &b->ls_max_edge})
+        x->release();
+    delete b;
+    return ENERO_OK;
+}
+
+extern "C" int enero_batch_dmax(enero_batch* b) { return b ? b->Dmax : -1; }
+
+extern "C" int enero_batch_reset(enero_batch* b, const double* tms) {
+    if (!b || !tms) return fail(ENERO_ERR_INVALID, "enero_batch_reset: null argument");
+    enero_ctx* c = b->c; enero_topo* t = b->t;
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const int B = b->B, E = t->E, NN = b->NN, D = b->Dmax;
+    CUDA_TRY(cudaMemcpyAsync(b->tm.p, tms, (size_t)B * NN * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(b->mid_cur.p, 0xFF, (size_t)B * NN * 4, st));
+    TopoView tv = view_of(t);
+    k_route_loads<<<B, 256, (size_t)E * 8, st>>>(tv, b->tm.as<double>(), nullptr, b->loads.as<double>(), b->max_uti.as<double>(), b->max_edge.as<int>());
+    LAUNCH_CHECK(c);
+    std::vector<double> loads((size_t)B * E);
+    CUDA_TRY(cudaMemcpyAsync(loads.data(), b->loads.p, loads.size() * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    b->h_elig.assign((size_t)B * D, 0); b->h_elig_len.assign(B, 0);
+    std::vector<int> sel;
+    b->max_len = 0;
+    for (int i = 0; i < B; ++i) {
+        topo_critical_demands(*t, loads.data() + (size_t)i * E, tms + (size_t)i * NN, nullptr, 0, b->pct, sel);
+        if (sel.empty()) return fail(ENERO_ERR_INVALID, "enero_batch_reset: traffic matrix yields no eligible demand");
+        std::copy(sel.begin(), sel.end(), b->h_elig.begin() + (size_t)i * D);
+        b->h_elig_len[i] = (int)sel.size();
+        b->max_len = std::max(b->max_len, (int)sel.size());
+    }
+    CUDA_TRY(cudaMemcpyAsync(b->elig.p, b->h_elig.data(), b->h_elig.size() * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(b->elig_len.p, b->h_elig_len.data(), (size_t)B * 4, cudaMemcpyHostToDevice, st));
+    k_episode_begin<<<(B + 3) / 4, 128, 0, st>>>(tv, ep_view(b)); LAUNCH_CHECK(c);
+    CUDA_TRY(cudaStreamSynchronize(st));
+    b->reset_done = true; b->policy_valid = false;
+    return ENERO_OK;
+}
+
+extern "C" int enero_batch_policy(enero_batch* b, float* probs_host, int32_t* nK_host) {
+    if (!b) return fail(ENERO_ERR_INVALID, "enero_batch_policy: null batch");
+    if (!b->reset_done) return fail(ENERO_ERR_STATE, "enero_batch_policy: reset first");
+    enero_ctx* c = b->c;
+    CUDA_TRY(cudaSetDevice(c->device));
+    TRY(decide_dev(c, b->t, b->B, b->loads.as<double>(), b->cur.as<int>(), b->cur_bw.as<double>(), b->done.as<uint8_t>(),
+                   b->logits.as<float>(), b->probs.as<float>(), b->nK.as<int>(), b->action.as<int>(), 5));
+    b->policy_valid = true;
+    if (probs_host) CUDA_TRY(cudaMemcpyAsync(probs_host, b->probs.p, (size_t)b->B * b->t->Kmax * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (nK_host) CUDA_TRY(cudaMemcpyAsync(nK_host, b->nK.p, (size_t)b->B * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (probs_host || nK_host) CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return ENERO_OK;
+}
+
+extern "C" int enero_batch_value(enero_batch* b, float* values_host) {
+    if (!b || !values_host) return fail(ENERO_ERR_INVALID, "enero_batch_value: null argument");
+    if (!b->reset_done) return fail(ENERO_ERR_STATE, "enero_batch_value: reset first");
+    enero_ctx* c = b->c;
+    CUDA_TRY(cudaSetDevice(c->device));
+    TRY(value_dev(c, b->t, b->B, b->loads.as<double>(), b->values.as<float>(), 5));
+    CUDA_TRY(cudaMemcpyAsync(values_host, b->values.p, (size_t)b->B * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return ENERO_OK;
+}
+
+static int step_dev(enero_batch* b) {
+    enero_ctx* c = b->c;
+    k_env_step<<<(b->B + 3) / 4, 128, 0, c->stream>>>(view_of(b->t), ep_view(b), b->action.as<int>());
+    LAUNCH_CHECK(c);
+    b->policy_valid = false;
+    return ENERO_OK;
+}
+
+extern "C" int enero_batch_step(enero_batch* b, const int32_t* actions, double* reward, uint8_t* done) {
+    if (!b) return fail(ENERO_ERR_INVALID, "enero_batch_step: null batch");
+    if (!b->reset_done) return fail(ENERO_ERR_STATE, "enero_batch_step: reset first");
+    enero_ctx* c = b->c;
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (actions) {
+        // validate against the candidate counts of the current demands (host mirror not kept: check on device data)
+        std::vector<int> cur((size_t)b->B * 2); std::vector<uint8_t> dn(b->B);
+        CUDA_TRY(cudaMemcpyAsync(cur.data(), b->cur.p, cur.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(dn.data(), b->done.p, dn.size(), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        for (int i = 0; i < b->B; ++i) {
+            if (dn[i]) continue;
+            const int sdi = cur[2 * i] * b->t->N + cur[2 * i + 1];
+            const int k = b->t->mid_off[sdi + 1] - b->t->mid_off[sdi];
+            if (actions[i] < 0 || actions[i] >= k) return fail(ENERO_ERR_INVALID, "enero_batch_step: action out of range");
+        }
+        CUDA_TRY(cudaMemcpyAsync(b->action.p, actions, (size_t)b->B * 4, cudaMemcpyHostToDevice, c->stream));
+    } else if (!b->policy_valid) {
+        return fail(ENERO_ERR_STATE, "enero_batch_step: greedy step needs enero_batch_policy first");
+    }
+    TRY(step_dev(b));
+    if (reward) CUDA_TRY(cudaMemcpyAsync(reward, b->last_reward.p, (size_t)b->B * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (done) CUDA_TRY(cudaMemcpyAsync(done, b->done.p, (size_t)b->B, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return ENERO_OK;
+}
+
+extern "C" int enero_batch_run_greedy(enero_batch* b) {
+    if (!b) return fail(ENERO_ERR_INVALID, "enero_batch_run_greedy: null batch");
+    if (!b->reset_done) return fail(ENERO_ERR_STATE, "enero_batch_run_greedy: reset first");
+    enero_ctx* c = b->c;
+    CUDA_TRY(cudaSetDevice(c->device));
+    for (int s = 0; s < b->max_len; ++s) {
+        TRY(decide_dev(c, b->t, b->B, b->loads.as<double>(), b->cur.as<int>(), b->cur_bw.as<double>(), b->done.as<uint8_t>(),
+                       b->logits.as<float>(), b->probs.as<float>(), b->nK.as<int>(), b->action.as<int>(), 5));
+        TRY(step_dev(b));
+    }
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return ENERO_OK;
+}
+
+extern "C" int enero_batch_get_state(enero_batch* b, double* loads, int32_t* cur, double* bw, double* max_uti,
+                                     int32_t* max_edge, uint8_t* done, int32_t* steps) {
+    if (!b) return fail(ENERO_ERR_INVALID, "enero_batch_get_state: null batch");
+    enero_ctx* c = b->c;
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const size_t B = b->B;
+    if (loads) CUDA_TRY(cudaMemcpyAsync(loads, b->loads.p, B * b->t->E * 8, cudaMemcpyDeviceToHost, st));
+    if (cur) CUDA_TRY(cudaMemcpyAsync(cur, b->cur.p, B * 8, cudaMemcpyDeviceToHost, st));
+    if (bw) CUDA_TRY(cudaMemcpyAsync(bw, b->cur_bw.p, B * 8, cudaMemcpyDeviceToHost, st));
+    if (max_uti) CUDA_TRY(cudaMemcpyAsync(max_uti, b->max_uti.p, B * 8, cudaMemcpyDeviceToHost, st));
+    if (max_edge) CUDA_TRY(cudaMemcpyAsync(max_edge, b->max_edge.p, B * 4, cudaMemcpyDeviceToHost, st));
+    if (done) CUDA_TRY(cudaMemcpyAsync(done, b->done.p, B, cudaMemcpyDeviceToHost, st));
+    if (steps) CUDA_TRY(cudaMemcpyAsync(steps, b->steps.p, B * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return ENERO_OK;
+}
+
+extern "C" int enero_batch_get_eligible(enero_batch* b, int32_t* elig, int32_t* elig_len) {
+    if (!b || !elig || !elig_len) return fail(ENERO_ERR_INVALID, "enero_batch_get_eligible: null argument");
+    const int N = b->t->N;
+    for (int i = 0; i < b->B; ++i) {
+        elig_len[i] = b->h_elig_len[i];
+        for (int k = 0; k < b->Dmax; ++k) {
+            const int sdi = k < b->h_elig_len[i] ? b->h_elig[(size_t)i * b->Dmax + k] : 0;
+            elig[((size_t)i * b->Dmax + k) * 2] = sdi / N;
+            elig[((size_t)i * b->Dmax + k) * 2 + 1] = sdi % N;
+        }
+    }
+    return ENERO_OK;
+}
+
+extern "C" int enero_batch_get_history(enero_batch* b, int32_t* action, double* reward, double* max_uti) {
+    if (!b) return fail(ENERO_ERR_INVALID, "enero_batch_get_history: null batch");
+    enero_ctx* c = b->c;
+    CUDA_TRY(cudaSetDevice(c->device));
+    const size_t n = (size_t)b->B * b->Dmax;
+    if (action) CUDA_TRY(cudaMemcpyAsync(action, b->h_action.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (reward) CUDA_TRY(cudaMemcpyAsync(reward, b->h_reward.p, n * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (max_uti) CUDA_TRY(cudaMemcpyAsync(max_uti, b->h_max.p, n * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return ENERO_OK;
+}
+
+// routing snapshot of the best step, in sp_middlepoints insertion order (script :181-184)
+static int best_routing_host(enero_batch* b, std::vector<double>& best, std::vector<double>& ospf,
+                             std::vector<int>& routing, std::vector<int>& nr) {
+    enero_ctx* c = b->c; enero_topo* t = b->t;
+    const int B = b->B, D = b->Dmax, N = t->N;
+    std::vector<int> bstep(B), act((size_t)B * D);
+    best.resize(B); ospf.resize(B);
+    CUDA_TRY(cudaMemcpyAsync(best.data(), b->best.p, (size_t)B * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(ospf.data(), b->ospf.p, (size_t)B * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(bstep.data(), b->best_step.p, (size_t)B * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(act.data(), b->h_action.p, act.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    routing.assign((size_t)B * D * 3, 0); nr.assign(B, 0);
+    for (int i = 0; i < B; ++i) {
+        int n = 0;
+        for (int s = 0; s <= bstep[i]; ++s) {
+            const int sdi = b->h_elig[(size_t)i * D + s];
+            const int src = sdi / N, dst = sdi % N;
+            const int mid = t->mids[t->mid_off[sdi] + act[(size_t)i * D + s]];
+            if (mid == dst) continue;
+            // the last step() de-allocates the dummy demand (1,2) and drops its entry before the copy
+            if (bstep[i] == b->h_elig_len[i] - 1 && src == 1 && dst == 2) continue;
+            int* r = &routing[((size_t)i * D + n) * 3];
+            r[0] = src; r[1] = dst; r[2] = mid; ++n;
+        }
+        nr[i] = n;
+    }
+    return ENERO_OK;
+}
+
+extern "C" int enero_batch_get_best(enero_batch* b, double* best, double* ospf, int32_t* routing, int32_t* n_routing) {
+    if (!b) return fail(ENERO_ERR_INVALID, "enero_batch_get_best: null batch");
+    CUDA_TRY(cudaSetDevice(b->c->device));
+    std::vector<double> vb, vo; std::vector<int> r, n;
+    TRY(best_routing_host(b, vb, vo, r, n));
+    if (best) std::copy(vb.begin(), vb.end(), best);
+    if (ospf) std::copy(vo.begin(), vo.end(), ospf);
+    if (routing) std::copy(r.begin(), r.end(), routing);
+    if (n_routing) std::copy(n.begin(), n.end(), n_routing);
+    return ENERO_OK;
+}
+
+// ---- Local Search ----------------------------------------------------------------------------------
+extern "C" int enero_batch_local_search(enero_batch* b, int mode, const int32_t* routing, const int32_t* n_routing,
+                                        int max_moves, double* start, double* final_val, int32_t* n_moves,
+                                        int32_t* moves, double* move_val) {
+    if (!b) return fail(ENERO_ERR_INVALID, "enero_batch_local_search: null batch");
+    if (mode < 0 || mode > 1 || max_moves < 1) return fail(ENERO_ERR_INVALID, "enero_batch_local_search: bad mode / max_moves");
+    enero_ctx* c = b->c; enero_topo* t = b->t;
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const int B = b->B, E = t->E, NN = b->NN, N = t->N, D = b->Dmax;
+    std::vector<int> own_r, own_n; std::vector<double> tmpb, tmpo;
+    int rstride = D;
+    if (mode == 0 && !routing) {
+        if (!b->reset_done) return fail(ENERO_ERR_STATE, "enero_batch_local_search: no episode to take a routing from");
+        TRY(best_routing_host(b, tmpb, tmpo, own_r, own_n));
+        routing = own_r.data(); n_routing = own_n.data();
+    }
+    if (mode == 0 && !n_routing) return fail(ENERO_ERR_INVALID, "enero_batch_local_search: n_routing missing");
+    // sp_middlepoints of the routing
+    std::vector<int> mid((size_t)B * NN, -1);
+    if (mode == 0)
+        for (int i = 0; i < B; ++i)
+            for (int k = 0; k < n_routing[i]; ++k) {
+                const int* r = routing + ((size_t)i * rstride + k) * 3;
+                if (r[0] < 0 || r[0] >= N || r[1] < 0 || r[1] >= N || r[2] < 0 || r[2] >= N || r[0] == r[1])
+                    return fail(ENERO_ERR_INVALID, "enero_batch_local_search: bad routing entry");
+                if (r[2] != r[1]) mid[(size_t)i * NN + r[0] * N + r[1]] = r[2];
+            }
+    CUDA_TRY(cudaMemcpyAsync(b->ls_mid.p, mid.data(), mid.size() * 4, cudaMemcpyHostToDevice, st));
+    TopoView tv = view_of(t);
+    k_route_loads<<<B, 256, (size_t)E * 8, st>>>(tv, b->tm.as<double>(), b->ls_mid.as<int>(), b->ls_loads.as<double>(),
+                                                 b->ls_val.as<double>(), b->ls_max_edge.as<int>());
+    LAUNCH_CHECK(c);
+    const int cap = mode == 0 ? D : N * (N - 1);
+    b->ls_cap = cap;
+    b->h_ls_elig.assign((size_t)B * cap, 0); b->h_ls_elig_len.assign(B, 0);
+    if (mode == 0) {
+        std::vector<double> loads((size_t)B * E), tm((size_t)B * NN);
+        CUDA_TRY(cudaMemcpyAsync(loads.data(), b->ls_loads.p, loads.size() * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(tm.data(), b->tm.p, tm.size() * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        std::vector<int> sel;
+        for (int i = 0; i < B; ++i) {
+            topo_critical_demands(*t, loads.data() + (size_t)i * E, tm.data() + (size_t)i * NN,
+                                  routing + (size_t)i * rstride * 3, n_routing[i], b->pct, sel);
+            std::copy(sel.begin(), sel.end(), b->h_ls_elig.begin() + (size_t)i * cap);
+            b->h_ls_elig_len[i] = (int)sel.size();
+        }
+    } else {
+        for (int i = 0; i < B; ++i) {
+            int n = 0;
+            for (int s = 0; s < N; ++s) for (int d = 0; d < N; ++d) if (s != d) b->h_ls_elig[(size_t)i * cap + n++] = s * N + d;
+            b->h_ls_elig_len[i] = n;
+        }
+    }
+    TRY(b->ls_elig.ensure((size_t)B * cap * 4)); TRY(b->ls_elig_len.ensure((size_t)B * 4));
+    TRY(b->ls_moves.ensure((size_t)B * max_moves * 12)); TRY(b->ls_move_val.ensure((size_t)B * max_moves * 8));
+    CUDA_TRY(cudaMemcpyAsync(b->ls_elig.p, b->h_ls_elig.data(), b->h_ls_elig.size() * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(b->ls_elig_len.p, b->h_ls_elig_len.data(), (size_t)B * 4, cudaMemcpyHostToDevice, st));
+    if (start) CUDA_TRY(cudaMemcpyAsync(start, b->ls_val.p, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
+    LsView lv{B, cap, max_moves, b->tm.as<double>(), b->ls_loads.as<double>(), b->ls_mid.as<int>(), b->ls_elig.as<int>(),
+              b->ls_elig_len.as<int>(), b->ls_val.as<double>(), b->ls_nmoves.as<int>(), b->ls_moves.as<int>(), b->ls_move_val.as<double>()};
+    const int nw = LS_TPB / 32;
+    const size_t smem = (size_t)E * 16 + nw * 8 + nw * 4 + nw * 8 + (size_t)nw * E + 16;
+    if (smem > 200 * 1024) return fail(ENERO_ERR_INVALID, "enero_batch_local_search: topology too large for the shared-memory LS kernel");
+    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_local_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_local_search<<<B, LS_TPB, smem, st>>>(tv, lv); LAUNCH_CHECK(c);
+    if (final_val) CUDA_TRY(cudaMemcpyAsync(final_val, b->ls_val.p, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
+    if (n_moves) CUDA_TRY(cudaMemcpyAsync(n_moves, b->ls_nmoves.p, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+    if (moves) CUDA_TRY(cudaMemcpyAsync(moves, b->ls_moves.p, (size_t)B * max_moves * 12, cudaMemcpyDeviceToHost, st));
+    if (move_val) CUDA_TRY(cudaMemcpyAsync(move_val, b->ls_move_val.p, (size_t)B * max_moves * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return ENERO_OK;
+}
+
+extern "C" int enero_batch_get_ls_eligible(enero_batch* b, int32_t* elig, int32_t* elig_len, int cap) {
+    if (!b || !elig || !elig_len) return fail(ENERO_ERR_INVALID, "enero_batch_get_ls_eligible: null argument");
+    if (cap < b->ls_cap) return fail(ENERO_ERR_INVALID, "enero_batch_get_ls_eligible: cap too small");
+    const int N = b->t->N;
+    for (int i = 0; i < b->B; ++i) {
+        elig_len[i] = b->h_ls_elig_len[i];
+        for (int k = 0; k < b->h_ls_elig_len[i]; ++k) {
+            const int sdi = b->h_ls_elig[(size_t)i * b->ls_cap + k];
+            elig[((size_t)i * cap + k) * 2] = sdi / N;
+            elig[((size_t)i * cap + k) * 2 + 1] = sdi % N;
+        }
+    }
+    return ENERO_OK;
+}

@@ -1,0 +1,375 @@
+// Environment-side kernels: link loads from a routing, per-candidate link features,
+// the middlepoint env step, and the Local Search.  fp64 link loads are integer-valued
+// (demands are floored on ingest, defo_process_results.py:224) so sums are exact and
+// order-independent; every utilisation is a correctly-rounded fp64 division, i.e. the
+// very numbers the reference's Python produces.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "enero_internal.h"
+#include "gnn_kernels.cuh"
+
+namespace enero {
+
+struct TopoView {   // by-value kernel argument
+    int N, E, Kmax;
+    const double* cap; const float* capf;
+    const int* sp_off; const int* sp_edge; const int* mid_off; const int* mids;
+};
+
+// ---- per-decision prologue: candidate count + fp32 utilisation feature -----------------
+// utilization feature = fp32(load / capacity): fp64 divide then cast
+// (script_eval_on_single_topology.py:144).
+__global__ void k_decision_prep(TopoView t, int B, const double* __restrict__ loads, const int* __restrict__ sd,
+                                const uint8_t* __restrict__ skip, int* __restrict__ nK, float* __restrict__ util) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)B * t.E) return;
+    const int b = (int)(i / t.E), e = (int)(i - (int64_t)b * t.E);
+    util[i] = (float)(loads[i] / t.cap[e]);
+    if (e == 0) {
+        const int s = sd[2 * b], d = sd[2 * b + 1];
+        int k = 0;
+        if (!(skip && skip[b]) && s >= 0 && d >= 0 && s < t.N && d < t.N && s != d)
+            k = t.mid_off[s * t.N + d + 1] - t.mid_off[s * t.N + d];
+        nK[b] = k;
+    }
+}
+
+// ---- candidate features (kernel 6, feature half) ----------------------------------------
+// Row (b, k, e) of the batched link_state = [util, cap/maxCap, mark, 0 x 17]
+// (mark_action_sp, environment16.py:711-725: assignment bw/cap on every link of
+// path(s,mid) U path(mid,d); get_graph_features, script :131-160) and its first
+// message operand A_0 = h_0 . Wm[0:20].
+__global__ void __launch_bounds__(MP_TPB)
+k_features(TopoView t, int B, int RPD, const int* __restrict__ sd, const double* __restrict__ bw,
+           const int* __restrict__ nK, const float* __restrict__ util, const float* __restrict__ wflat,
+           float* __restrict__ h0, float* __restrict__ A0) {
+    __shared__ __align__(16) float sw[3 * H];
+    if (threadIdx.x < 3 * H) sw[threadIdx.x] = wflat[W_MSG_K + threadIdx.x];
+    __syncthreads();
+    const int64_t r = (int64_t)blockIdx.x * MP_TPB + threadIdx.x;
+    if (r >= (int64_t)B * RPD) return;
+    const int b = (int)(r / RPD);
+    const int lr = (int)(r - (int64_t)b * RPD);
+    if (lr >= nK[b] * t.E) return;
+    const int k = lr / t.E, e = lr - k * t.E;
+    const int s = sd[2 * b], d = sd[2 * b + 1];
+    const int mid = t.mids[t.mid_off[s * t.N + d] + k];
+    bool on = false;
+    for (int i = t.sp_off[s * t.N + mid]; i < t.sp_off[s * t.N + mid + 1]; ++i) on |= (t.sp_edge[i] == e);
+    if (mid != d)
+        for (int i = t.sp_off[mid * t.N + d]; i < t.sp_off[mid * t.N + d + 1]; ++i) on |= (t.sp_edge[i] == e);
+    float h[H];
+#pragma unroll
+    for (int j = 0; j < H; ++j) h[j] = 0.f;
+    h[0] = util[(int64_t)b * t.E + e];
+    h[1] = t.capf[e];
+    h[2] = on ? (float)(bw[b] / t.cap[e]) : 0.f;
+    store_row(h0 + r * H, h);
+    float a[H];
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+        float v = 0.f;
+        v = fmaf(h[0], sw[j], v);
+        v = fmaf(h[1], sw[H + j], v);
+        v = fmaf(h[2], sw[2 * H + j], v);
+        a[j] = v;
+    }
+    store_row(A0 + r * H, a);
+}
+
+// critic features: [util, cap/maxCap, 0 x 18] on one graph per state
+// (critic_get_graph_features, train_Enero_3top_script.py:204-230)
+__global__ void __launch_bounds__(MP_TPB)
+k_features_critic(TopoView t, int B, const float* __restrict__ util, const float* __restrict__ wflat,
+                  float* __restrict__ h0, float* __restrict__ A0) {
+    __shared__ __align__(16) float sw[2 * H];
+    if (threadIdx.x < 2 * H) sw[threadIdx.x] = wflat[W_MSG_K + threadIdx.x];
+    __syncthreads();
+    const int64_t r = (int64_t)blockIdx.x * MP_TPB + threadIdx.x;
+    if (r >= (int64_t)B * t.E) return;
+    const int e = (int)(r % t.E);
+    float h[H], a[H];
+#pragma unroll
+    for (int j = 0; j < H; ++j) h[j] = 0.f;
+    h[0] = util[r];
+    h[1] = t.capf[e];
+    store_row(h0 + r * H, h);
+#pragma unroll
+    for (int j = 0; j < H; ++j) a[j] = fmaf(h[1], sw[H + j], fmaf(h[0], sw[j], 0.f));
+    store_row(A0 + r * H, a);
+}
+
+// ---- warp helpers ------------------------------------------------------------------------
+// argmax of load/cap over links with the reference's scan semantics: start from (0,0,0),
+// strict '>', links in id order  ->  largest value, lowest id on ties, id -1 if nothing > 0
+// (environment16.py:604-612).
+__device__ __forceinline__ void warp_max_uti(const double* loads, const double* cap, int E, int lane,
+                                             double& best, int& best_e) {
+    best = 0.0; best_e = -1;
+    for (int e = lane; e < E; e += 32) {
+        const double u = loads[e] / cap[e];
+        if (u > best) { best = u; best_e = e; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oe = __shfl_xor_sync(0xffffffffu, best_e, o);
+        if (ob > best || (ob == best && oe >= 0 && (best_e < 0 || oe < best_e))) { best = ob; best_e = oe; }
+    }
+}
+
+// add sign*bw on every link of the shortest path a->b (links of one SP are distinct)
+__device__ __forceinline__ void warp_route_add(const TopoView& t, double* loads, int a, int b, double v, int lane) {
+    const int i0 = t.sp_off[a * t.N + b], i1 = t.sp_off[a * t.N + b + 1];
+    for (int i = i0 + lane; i < i1; i += 32) loads[t.sp_edge[i]] += v;
+    __syncwarp();
+}
+__device__ __forceinline__ void warp_demand_add(const TopoView& t, double* loads, int s, int d, int mid, double v, int lane) {
+    if (mid < 0 || mid == d) warp_route_add(t, loads, s, d, v, lane);
+    else { warp_route_add(t, loads, s, mid, v, lane); warp_route_add(t, loads, mid, d, v, lane); }
+}
+
+// ---- link loads of a routing (kernel 6, load half) -----------------------------------------
+// compute_link_utilization_reset (environment16.py:240-245) / reset_DRL_hill_sp
+// (environment15.py:504-518): one CTA per episode, loads accumulated in shared memory.
+// mid_cur[b][s*N+d] = middlepoint or -1 (direct shortest path).
+__global__ void __launch_bounds__(256)
+k_route_loads(TopoView t, const double* __restrict__ tm, const int* __restrict__ mid_cur,
+              double* __restrict__ loads, double* __restrict__ max_uti, int* __restrict__ max_edge) {
+    extern __shared__ double sl[];
+    const int b = blockIdx.x, NN = t.N * t.N;
+    for (int e = threadIdx.x; e < t.E; e += blockDim.x) sl[e] = 0.0;
+    __syncthreads();
+    for (int sdi = threadIdx.x; sdi < NN; sdi += blockDim.x) {
+        const int s = sdi / t.N, d = sdi - s * t.N;
+        if (s == d) continue;
+        const double v = tm[(int64_t)b * NN + sdi];
+        const int mid = mid_cur ? mid_cur[(int64_t)b * NN + sdi] : -1;
+        const int m1 = (mid < 0 || mid == d) ? d : mid;
+        for (int i = t.sp_off[s * t.N + m1]; i < t.sp_off[s * t.N + m1 + 1]; ++i) atomicAdd(&sl[t.sp_edge[i]], v);
+        if (m1 != d)
+            for (int i = t.sp_off[m1 * t.N + d]; i < t.sp_off[m1 * t.N + d + 1]; ++i) atomicAdd(&sl[t.sp_edge[i]], v);
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < t.E; e += blockDim.x) loads[(int64_t)b * t.E + e] = sl[e];
+    if (threadIdx.x < 32) {
+        double best; int be;
+        warp_max_uti(sl, t.cap, t.E, threadIdx.x, best, be);
+        if (threadIdx.x == 0) { max_uti[b] = best; max_edge[b] = be; }
+    }
+}
+
+// ---- episode state ------------------------------------------------------------------------
+struct EpisodeView {
+    int B, Dmax;
+    const double* tm;     // [B][N*N]
+    double* loads;        // [B][E]
+    int* mid_cur;         // [B][N*N]   sp_middlepoints (-1 = none)
+    const int* elig;      // [B][Dmax]  list_eligible_demands as s*N+d
+    const int* elig_len;  // [B]
+    int* it;              // [B] iter_list_elig_demn
+    int* cur;             // [B][2] current demand (s,d)
+    double* cur_bw;       // [B]
+    uint8_t* done;        // [B]
+    int* steps;           // [B] decisions taken
+    double* max_uti;      // [B] edgeMaxUti[2]
+    int* max_edge;        // [B]
+    double* best; int* best_step; double* ospf;      // [B]
+    int* h_action; double* h_reward; double* h_max;  // [B][Dmax]
+    double* last_reward;  // [B]
+};
+
+// first demand of the episode: _obtain_demand + decrease_links_utilization_sp
+// (environment16.py:682-688)
+__global__ void k_episode_begin(TopoView t, EpisodeView ep) {
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= ep.B) return;
+    const int NN = t.N * t.N;
+    const int sdi = ep.elig[(int64_t)b * ep.Dmax];
+    const int s = sdi / t.N, d = sdi - s * t.N;
+    const double v = ep.tm[(int64_t)b * NN + sdi];
+    warp_route_add(t, ep.loads + (int64_t)b * t.E, s, d, -v, lane);
+    if (lane == 0) {
+        ep.it[b] = 1; ep.cur[2 * b] = s; ep.cur[2 * b + 1] = d; ep.cur_bw[b] = v;
+        ep.done[b] = 0; ep.steps[b] = 0;
+        ep.best[b] = ep.max_uti[b]; ep.ospf[b] = ep.max_uti[b]; ep.best_step[b] = -1;
+    }
+}
+
+// Env16.step (environment16.py:582-640), one warp per episode.
+__global__ void __launch_bounds__(128)
+k_env_step(TopoView t, EpisodeView ep, const int* __restrict__ action) {
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= ep.B || ep.done[b]) return;
+    const int NN = t.N * t.N;
+    double* loads = ep.loads + (int64_t)b * t.E;
+    int* mid_cur = ep.mid_cur + (int64_t)b * NN;
+    const int s = ep.cur[2 * b], d = ep.cur[2 * b + 1];
+    const double bw = ep.cur_bw[b];
+    const int a = action[b];
+    const int mid = t.mids[t.mid_off[s * t.N + d] + a];
+    warp_demand_add(t, loads, s, d, mid, bw, lane);
+    if (mid != d && lane == 0) mid_cur[s * t.N + d] = mid;
+    __syncwarp();
+    double nu; int ne;
+    warp_max_uti(loads, t.cap, t.E, lane, nu, ne);
+    const double old = ep.max_uti[b];
+    const int step = ep.steps[b];
+    // np.around(x, 2) == rint(x * 100) / 100 in fp64
+    const double reward = rint((old - nu) * 10.0 * 100.0) / 100.0;
+    int it = ep.it[b];
+    int ns, nd; bool fin = false;
+    if (it < ep.elig_len[b]) {
+        const int sdi = ep.elig[(int64_t)b * ep.Dmax + it];
+        ns = sdi / t.N; nd = sdi - ns * t.N; ++it;
+    } else { ns = 1; nd = 2; fin = true; }       // dummy demand of the finished episode (:622-626)
+    const double nbw = ep.tm[(int64_t)b * NN + ns * t.N + nd];
+    const int m2 = mid_cur[ns * t.N + nd];
+    __syncwarp();
+    warp_demand_add(t, loads, ns, nd, m2, -nbw, lane);
+    if (lane == 0) {
+        // the snapshot the eval driver copies after step() no longer holds the next demand's entry
+        if (m2 >= 0) mid_cur[ns * t.N + nd] = -1;
+        ep.max_uti[b] = nu; ep.max_edge[b] = ne;
+        ep.h_action[(int64_t)b * ep.Dmax + step] = a;
+        ep.h_reward[(int64_t)b * ep.Dmax + step] = reward;
+        ep.h_max[(int64_t)b * ep.Dmax + step] = nu;
+        ep.last_reward[b] = reward;
+        if (nu < ep.best[b]) { ep.best[b] = nu; ep.best_step[b] = step; }
+        ep.it[b] = it; ep.cur[2 * b] = ns; ep.cur[2 * b + 1] = nd; ep.cur_bw[b] = nbw;
+        ep.steps[b] = step + 1; ep.done[b] = fin ? 1 : 0;
+    }
+}
+
+// ---- Local Search (kernel 7) -----------------------------------------------------------------
+// One CTA per episode runs the whole hill climbing of play_DRL_GNN_sp_hill_climbing_games
+// (script_eval_on_single_topology.py:482-509) on device: every (demand, middlepoint) move of
+// explore_neighbourhood_DRL_sp (:395-435) is evaluated by one warp against the current loads
+// (get_value_sp, :317-351) with a warp-level fp64 max-reduction; the CTA keeps the first
+// strictly best move in (demand, action) order, applies it (step_hill_sp, environment15.py:
+// 378-404) and repeats until the reference's stop rule.
+struct LsView {
+    int B, Dcap, max_moves;
+    const double* tm; double* loads; int* mid_cur;
+    const int* elig; const int* elig_len;          // [B][Dcap] frozen demand list
+    double* cur_val;                               // [B] in: max uti at reset; out: final
+    int* n_moves; int* moves; double* move_val;    // [B], [B][max_moves][3], [B][max_moves]
+};
+
+constexpr int LS_TPB = 256;
+
+__global__ void __launch_bounds__(LS_TPB)
+k_local_search(TopoView t, LsView ls) {
+    extern __shared__ double smem[];
+    double* sl = smem;                                   // [E] loads
+    double* scap = sl + t.E;                             // [E]
+    double* wbest = scap + t.E;                          // [nwarps]
+    int* wbest_i = reinterpret_cast<int*>(wbest + LS_TPB / 32);   // [nwarps] move order key
+    int* wbest_m = wbest_i + LS_TPB / 32;                // [nwarps][2] (demand idx, action)
+    signed char* cnt = reinterpret_cast<signed char*>(wbest_m + 2 * (LS_TPB / 32));   // [nwarps][E]
+    __shared__ double s_cur; __shared__ int s_stop; __shared__ int s_bd, s_ba;
+
+    const int b = blockIdx.x, NN = t.N * t.N;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = LS_TPB / 32;
+    const double* tm = ls.tm + (int64_t)b * NN;
+    int* mid_cur = ls.mid_cur + (int64_t)b * NN;
+    const int* elig = ls.elig + (int64_t)b * ls.Dcap;
+    const int nd = ls.elig_len[b];
+    for (int e = threadIdx.x; e < t.E; e += LS_TPB) { sl[e] = ls.loads[(int64_t)b * t.E + e]; scap[e] = t.cap[e]; }
+    signed char* mycnt = cnt + wid * t.E;
+    for (int e = lane; e < t.E; e += 32) mycnt[e] = 0;
+    if (threadIdx.x == 0) { s_cur = ls.cur_val[b]; s_stop = 0; }
+    int nmoves = 0;
+    __syncthreads();
+
+    while (true) {
+        // ---- explore the neighbourhood
+        double best = 1e300; int best_key = 0x7fffffff, best_d = -1, best_a = -1;
+        for (int di = wid; di < nd; di += nw) {
+            const int sdi = elig[di];
+            const int s = sdi / t.N, d = sdi - s * t.N;
+            const double bw = tm[sdi];
+            const int m0 = mid_cur[sdi];
+            const int k0 = t.mid_off[sdi], k1 = t.mid_off[sdi + 1];
+            // visit counts of the current route, negated (de-allocation, :404-416)
+            {
+                const int a0 = (m0 < 0 || m0 == d) ? d : m0;
+                for (int i = t.sp_off[s * t.N + a0] + lane; i < t.sp_off[s * t.N + a0 + 1]; i += 32) mycnt[t.sp_edge[i]] -= 1;
+                __syncwarp();
+                if (a0 != d) { for (int i = t.sp_off[a0 * t.N + d] + lane; i < t.sp_off[a0 * t.N + d + 1]; i += 32) mycnt[t.sp_edge[i]] -= 1; __syncwarp(); }
+            }
+            for (int a = 0; a < k1 - k0; ++a) {
+                const int m1 = t.mids[k0 + a];
+                for (int i = t.sp_off[s * t.N + m1] + lane; i < t.sp_off[s * t.N + m1 + 1]; i += 32) mycnt[t.sp_edge[i]] += 1;
+                __syncwarp();
+                if (m1 != d) { for (int i = t.sp_off[m1 * t.N + d] + lane; i < t.sp_off[m1 * t.N + d + 1]; i += 32) mycnt[t.sp_edge[i]] += 1; __syncwarp(); }
+                double mx = -1000000.0;
+                for (int e = lane; e < t.E; e += 32) {
+                    const double u = (sl[e] + bw * (double)mycnt[e]) / scap[e];
+                    mx = fmax(mx, u);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                // evalState = -mx ; "if evalState > nextVal" keeps the first strictly better move
+                const int key = di * t.Kmax + a;
+                if (mx < best || (mx == best && key < best_key)) { best = mx; best_key = key; best_d = di; best_a = a; }
+                __syncwarp();
+                for (int i = t.sp_off[s * t.N + m1] + lane; i < t.sp_off[s * t.N + m1 + 1]; i += 32) mycnt[t.sp_edge[i]] -= 1;
+                __syncwarp();
+                if (m1 != d) { for (int i = t.sp_off[m1 * t.N + d] + lane; i < t.sp_off[m1 * t.N + d + 1]; i += 32) mycnt[t.sp_edge[i]] -= 1; __syncwarp(); }
+            }
+            {
+                const int a0 = (m0 < 0 || m0 == d) ? d : m0;
+                for (int i = t.sp_off[s * t.N + a0] + lane; i < t.sp_off[s * t.N + a0 + 1]; i += 32) mycnt[t.sp_edge[i]] += 1;
+                __syncwarp();
+                if (a0 != d) { for (int i = t.sp_off[a0 * t.N + d] + lane; i < t.sp_off[a0 * t.N + d + 1]; i += 32) mycnt[t.sp_edge[i]] += 1; __syncwarp(); }
+            }
+        }
+        if (lane == 0) { wbest[wid] = best; wbest_i[wid] = best_key; wbest_m[2 * wid] = best_d; wbest_m[2 * wid + 1] = best_a; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double bb = 1e300; int bk = 0x7fffffff, bd = -1, ba = -1;
+            for (int w = 0; w < nw; ++w)
+                if (wbest[w] < bb || (wbest[w] == bb && wbest_i[w] < bk)) { bb = wbest[w]; bk = wbest_i[w]; bd = wbest_m[2 * w]; ba = wbest_m[2 * w + 1]; }
+            // nextVal = -bb (or -1000000 with no move), currentVal = -s_cur (script :483-486)
+            const double nextVal = bd >= 0 ? -bb : -1000000.0;
+            const double currentVal = -s_cur;
+            const bool stop = (nextVal <= currentVal) || (fabs((-1.0) * nextVal - (-1.0) * currentVal) < 1e-4) ||
+                              nmoves >= ls.max_moves;
+            s_stop = stop ? 1 : 0; s_bd = bd; s_ba = ba;
+        }
+        __syncthreads();
+        if (s_stop) break;
+        // ---- apply the move: de-allocate (:494-502) + step_hill_sp
+        if (wid == 0) {
+            const int sdi = elig[s_bd];
+            const int s = sdi / t.N, d = sdi - s * t.N;
+            const double bw = tm[sdi];
+            const int m0 = mid_cur[sdi];
+            const int m1 = t.mids[t.mid_off[sdi] + s_ba];
+            warp_demand_add(t, sl, s, d, m0, -bw, lane);
+            warp_demand_add(t, sl, s, d, m1, bw, lane);
+            double nu; int ne;
+            warp_max_uti(sl, scap, t.E, lane, nu, ne);
+            if (lane == 0) {
+                mid_cur[sdi] = (m1 != d) ? m1 : -1;
+                s_cur = nu;
+                if (ls.moves) {
+                    int* mv = ls.moves + ((int64_t)b * ls.max_moves + nmoves) * 3;
+                    mv[0] = s_ba; mv[1] = s; mv[2] = d;
+                    ls.move_val[(int64_t)b * ls.max_moves + nmoves] = nu;
+                }
+            }
+        }
+        ++nmoves;
+        __syncthreads();
+    }
+    for (int e = threadIdx.x; e < t.E; e += LS_TPB) ls.loads[(int64_t)b * t.E + e] = sl[e];
+    if (threadIdx.x == 0) { ls.cur_val[b] = s_cur; ls.n_moves[b] = nmoves; }
+}
+
+}  // namespace enero

@@ -1,0 +1,153 @@
+"""Device-resident batch of ENERO episodes (GraphEnv-v16 semantics for B traffic
+matrices of one topology) and the two-stage optimiser built on it:
+
+    DRL stage   play_middRout_games_sp            script_eval_on_single_topology.py:162-188
+    LS stage    play_DRL_GNN_sp_hill_climbing_games                        ... :473-509
+
+Everything numeric runs in libenero_b200.so on the GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .runtime import Context
+from .topology import Topology
+
+
+class EpisodeBatch:
+    def __init__(self, ctx: Context, topo: Topology, batch: int, percentage_demands: float = 0.15):
+        self.ctx, self.topo, self.B = ctx, topo, int(batch)
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        _lib.check(self._lib.enero_batch_create(ctx.handle, topo.handle, self.B, float(percentage_demands), C.byref(h)))
+        self._h = h
+        self.Dmax = int(self._lib.enero_batch_dmax(h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.enero_batch_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- Env16 -----------------------------------------------------------------------------
+    def reset(self, tms):
+        """tms: fp64 [B,N,N] (floored demands). Returns (bw[B], sd[B,2]) of the first demands."""
+        tms = np.ascontiguousarray(tms, dtype=np.float64)
+        if tms.shape != (self.B, self.topo.N, self.topo.N):
+            raise ValueError("tms must be [B,N,N]")
+        _lib.check(self._lib.enero_batch_reset(self._h, _lib.ptr(tms)))
+        st = self.state()
+        return st["bw"], st["cur"]
+
+    def policy(self, want_probs: bool = True):
+        probs = np.zeros((self.B, self.topo.Kmax), dtype=np.float32) if want_probs else None
+        nK = np.zeros(self.B, dtype=np.int32) if want_probs else None
+        _lib.check(self._lib.enero_batch_policy(self._h, _lib.ptr(probs), _lib.ptr(nK)))
+        return probs, nK
+
+    def value(self) -> np.ndarray:
+        v = np.zeros(self.B, dtype=np.float32)
+        _lib.check(self._lib.enero_batch_value(self._h, _lib.ptr(v)))
+        return v
+
+    def step(self, actions=None):
+        """actions None = greedy argmax of the last policy(). -> (reward[B], done[B])."""
+        a = None if actions is None else np.ascontiguousarray(actions, dtype=np.int32).reshape(-1)
+        if a is not None and a.size != self.B:
+            raise ValueError("need one action per episode")
+        reward = np.zeros(self.B, dtype=np.float64)
+        done = np.zeros(self.B, dtype=np.uint8)
+        _lib.check(self._lib.enero_batch_step(self._h, _lib.ptr(a), _lib.ptr(reward), _lib.ptr(done)))
+        return reward, done.astype(bool)
+
+    def run_greedy(self):
+        _lib.check(self._lib.enero_batch_run_greedy(self._h))
+
+    def state(self) -> dict:
+        B, E = self.B, self.topo.E
+        out = {"loads": np.zeros((B, E)), "cur": np.zeros((B, 2), dtype=np.int32), "bw": np.zeros(B),
+               "max_uti": np.zeros(B), "max_edge": np.zeros(B, dtype=np.int32),
+               "done": np.zeros(B, dtype=np.uint8), "steps": np.zeros(B, dtype=np.int32)}
+        _lib.check(self._lib.enero_batch_get_state(self._h, *[_lib.ptr(out[k]) for k in
+                                                   ("loads", "cur", "bw", "max_uti", "max_edge", "done", "steps")]))
+        return out
+
+    def eligible(self):
+        elig = np.zeros((self.B, self.Dmax, 2), dtype=np.int32)
+        n = np.zeros(self.B, dtype=np.int32)
+        _lib.check(self._lib.enero_batch_get_eligible(self._h, _lib.ptr(elig), _lib.ptr(n)))
+        return elig, n
+
+    def history(self):
+        a = np.zeros((self.B, self.Dmax), dtype=np.int32)
+        r = np.zeros((self.B, self.Dmax))
+        m = np.zeros((self.B, self.Dmax))
+        _lib.check(self._lib.enero_batch_get_history(self._h, _lib.ptr(a), _lib.ptr(r), _lib.ptr(m)))
+        return a, r, m
+
+    def best(self):
+        """-> (best max-uti[B], ospf[B], routing list per episode [(s,d,mid), ...])."""
+        best = np.zeros(self.B)
+        ospf = np.zeros(self.B)
+        routing = np.zeros((self.B, self.Dmax, 3), dtype=np.int32)
+        n = np.zeros(self.B, dtype=np.int32)
+        _lib.check(self._lib.enero_batch_get_best(self._h, _lib.ptr(best), _lib.ptr(ospf), _lib.ptr(routing), _lib.ptr(n)))
+        return best, ospf, [[tuple(int(v) for v in routing[b, k]) for k in range(n[b])] for b in range(self.B)]
+
+    # ---- Env15 + HILL_CLIMBING ----------------------------------------------------------------
+    def local_search(self, routing=None, mode: int = 0, max_moves: int = 4096, want_moves: bool = True):
+        """routing: per-episode list of (s,d,mid) in insertion order, or None for the batch's own
+        best DRL routing.  -> dict(start, final, n_moves, moves, move_val)."""
+        B = self.B
+        r_arr = n_arr = None
+        if routing is not None:
+            r_arr = np.zeros((B, self.Dmax, 3), dtype=np.int32)
+            n_arr = np.zeros(B, dtype=np.int32)
+            for b, lst in enumerate(routing):
+                if len(lst) > self.Dmax:
+                    raise ValueError("routing longer than the demand budget")
+                n_arr[b] = len(lst)
+                for k, e in enumerate(lst):
+                    r_arr[b, k] = e
+        start = np.zeros(B)
+        final = np.zeros(B)
+        n_moves = np.zeros(B, dtype=np.int32)
+        moves = np.zeros((B, max_moves, 3), dtype=np.int32) if want_moves else None
+        vals = np.zeros((B, max_moves)) if want_moves else None
+        _lib.check(self._lib.enero_batch_local_search(self._h, int(mode), _lib.ptr(r_arr), _lib.ptr(n_arr), int(max_moves),
+                                                      _lib.ptr(start), _lib.ptr(final), _lib.ptr(n_moves),
+                                                      _lib.ptr(moves), _lib.ptr(vals)))
+        return {"start": start, "final": final, "n_moves": n_moves, "moves": moves, "move_val": vals}
+
+    def ls_eligible(self):
+        cap = max(self.Dmax, self.topo.N * (self.topo.N - 1))
+        elig = np.zeros((self.B, cap, 2), dtype=np.int32)
+        n = np.zeros(self.B, dtype=np.int32)
+        _lib.check(self._lib.enero_batch_get_ls_eligible(self._h, _lib.ptr(elig), _lib.ptr(n), cap))
+        return elig, n
+
+
+def run_enero(ctx: Context, topo: Topology, tms, percentage_demands: float = 0.15, local_search: bool = True):
+    """Full Enero inference (greedy DRL + Local Search) for a batch of traffic matrices."""
+    tms = np.ascontiguousarray(tms, dtype=np.float64)
+    eb = EpisodeBatch(ctx, topo, tms.shape[0], percentage_demands)
+    try:
+        eb.reset(tms)
+        eb.run_greedy()
+        best, ospf, routing = eb.best()
+        out = {"ospf": ospf, "drl": best, "routing": routing, "decisions": eb.state()["steps"]}
+        if local_search:
+            ls = eb.local_search(None, mode=0, want_moves=False)
+            out["enero"] = ls["final"]
+            out["ls_moves"] = ls["n_moves"]
+        return out
+    finally:
+        eb.close()

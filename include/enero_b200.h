@@ -1,0 +1,160 @@
+/*
+ * enero_b200 -- C ABI of the B200-native ENERO hot path.
+ *
+ * The reference (BNN-UPC/ENERO) has no FFI: its boundary is two Python class
+ * contracts (actor/critic `myModel`, gym-graph `Env16`/`Env15`) plus file formats
+ * (SURVEY.md section 8b).  This header is the flat C surface the Python shims in
+ * enero_b200/ bind with ctypes; each entry point cites the reference code it
+ * replaces (paths relative to the reference tree).
+ *
+ * Conventions: every function returns 0 on success and a negative code on error,
+ * with a message available from enero_last_error() (thread-local).  No exceptions
+ * cross the boundary.  The caller owns every buffer it passes; the library owns
+ * handles until the matching *_destroy.  One ctx per (process, device); a ctx is
+ * thread-compatible, not thread-safe.  Pointers named *_host are host memory,
+ * *_dev are device memory on the ctx's device; `ptr_kind` selects per call
+ * (ENERO_HOST = 0, ENERO_DEVICE = 1) where both are accepted.
+ */
+#ifndef ENERO_B200_H_
+#define ENERO_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ENERO_OK 0
+#define ENERO_ERR_INVALID -1
+#define ENERO_ERR_CUDA -2
+#define ENERO_ERR_STATE -3
+
+#define ENERO_HOST 0
+#define ENERO_DEVICE 1
+
+#define ENERO_ACTOR 0
+#define ENERO_CRITIC 1
+
+#define ENERO_H 20            /* link_state_dim  (train_Enero_3top_script.py:83) */
+#define ENERO_NPARAMS 4201    /* parameters per model, Keras variable order (:238-248) */
+
+typedef struct enero_ctx enero_ctx;
+typedef struct enero_topo enero_topo;
+typedef struct enero_batch enero_batch;
+
+/* ---- library ------------------------------------------------------------ */
+const char* enero_last_error(void);
+int enero_version(void);
+int enero_device_count(void);
+
+/* ---- context -------------------------------------------------------------- */
+int enero_ctx_create(int device, enero_ctx** out);
+int enero_ctx_destroy(enero_ctx* ctx);
+int enero_ctx_sync(enero_ctx* ctx);
+/* kernels launched by this ctx since creation (bench.py's gpu_launches) */
+int64_t enero_ctx_launch_count(enero_ctx* ctx);
+/* raw cudaStream_t the ctx launches on (for CUDA-event timing by the caller) */
+void* enero_ctx_stream(enero_ctx* ctx);
+
+/* ---- weights ---------------------------------------------------------------
+ * Flat fp32[4201] in Keras variable order: FirstLayer/kernel[40,20], bias[20],
+ * gru/kernel[20,60], recurrent_kernel[20,60], bias[2,60], Readout1/kernel[20,20],
+ * bias[20], Readout2/kernel[20,20], bias[20], Readout3/kernel[20,1], bias[1]
+ * (actorPPOmiddR.py:12-39; criticPPO.py:12-35).  `which` = ENERO_ACTOR / ENERO_CRITIC. */
+int enero_weights_upload(enero_ctx* ctx, int which, const float* flat_host);
+int enero_weights_download(enero_ctx* ctx, int which, float* flat_host);
+
+/* ---- topology (host precompute; no GPU needed until enero_topo_upload) -------
+ * Replaces Env16.generate_environment: edge ids (environment16.py:557-569), pair
+ * lists _first_second (:507-524), compute_SPs (:478-505, closed form SURVEY Q3) and
+ * compute_middlepoint_set_remove_rep_actions_no_loop (:395-476).
+ * Links are given in edge-id order (grouped by source node in node-insertion
+ * order, each node's links in adjacency order).  `K` is NUM_ACTIONS (clamped to N).
+ * sp_off/sp_nodes optionally override the BFS shortest paths with the content of
+ * a shortest_paths.json (sp_off[N*N+1] offsets into sp_nodes; pass NULL to compute). */
+int enero_topo_build(int n_nodes, int n_edges, const int32_t* edge_src, const int32_t* edge_dst,
+                     const double* capacity, int K, const int32_t* sp_off, const int32_t* sp_nodes,
+                     enero_topo** out);
+int enero_topo_destroy(enero_topo* topo);
+/* sizes: out[0]=N out[1]=E out[2]=P out[3]=K out[4]=max(first)+1 out[5]=max(second)+1
+ *        out[6]=total middlepoints out[7]=Kmax (largest candidate set) out[8]=total sp edges */
+int enero_topo_sizes(const enero_topo* topo, int64_t out[9]);
+int enero_topo_get_pairs(const enero_topo* topo, int32_t* first, int32_t* second);
+/* shortest paths as edge-id lists: off[N*N+1], edges[out[8]] */
+int enero_topo_get_sp_edges(const enero_topo* topo, int32_t* off, int32_t* edges);
+/* candidate middlepoints src_dst_k_middlepoints: off[N*N+1], mids[out[6]] */
+int enero_topo_get_middlepoints(const enero_topo* topo, int32_t* off, int32_t* mids);
+int enero_topo_get_capacity_feature(const enero_topo* topo, float* capf);
+int enero_topo_upload(enero_ctx* ctx, enero_topo* topo);
+
+/* ---- GNN, signature-compatible path ------------------------------------------
+ * actor.myModel.call (actorPPOmiddR.py:42-69) when graph_id != NULL, critic.myModel.call
+ * (criticPPO.py:38-64) when graph_id == NULL (single graph, n_graphs must be 1).
+ * link_state fp32[n,20]; graph_id int32[n] ascending; first/second int32[p] (arbitrary,
+ * honours the max(index)+1 batching quirk Q1); out fp32[n_graphs]. */
+int enero_gnn_forward(enero_ctx* ctx, int which, const float* link_state, const int32_t* graph_id,
+                      const int32_t* first, const int32_t* second, int64_t n, int64_t p,
+                      int n_graphs, int T, float* out, int ptr_kind);
+
+/* ---- fused decision batch ------------------------------------------------------
+ * pred_action_node_distrib_sp (script_eval_on_single_topology.py:83-129): for each of B
+ * independent decisions, build the K' candidate graphs of demand (s,d,bw) over link loads
+ * `loads` (mark_action_sp, environment16.py:711-725; get_graph_features, script :131-160),
+ * run the actor over all of them and soft-max the logits.
+ * loads fp64[B,E] (current demand already removed), sd int32[B,2], bw fp64[B].
+ * Outputs (any may be NULL): logits/probs fp32[B,Kmax] (entries >= nK[b] are 0),
+ * nK int32[B], action int32[B] (np.argmax of probs: first maximum). */
+int enero_decide_batch(enero_ctx* ctx, enero_topo* topo, int B, const double* loads,
+                       const int32_t* sd, const double* bw, float* logits, float* probs,
+                       int32_t* nK, int32_t* action, int ptr_kind);
+/* critic value of B link-load states (critic_get_graph_features, train script :204-230) */
+int enero_value_batch(enero_ctx* ctx, enero_topo* topo, int B, const double* loads, float* values,
+                      int ptr_kind);
+
+/* ---- device-resident episode batch (GraphEnv-v16 semantics for B episodes) -------- */
+int enero_batch_create(enero_ctx* ctx, enero_topo* topo, int B, double percentage_demands,
+                       enero_batch** out);
+int enero_batch_destroy(enero_batch* b);
+/* Env16.reset (environment16.py:642-690) with top_K_critical_demands=True for B traffic
+ * matrices tms_host fp64[B,N,N] (already floored, defo_process_results.py:216-225). */
+int enero_batch_reset(enero_batch* b, const double* tms_host);
+/* actor over the current demand of every live episode; probs_host fp32[B,Kmax] / nK_host may be NULL */
+int enero_batch_policy(enero_batch* b, float* probs_host, int32_t* nK_host);
+/* critic over the current link loads of every episode; values_host fp32[B] */
+int enero_batch_value(enero_batch* b, float* values_host);
+/* Env16.step (environment16.py:582-640).  actions_host == NULL: greedy np.argmax of the last
+ * enero_batch_policy.  Outputs (nullable): reward fp64[B], done u8[B]. */
+int enero_batch_step(enero_batch* b, const int32_t* actions_host, double* reward_host, uint8_t* done_host);
+/* whole greedy episodes (play_middRout_games_sp, script :162-188) without host round trips */
+int enero_batch_run_greedy(enero_batch* b);
+/* current state: loads fp64[B,E]; cur int32[B,2]; bw fp64[B]; max_uti fp64[B];
+ * max_edge int32[B] (edge id, -1 = the reference's (0,0,0)); done u8[B]; steps int32[B] */
+int enero_batch_get_state(enero_batch* b, double* loads, int32_t* cur, double* bw, double* max_uti,
+                          int32_t* max_edge, uint8_t* done, int32_t* steps);
+/* list_eligible_demands: elig int32[B,Dmax,2], elig_len int32[B]; Dmax via enero_batch_dmax */
+int enero_batch_dmax(enero_batch* b);
+int enero_batch_get_eligible(enero_batch* b, int32_t* elig, int32_t* elig_len);
+/* per-step history: action int32[B,Dmax], reward fp64[B,Dmax], max_uti fp64[B,Dmax] */
+int enero_batch_get_history(enero_batch* b, int32_t* action, double* reward, double* max_uti);
+/* best (lowest) max utilisation seen, the initial (OSPF) value and the routing snapshot taken at
+ * that step (script :181-184): routing int32[B,Dmax,3] = (s,d,mid) in insertion order, n int32[B] */
+int enero_batch_get_best(enero_batch* b, double* best, double* ospf, int32_t* routing, int32_t* n_routing);
+
+/* ---- Local Search (GraphEnv-v15 + HILL_CLIMBING) ------------------------------------
+ * reset_DRL_hill_sp (environment15.py:485-544) from a routing per episode (routing
+ * int32[B,Dmax,3], n int32[B]; NULL = the batch's own best routing), then the hill-climbing
+ * loop of play_DRL_GNN_sp_hill_climbing_games (script :473-509) to convergence on device.
+ * mode 0 = critical demands of the routing (explore_neighbourhood_DRL_sp), 1 = all N(N-1)
+ * demands from plain shortest paths (play_sp_hill_climbing_games, script :437-471).
+ * Outputs (nullable): start fp64[B] (max uti at reset), final fp64[B], n_moves int32[B],
+ * moves int32[B,max_moves,3] = (action,s,d), move_val fp64[B,max_moves]. */
+int enero_batch_local_search(enero_batch* b, int mode, const int32_t* routing, const int32_t* n_routing,
+                             int max_moves, double* start, double* final_val, int32_t* n_moves,
+                             int32_t* moves, double* move_val);
+/* critical demands chosen by the last enero_batch_local_search reset: elig int32[B,Dcap,2] */
+int enero_batch_get_ls_eligible(enero_batch* b, int32_t* elig, int32_t* elig_len, int cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ENERO_B200_H_ */

@@ -1,0 +1,267 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the oracle and the
+reference-recorded golden fixtures.
+
+Tolerances: integer / fp64 quantities (indices, loads, utilisations, rewards, action and
+move sequences) bit-exact; fp32 logits / probabilities / values within 1e-5 relative
+(atol 1e-6 for values near zero), as BASELINE.json's north_star states.
+"""
+import numpy as np
+import pytest
+
+from conftest import CASE_NAMES, case_graph_file, load_case
+from oracle import enero_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-5, 1e-6
+
+
+@pytest.fixture(scope="module")
+def ctx(weights):
+    from enero_b200.runtime import Context
+    c = Context(0)
+    flat = [weights[k] for k in orc.WEIGHT_NAMES]
+    c.upload_weights(0, flat)
+    # no critic checkpoint is shipped: a deterministic perturbation of the actor stands in
+    rng = np.random.default_rng(7)
+    c.upload_weights(1, [w + rng.normal(0, 0.05, w.shape).astype(np.float32) for w in flat])
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def critic_weights(ctx):
+    return dict(zip(orc.WEIGHT_NAMES, ctx.download_weights(1)))
+
+
+def _topos(name, tmp_path_factory):
+    from enero_b200.topology import Topology
+    case = load_case(name)
+    gf = case_graph_file(case, tmp_path_factory.mktemp(name))
+    return case, Topology(gf, K=100), orc.Topology(gf, K=100)
+
+
+@pytest.fixture(scope="module", params=CASE_NAMES)
+def trio(request, tmp_path_factory):
+    return _topos(request.param, tmp_path_factory)
+
+
+def test_weights_roundtrip(ctx, weights):
+    got = ctx.download_weights(0)
+    for g, k in zip(got, orc.WEIGHT_NAMES):
+        assert np.array_equal(g, weights[k])
+
+
+def test_gnn_forward_signature_path(ctx, trio, weights, critic_weights):
+    """actor.myModel.call / critic.myModel.call with explicit first/second (quirk Q1 included:
+    tiny12 and zoo30 have max(second)+1 < E)."""
+    case, topo, ot = trio
+    ep = case["episodes"][0]
+    env = orc.Env16(ot)
+    _, s, d = env.reset(np.array(case["tms"][str(ep["tm_id"])]))
+    for step in range(3):
+        feats = env.candidate_features(s, d)
+        b = orc.batch_candidates(feats, ot.first, ot.second)
+        want = orc.actor_forward(weights, b["link_state"], b["graph_id"], b["first"], b["second"], b["num_edges"]).reshape(-1)
+        got = ctx.gnn_forward(0, b["link_state"], b["graph_id"], b["first"], b["second"], len(feats))
+        np.testing.assert_allclose(got, want, rtol=RTOL, atol=ATOL)
+        cf = env.critic_features()
+        wantv = orc.critic_forward(critic_weights, cf, ot.first, ot.second, ot.E).reshape(-1)
+        gotv = ctx.gnn_forward(1, cf, None, ot.first, ot.second, 1)
+        np.testing.assert_allclose(gotv, wantv, rtol=RTOL, atol=ATOL)
+        _, _, _, _, s, d, _, _, _ = env.step(ep["steps"][step]["action"])
+
+
+def test_gnn_forward_arbitrary_indices(ctx, weights):
+    """unsorted, repeated and missing destinations; empty graphs; shuffled pair order."""
+    rng = np.random.default_rng(3)
+    n, p, G = 257, 900, 7
+    ls = rng.normal(0, 0.5, (n, 20)).astype(np.float32)
+    first = rng.integers(0, n, p).astype(np.int32)
+    second = rng.integers(0, n - 40, p).astype(np.int32)       # rows >= n-40 receive nothing
+    gid = np.sort(rng.choice([0, 1, 2, 4, 6], n)).astype(np.int32)   # graphs 3 and 5 are empty
+    want = orc.actor_forward(weights, ls, gid, first, second, n).reshape(-1)
+    full = np.zeros(G, dtype=np.float32)
+    full[:] = orc.readout(weights, np.zeros((1, 20), dtype=np.float32)).reshape(-1)[0]
+    full[:want.size] = want
+    for g in (3, 5):
+        full[g] = orc.readout(weights, np.zeros((1, 20), dtype=np.float32)).reshape(-1)[0]
+    got = ctx.gnn_forward(0, ls, gid, first, second, G)
+    np.testing.assert_allclose(got, full, rtol=RTOL, atol=ATOL)
+
+
+def test_gnn_forward_rejects_bad_indices(ctx):
+    from enero_b200._lib import EneroError
+    ls = np.zeros((8, 20), dtype=np.float32)
+    with pytest.raises(EneroError):
+        ctx.gnn_forward(0, ls, np.zeros(8, np.int32), np.array([0, 9], np.int32), np.array([1, 2], np.int32), 1)
+    with pytest.raises(EneroError):
+        ctx.gnn_forward(0, ls, np.array([1, 0, 0, 0, 0, 0, 0, 0], np.int32), np.array([0], np.int32), np.array([1], np.int32), 2)
+
+
+def test_decide_batch_matches_oracle_and_golden(ctx, trio, weights):
+    case, topo, ot = trio
+    for ep in case["episodes"]:
+        tm = np.array(case["tms"][str(ep["tm_id"])])
+        decs = ep["decisions"]
+        B = len(decs)
+        loads = np.array([dc["loads_before"] for dc in decs])
+        sd = np.array([[dc["s"], dc["d"]] for dc in decs], dtype=np.int32)
+        bw = np.array([tm[dc["s"], dc["d"]] for dc in decs])
+        logits, probs, nK, action = ctx.decide_batch(topo, loads, sd, bw)
+        for b, dc in enumerate(decs):
+            k = len(dc["logits"])
+            assert nK[b] == k
+            np.testing.assert_allclose(logits[b, :k], dc["logits"], rtol=RTOL, atol=ATOL)
+            np.testing.assert_allclose(probs[b, :k], dc["probs"], rtol=RTOL, atol=ATOL)
+            assert not logits[b, k:].any() and not probs[b, k:].any()
+            assert action[b] == ep["steps"][b]["action"]
+
+
+def test_value_batch_matches_oracle(ctx, trio, critic_weights):
+    case, topo, ot = trio
+    ep = case["episodes"][0]
+    loads = np.array([dc["loads_before"] for dc in ep["decisions"][:8]])
+    got = ctx.value_batch(topo, loads)
+    for b in range(loads.shape[0]):
+        ls = np.zeros((ot.E, 20), dtype=np.float32)
+        ls[:, 0] = (loads[b] / ot.cap).astype(np.float32)
+        ls[:, 1] = ot.link_capacity_feature
+        want = orc.critic_forward(critic_weights, ls, ot.first, ot.second, ot.E).reshape(-1)[0]
+        np.testing.assert_allclose(got[b], want, rtol=RTOL, atol=ATOL)
+
+
+def test_greedy_episodes_and_local_search_bit_exact(ctx, trio):
+    """Whole Enero pipeline on device against the reference-recorded trace: greedy action
+    sequence, rewards, max utilisation per step, best routing snapshot, LS move sequence and
+    final max link utilisation -- all bit-exact."""
+    from enero_b200.engine import EpisodeBatch
+    case, topo, ot = trio
+    eps = case["episodes"]
+    tms = np.array([case["tms"][str(ep["tm_id"])] for ep in eps])
+    eb = EpisodeBatch(ctx, topo, len(eps))
+    bw, cur = eb.reset(tms)
+    elig, n_elig = eb.eligible()
+    st = eb.state()
+    for b, ep in enumerate(eps):
+        r = ep["reset"]
+        assert (bw[b], cur[b, 0], cur[b, 1]) == (r["demand"], r["s"], r["d"])
+        assert [[int(s), int(d)] for s, d in elig[b, :n_elig[b]]] == [[e[0], e[1]] for e in r["elig"]]
+        assert st["max_uti"][b] == r["edge_max"][2]
+        assert st["loads"][b].tolist() == ep["decisions"][0]["loads_before"]
+    eb.run_greedy()
+    act, rew, mx = eb.history()
+    st = eb.state()
+    best, ospf, routing = eb.best()
+    for b, ep in enumerate(eps):
+        n = len(ep["steps"])
+        assert st["steps"][b] == n and st["done"][b]
+        assert act[b, :n].tolist() == [s["action"] for s in ep["steps"]]
+        assert rew[b, :n].tolist() == [s["reward"] for s in ep["steps"]]
+        assert mx[b, :n].tolist() == [s["edge_max"][2] for s in ep["steps"]]
+        assert st["loads"][b].tolist() == ep["steps"][-1]["loads_after"]
+        last = ep["steps"][-1]["edge_max"]
+        assert st["max_edge"][b] == ot.eid[(last[0], last[1])]
+        assert (best[b], ospf[b]) == (ep["best"], ep["ospf"])
+        assert [list(r) for r in routing[b]] == ep["best_routing"]
+    ls = eb.local_search(None, mode=0)
+    le, ln = eb.ls_eligible()
+    for b, ep in enumerate(eps):
+        g = ep["ls"]
+        assert ls["start"][b] == -g["reset_val"]
+        assert [[int(s), int(d)] for s, d in le[b, :ln[b]]] == [[e[0], e[1]] for e in g["elig"]]
+        n = ls["n_moves"][b]
+        got = [[int(ls["moves"][b, k, 0]), int(ls["moves"][b, k, 1]), int(ls["moves"][b, k, 2]), float(ls["move_val"][b, k])]
+               for k in range(n)]
+        assert got == g["moves"]
+        assert ls["final"][b] == g["final"]
+    # the same Local Search from an explicitly supplied routing
+    ls2 = eb.local_search([ [tuple(r) for r in ep["best_routing"]] for ep in eps ], mode=0)
+    assert ls2["final"].tolist() == [ep["ls"]["final"] for ep in eps]
+    eb.close()
+
+
+def test_stepwise_env_matches_trace(ctx, trio):
+    """policy() / step(actions) one decision at a time (the training-rollout usage)."""
+    from enero_b200.engine import EpisodeBatch
+    case, topo, ot = trio
+    ep = case["episodes"][0]
+    eb = EpisodeBatch(ctx, topo, 1)
+    eb.reset(np.array([case["tms"][str(ep["tm_id"])]]))
+    for k, (stp, dc) in enumerate(zip(ep["steps"][:6], ep["decisions"][:6])):
+        probs, nK = eb.policy()
+        np.testing.assert_allclose(probs[0, :nK[0]], dc["probs"], rtol=RTOL, atol=ATOL)
+        reward, done = eb.step([stp["action"]])
+        assert reward[0] == stp["reward"] and bool(done[0]) == stp["done"]
+        st = eb.state()
+        assert st["loads"][0].tolist() == stp["loads_after"]
+        assert [st["bw"][0], st["cur"][0, 0], st["cur"][0, 1]] == stp["next"]
+    eb.close()
+
+
+@pytest.mark.parametrize("name", ["tri9", "tiny12"])
+def test_plain_hill_climbing(ctx, name, tmp_path_factory):
+    from enero_b200.engine import EpisodeBatch
+    case, topo, ot = _topos(name, tmp_path_factory)
+    eps = case["episodes"]
+    eb = EpisodeBatch(ctx, topo, len(eps))
+    eb.reset(np.array([case["tms"][str(ep["tm_id"])] for ep in eps]))
+    ls = eb.local_search(None, mode=1, want_moves=False)
+    assert ls["final"].tolist() == [ep["plain_hill_final"] for ep in eps]
+    eb.close()
+
+
+def test_full_size_properties(ctx, tmp_path):
+    """BASELINE config 2 size (100 links): size-independent properties on 48 synthetic TMs."""
+    from enero_b200 import datasets as ds
+    from enero_b200.engine import EpisodeBatch
+    from enero_b200.topology import Topology
+    links, caps = ds.zoo_like(30, 50, 4242)
+    p = str(tmp_path / "g.graph")
+    ds.write_graph_file(p, 30, links, caps)
+    gf = ds.parse_graph_file(p)
+    topo = Topology(gf, K=100)
+    sigma = ds.sigma_for_mean_utilisation(gf)
+    base = [ds.uniform_tm(30, sigma, 9000 + j) for j in range(24)]
+    tms = np.array(base + base)                     # every TM twice: determinism across batch slots
+    eb = EpisodeBatch(ctx, topo, len(tms))
+    eb.reset(tms)
+    st0 = eb.state()
+    # conservation: total load == sum over demands of bw * hops, with the first demand removed
+    hops = np.array([[len(topo.sp_edges(s, d)) if s != d else 0 for d in range(30)] for s in range(30)])
+    for b in range(len(tms)):
+        s, d = st0["cur"][b]
+        assert st0["loads"][b].sum() == (tms[b] * hops).sum() - tms[b][s, d] * hops[s, d]
+    eb.run_greedy()
+    best, ospf, routing = eb.best()
+    act, rew, mx = eb.history()
+    st = eb.state()
+    assert (best <= ospf).all() and st["done"].all()
+    assert np.array_equal(act[:24], act[24:]) and np.array_equal(mx[:24], mx[24:])
+    # telescoping rewards: sum of un-rounded rewards == 10 * (ospf - final max)
+    for b in range(len(tms)):
+        n = st["steps"][b]
+        assert abs(rew[b, :n].sum() - 10 * (ospf[b] - mx[b, n - 1])) < 0.005 * n + 1e-9
+    ls = eb.local_search(None, mode=0)
+    assert (ls["final"] <= ls["start"] + 1e-12).all()
+    assert np.array_equal(ls["final"][:24], ls["final"][24:])
+    # Local Search restarts from the DRL best routing: same max utilisation, unless the best was the
+    # final step (whose snapshot lacks the dummy demand (1,2), environment16.py:622-635)
+    for b in range(len(tms)):
+        if mx[b, st["steps"][b] - 1] > best[b]:
+            assert ls["start"][b] == best[b]
+    # idempotence: a second LS from the LS result makes no move -- replay moves to build that routing
+    final_routing = []
+    for b in range(len(tms)):
+        cur = {(s, d): m for s, d, m in routing[b]}
+        for k in range(ls["n_moves"][b]):
+            a, s, d = (int(v) for v in ls["moves"][b, k])
+            m = topo.middlepoints(s, d)[a]
+            cur.pop((s, d), None)
+            if m != d:
+                cur[(s, d)] = m
+        final_routing.append([(s, d, m) for (s, d), m in cur.items()])
+    if max(len(r) for r in final_routing) <= eb.Dmax:
+        ls2 = eb.local_search(final_routing, mode=0)
+        assert np.array_equal(ls2["start"], ls["final"])
+    eb.close()
