@@ -40,6 +40,8 @@ SIGNATURES = {
     "enero_ctx_sync": (C.c_int, [_vp]),
     "enero_ctx_launch_count": (C.c_int64, [_vp]),
     "enero_ctx_stream": (_vp, [_vp]),
+    "enero_ctx_profile_begin": (C.c_int, [_vp]),
+    "enero_ctx_profile_end": (C.c_int, [_vp, _vp, _vp]),
     "enero_weights_upload": (C.c_int, [_vp, C.c_int, _vp]),
     "enero_weights_download": (C.c_int, [_vp, C.c_int, _vp]),
     "enero_topo_build": (C.c_int, [C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp, _p(_vp)]),
@@ -60,6 +62,8 @@ SIGNATURES = {
     "enero_batch_value": (C.c_int, [_vp, _vp]),
     "enero_batch_step": (C.c_int, [_vp, _vp, _vp, _vp]),
     "enero_batch_run_greedy": (C.c_int, [_vp]),
+    "enero_batch_snapshot": (C.c_int, [_vp]),
+    "enero_batch_restore": (C.c_int, [_vp]),
     "enero_batch_get_state": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "enero_batch_dmax": (C.c_int, [_vp]),
     "enero_batch_get_eligible": (C.c_int, [_vp, _vp, _vp]),

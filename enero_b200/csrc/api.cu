@@ -55,6 +55,9 @@ struct enero_ctx {
     DevBuf h[2], A[2], util, nK, logits, probs, action, in_loads, in_sd, in_bw, ones;
     DevBuf x_ls, x_gid, x_first, x_second, x_cnt, x_off, x_cur, x_slot, x_src, x_goff, x_err, x_out;
     int occ_iter[2][2] = {{0, 0}, {0, 0}};   // [indexer][last] resident CTAs/SM of k_mp_iter
+    // optional per-launch CUDA-event timing of the dominant kernel (bench.py roofline leg)
+    bool prof = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_ev;
 };
 
 #define LAUNCH_CHECK(ctx)                                                     \
@@ -112,6 +115,30 @@ extern "C" int enero_ctx_sync(enero_ctx* c) {
 }
 extern "C" int64_t enero_ctx_launch_count(enero_ctx* c) { return c ? c->launches : -1; }
 extern "C" void* enero_ctx_stream(enero_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+extern "C" int enero_ctx_profile_begin(enero_ctx* c) {
+    if (!c) return fail(ENERO_ERR_INVALID, "null ctx");
+    for (auto& e : c->prof_ev) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    c->prof_ev.clear();
+    c->prof = true;
+    return ENERO_OK;
+}
+extern "C" int enero_ctx_profile_end(enero_ctx* c, double* mp_iter_ms, int64_t* mp_iter_launches) {
+    if (!c) return fail(ENERO_ERR_INVALID, "null ctx");
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    double tot = 0;
+    for (auto& e : c->prof_ev) {
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e.first, e.second));
+        tot += ms;
+        cudaEventDestroy(e.first); cudaEventDestroy(e.second);
+    }
+    if (mp_iter_ms) *mp_iter_ms = tot;
+    if (mp_iter_launches) *mp_iter_launches = (int64_t)c->prof_ev.size();
+    c->prof_ev.clear();
+    c->prof = false;
+    return ENERO_OK;
+}
 
 extern "C" int enero_weights_upload(enero_ctx* c, int which, const float* flat) {
     if (!c || !flat || which < 0 || which > 1) return fail(ENERO_ERR_INVALID, "enero_weights_upload: bad argument");
@@ -181,9 +208,15 @@ static int run_iterations(enero_ctx* c, const IDX& idx, int which, int T, int64_
         const float* Ain = c->A[it & 1].as<float>();
         float* hout = c->h[(it + 1) & 1].as<float>();
         float* Aout = c->A[(it + 1) & 1].as<float>();
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (c->prof) {
+            CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+            CUDA_TRY(cudaEventRecord(e0, c->stream));
+        }
         if (last) k_mp_iter<IDX, true><<<grid, MP_TPB, 0, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles);
         else k_mp_iter<IDX, false><<<grid, MP_TPB, 0, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles);
         LAUNCH_CHECK(c);
+        if (c->prof) { CUDA_TRY(cudaEventRecord(e1, c->stream)); c->prof_ev.emplace_back(e0, e1); }
     }
     return ENERO_OK;
 }
@@ -361,6 +394,7 @@ struct enero_batch {
     bool reset_done = false, policy_valid = false;
     DevBuf tm, loads, mid_cur, elig, elig_len, it, cur, cur_bw, done, steps, max_uti, max_edge, best, best_step, ospf,
         h_action, h_reward, h_max, last_reward, logits, probs, nK, action, values;
+    DevBuf snap;                                    // enero_batch_snapshot image of the mutable state
     DevBuf ls_loads, ls_mid, ls_elig, ls_elig_len, ls_val, ls_nmoves, ls_moves, ls_move_val, ls_max_edge;
     std::vector<int> h_elig, h_elig_len;           // host mirror of list_eligible_demands
     std::vector<int> h_ls_elig, h_ls_elig_len; int ls_cap = 0;
@@ -407,7 +441,7 @@ extern "C" int enero_batch_destroy(enero_batch* b) {
     for (DevBuf* x : {&b->tm, &b->loads, &b->mid_cur, &b->elig, &b->elig_len, &b->it, &b->cur, &b->cur_bw, &b->done, &b->steps,
                       &b->max_uti, &b->max_edge, &b->best, &b->best_step, &b->ospf, &b->h_action, &b->h_reward, &b->h_max,
                       &b->last_reward, &b->logits, &b->probs, &b->nK, &b->action, &b->values, &b->ls_loads, &b->ls_mid,
-                      &b->ls_elig, &b->ls_elig_len, &b->ls_val, &b->ls_nmoves, &b->ls_moves, &b->ls_move_val, &b->ls_max_edge})
+                      &b->snap, &b->ls_elig, &b->ls_elig_len, &b->ls_val, &b->ls_nmoves, &b->ls_moves, &b->ls_move_val, &b->ls_max_edge})
         x->release();
     delete b;
     return ENERO_OK;
@@ -444,6 +478,39 @@ extern "C" int enero_batch_reset(enero_batch* b, const double* tms) {
     k_episode_begin<<<(B + 3) / 4, 128, 0, st>>>(tv, ep_view(b)); LAUNCH_CHECK(c);
     CUDA_TRY(cudaStreamSynchronize(st));
     b->reset_done = true; b->policy_valid = false;
+    return ENERO_OK;
+}
+
+// mutable episode state = (buffer, bytes) list, in a fixed order
+static std::vector<std::pair<DevBuf*, size_t>> mutable_state(enero_batch* b) {
+    const size_t B = b->B, NN = b->NN, E = b->t->E, D = b->Dmax;
+    return {{&b->loads, B * E * 8}, {&b->mid_cur, B * NN * 4}, {&b->it, B * 4}, {&b->cur, B * 8}, {&b->cur_bw, B * 8},
+            {&b->done, B}, {&b->steps, B * 4}, {&b->max_uti, B * 8}, {&b->max_edge, B * 4}, {&b->best, B * 8},
+            {&b->best_step, B * 4}, {&b->ospf, B * 8}, {&b->h_action, B * D * 4}, {&b->h_reward, B * D * 8},
+            {&b->h_max, B * D * 8}};
+}
+extern "C" int enero_batch_snapshot(enero_batch* b) {
+    if (!b || !b->reset_done) return fail(ENERO_ERR_STATE, "enero_batch_snapshot: reset first");
+    CUDA_TRY(cudaSetDevice(b->c->device));
+    size_t tot = 0;
+    for (auto& x : mutable_state(b)) tot += (x.second + 255) & ~size_t(255);
+    TRY(b->snap.ensure(tot));
+    size_t o = 0;
+    for (auto& x : mutable_state(b)) {
+        CUDA_TRY(cudaMemcpyAsync((char*)b->snap.p + o, x.first->p, x.second, cudaMemcpyDeviceToDevice, b->c->stream));
+        o += (x.second + 255) & ~size_t(255);
+    }
+    return ENERO_OK;
+}
+extern "C" int enero_batch_restore(enero_batch* b) {
+    if (!b || !b->snap.p) return fail(ENERO_ERR_STATE, "enero_batch_restore: no snapshot");
+    CUDA_TRY(cudaSetDevice(b->c->device));
+    size_t o = 0;
+    for (auto& x : mutable_state(b)) {
+        CUDA_TRY(cudaMemcpyAsync(x.first->p, (char*)b->snap.p + o, x.second, cudaMemcpyDeviceToDevice, b->c->stream));
+        o += (x.second + 255) & ~size_t(255);
+    }
+    b->policy_valid = false;
     return ENERO_OK;
 }
 
@@ -504,7 +571,7 @@ extern "C" int enero_batch_step(enero_batch* b, const int32_t* actions, double* 
     TRY(step_dev(b));
     if (reward) CUDA_TRY(cudaMemcpyAsync(reward, b->last_reward.p, (size_t)b->B * 8, cudaMemcpyDeviceToHost, c->stream));
     if (done) CUDA_TRY(cudaMemcpyAsync(done, b->done.p, (size_t)b->B, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (reward || done || actions) CUDA_TRY(cudaStreamSynchronize(c->stream));   // otherwise asynchronous
     return ENERO_OK;
 }
 

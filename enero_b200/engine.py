@@ -58,11 +58,15 @@ class EpisodeBatch:
         _lib.check(self._lib.enero_batch_value(self._h, _lib.ptr(v)))
         return v
 
-    def step(self, actions=None):
-        """actions None = greedy argmax of the last policy(). -> (reward[B], done[B])."""
+    def step(self, actions=None, want_outputs: bool = True):
+        """actions None = greedy argmax of the last policy(). -> (reward[B], done[B]);
+        want_outputs=False with actions=None only enqueues the step (asynchronous)."""
         a = None if actions is None else np.ascontiguousarray(actions, dtype=np.int32).reshape(-1)
         if a is not None and a.size != self.B:
             raise ValueError("need one action per episode")
+        if a is None and not want_outputs:
+            _lib.check(self._lib.enero_batch_step(self._h, None, None, None))
+            return None, None
         reward = np.zeros(self.B, dtype=np.float64)
         done = np.zeros(self.B, dtype=np.uint8)
         _lib.check(self._lib.enero_batch_step(self._h, _lib.ptr(a), _lib.ptr(reward), _lib.ptr(done)))
@@ -70,6 +74,12 @@ class EpisodeBatch:
 
     def run_greedy(self):
         _lib.check(self._lib.enero_batch_run_greedy(self._h))
+
+    def snapshot(self):
+        _lib.check(self._lib.enero_batch_snapshot(self._h))
+
+    def restore(self):
+        _lib.check(self._lib.enero_batch_restore(self._h))
 
     def state(self) -> dict:
         B, E = self.B, self.topo.E

@@ -79,6 +79,15 @@ class Context:
     def stream(self) -> int:
         return int(self._lib.enero_ctx_stream(self._h) or 0)
 
+    def profile_begin(self):
+        _lib.check(self._lib.enero_ctx_profile_begin(self._h))
+
+    def profile_end(self):
+        ms = C.c_double(0)
+        n = C.c_int64(0)
+        _lib.check(self._lib.enero_ctx_profile_end(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     # ---- weights -------------------------------------------------------------------------
     def upload_weights(self, which: int, tensors):
         flat = flatten_weights(tensors)

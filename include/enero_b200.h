@@ -56,6 +56,11 @@ int64_t enero_ctx_launch_count(enero_ctx* ctx);
 /* raw cudaStream_t the ctx launches on (for CUDA-event timing by the caller) */
 void* enero_ctx_stream(enero_ctx* ctx);
 
+/* per-launch CUDA-event timing of the dominant kernel (k_mp_iter) between begin and end:
+ * total milliseconds and number of launches (bench.py's roofline leg; off by default) */
+int enero_ctx_profile_begin(enero_ctx* ctx);
+int enero_ctx_profile_end(enero_ctx* ctx, double* mp_iter_ms, int64_t* mp_iter_launches);
+
 /* ---- weights ---------------------------------------------------------------
  * Flat fp32[4201] in Keras variable order: FirstLayer/kernel[40,20], bias[20],
  * gru/kernel[20,60], recurrent_kernel[20,60], bias[2,60], Readout1/kernel[20,20],
@@ -123,10 +128,14 @@ int enero_batch_policy(enero_batch* b, float* probs_host, int32_t* nK_host);
 /* critic over the current link loads of every episode; values_host fp32[B] */
 int enero_batch_value(enero_batch* b, float* values_host);
 /* Env16.step (environment16.py:582-640).  actions_host == NULL: greedy np.argmax of the last
- * enero_batch_policy.  Outputs (nullable): reward fp64[B], done u8[B]. */
+ * enero_batch_policy.  Outputs (nullable): reward fp64[B], done u8[B].  With all three pointers NULL the
+ * call only enqueues the kernel (asynchronous); otherwise it returns after the stream has drained. */
 int enero_batch_step(enero_batch* b, const int32_t* actions_host, double* reward_host, uint8_t* done_host);
 /* whole greedy episodes (play_middRout_games_sp, script :162-188) without host round trips */
 int enero_batch_run_greedy(enero_batch* b);
+/* save / restore the mutable episode state on device (rollout restarts, benchmarking) */
+int enero_batch_snapshot(enero_batch* b);
+int enero_batch_restore(enero_batch* b);
 /* current state: loads fp64[B,E]; cur int32[B,2]; bw fp64[B]; max_uti fp64[B];
  * max_edge int32[B] (edge id, -1 = the reference's (0,0,0)); done u8[B]; steps int32[B] */
 int enero_batch_get_state(enero_batch* b, double* loads, int32_t* cur, double* bw, double* max_uti,
