@@ -86,10 +86,14 @@ extern "C" int enero_ctx_create(int device, enero_ctx** out) {
         CUDA_TRY(cudaMalloc(&c->w[i], sizeof(float) * (ENERO_NPARAMS + 3)));
         CUDA_TRY(cudaMemset(c->w[i], 0, sizeof(float) * (ENERO_NPARAMS + 3)));
     }
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_iter[0][0], k_mp_iter<IdxExplicit, false>, MP_TPB, 0));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_iter[0][1], k_mp_iter<IdxExplicit, true>, MP_TPB, 0));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_iter[1][0], k_mp_iter<IdxTopo, false>, MP_TPB, 0));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_iter[1][1], k_mp_iter<IdxTopo, true>, MP_TPB, 0));
+    CUDA_TRY(cudaFuncSetAttribute(k_mp_iter<IdxExplicit, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MP_SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(k_mp_iter<IdxExplicit, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MP_SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(k_mp_iter<IdxTopo, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MP_SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(k_mp_iter<IdxTopo, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MP_SMEM_BYTES));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_iter[0][0], k_mp_iter<IdxExplicit, false>, MP_TPB, MP_SMEM_BYTES));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_iter[0][1], k_mp_iter<IdxExplicit, true>, MP_TPB, MP_SMEM_BYTES));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_iter[1][0], k_mp_iter<IdxTopo, false>, MP_TPB, MP_SMEM_BYTES));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_iter[1][1], k_mp_iter<IdxTopo, true>, MP_TPB, MP_SMEM_BYTES));
     *out = c;
     return ENERO_OK;
 }
@@ -199,7 +203,7 @@ static TopoView view_of(const enero_topo* t) {
 // ---- message passing driver ---------------------------------------------------------------
 template <class IDX>
 static int run_iterations(enero_ctx* c, const IDX& idx, int which, int T, int64_t rows, int idx_kind) {
-    const int64_t ntiles = (rows + MP_TPB - 1) / MP_TPB;
+    const int64_t ntiles = (rows + MP_ROWS - 1) / MP_ROWS;
     for (int it = 0; it < T; ++it) {
         const bool last = (it == T - 1);
         const int occ = std::max(1, c->occ_iter[idx_kind][last ? 1 : 0]);
@@ -213,8 +217,8 @@ static int run_iterations(enero_ctx* c, const IDX& idx, int which, int T, int64_
             CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
             CUDA_TRY(cudaEventRecord(e0, c->stream));
         }
-        if (last) k_mp_iter<IDX, true><<<grid, MP_TPB, 0, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles);
-        else k_mp_iter<IDX, false><<<grid, MP_TPB, 0, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles);
+        if (last) k_mp_iter<IDX, true><<<grid, MP_TPB, MP_SMEM_BYTES, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles);
+        else k_mp_iter<IDX, false><<<grid, MP_TPB, MP_SMEM_BYTES, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles);
         LAUNCH_CHECK(c);
         if (c->prof) { CUDA_TRY(cudaEventRecord(e1, c->stream)); c->prof_ev.emplace_back(e0, e1); }
     }

@@ -264,8 +264,8 @@ constexpr int LS_TPB = 256;
 
 __global__ void __launch_bounds__(LS_TPB)
 k_local_search(TopoView t, LsView ls) {
-    extern __shared__ double smem[];
-    double* sl = smem;                                   // [E] loads
+    extern __shared__ double ls_smem[];
+    double* sl = ls_smem;                                // [E] loads
     double* scap = sl + t.E;                             // [E]
     double* wbest = scap + t.E;                          // [nwarps]
     int* wbest_i = reinterpret_cast<int*>(wbest + LS_TPB / 32);   // [nwarps] move order key

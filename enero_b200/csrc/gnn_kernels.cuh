@@ -101,70 +101,200 @@ struct IdxTopo {
     }
 };
 
+// ---- packed fp32x2 helpers (Blackwell FFMA2: two FMAs per lane per issue slot) ---------
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pack2(float lo, float hi) { u64 d; asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi)); return d; }
+__device__ __forceinline__ void unpack2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+// c + x * (w.lo, w.hi): ptxas folds the {x, x} pack into FFMA2's scalar-broadcast operand form
+__device__ __forceinline__ u64 fma2s(float x, u64 w, u64 c) {
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(pack2(x, x)), "l"(w), "l"(c));
+    return d;
+}
+
+// fast transcendental forms (MUFU.EX2 / MUFU.RCP); relative error ~1e-6, see DESIGN.md
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+constexpr float LOG2E = 1.4426950408889634f;
+__device__ __forceinline__ float selu_fast(float x) {
+    const float scale = 1.0507009873554804934193349852946f;
+    const float scale_alpha = 1.7580993408473768599402175208123f;
+    const float e = ex2_approx(x * LOG2E);
+    return x < 0.f ? fmaf(scale_alpha, e, -scale_alpha) : scale * x;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return rcp_approx(1.f + ex2_approx(-LOG2E * x)); }
+__device__ __forceinline__ float tanh_fast(float x) { return fmaf(-2.f, rcp_approx(1.f + ex2_approx((2.f * LOG2E) * x)), 1.f); }
+
 // ---- one message-passing iteration ------------------------------------------------
-// Persistent CTAs: weights staged once in shared memory, then a grid-stride loop over
-// 128-row tiles.  h_in/A_in are read, h_out/A_out written (ping-pong across launches).
+// Persistent CTAs of 128 threads; every thread owns MP_R = 2 link-state rows of a 256-row tile so
+// that each broadcast LDS.128 of weights feeds 8 FMAs (the shared-memory return path, not the FMA
+// pipe, is the limiter at 4 FMAs per load: tools/ubench_matvec.cu).  The row vectors (h, agg) stay in
+// registers; mat-vecs run as rolled loops over blocks of 4 outputs (k fully unrolled) so the
+// instruction footprint stays ~15 KB -- the first version, fully unrolled (~80 KB of straight-line
+// code), spent 45 % of its issue slots waiting on instruction fetch (profiles/r01_*).
+// Outputs of a block (dynamic index) go through per-thread shared-memory slots with an 80-byte
+// stride, which is bank-conflict-free for LDS/STS.128.
+constexpr int MP_R = 2;
+constexpr int MP_ROWS = MP_TPB * MP_R;                       // rows per tile
+constexpr int MP_SMEM_FLOATS = W_MP_FLOATS + 2 * MP_ROWS * H;  // weights + h slots + B/z slots
+constexpr size_t MP_SMEM_BYTES = sizeof(float) * MP_SMEM_FLOATS;
+
 template <class IDX, bool LAST>
-__global__ void __launch_bounds__(MP_TPB)
+__global__ void __launch_bounds__(MP_TPB, 3)
 k_mp_iter(const IDX idx, const float* __restrict__ wflat, const float* __restrict__ h_in,
           const float* __restrict__ A_in, float* __restrict__ h_out, float* __restrict__ A_out,
           int64_t ntiles) {
-    __shared__ __align__(16) float sw[W_MP_FLOATS];
+    extern __shared__ __align__(16) float mp_smem[];
+    float* sw = mp_smem;
+    float* sh = mp_smem + W_MP_FLOATS;                // [MP_R][128][20]  h (old, then new)
+    float* sb = sh + MP_ROWS * H;                   // [MP_R][128][20]  B, then z
     for (int i = threadIdx.x; i < W_MP_FLOATS / 4; i += MP_TPB)
         reinterpret_cast<float4*>(sw)[i] = reinterpret_cast<const float4*>(wflat)[i];
     __syncthreads();
+    float* myh[MP_R]; float* myb[MP_R];
+#pragma unroll
+    for (int r = 0; r < MP_R; ++r) { myh[r] = sh + (r * MP_TPB + threadIdx.x) * H; myb[r] = sb + (r * MP_TPB + threadIdx.x) * H; }
 
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        // keep ptxas from hoisting the (loop-invariant) weight LDS out of the tile loop into registers
-        asm volatile("" ::: "memory");
-        const int64_t r = tile * MP_TPB + threadIdx.x;
-        if (!idx.valid(r)) continue;
-        float h[H], t[H], agg[H];
-        load_row(h, h_in + r * H);
-        // B_r = bm + h . Wm[20:40]
+        int64_t row[MP_R]; bool ok[MP_R];
 #pragma unroll
-        for (int j = 0; j < H; ++j) { t[j] = sw[W_MSG_B + j]; agg[j] = 0.f; }
-        mv20<H>(t, h, sw + W_MSG_K + H * H);
-        int pb, pe; const int* list; int64_t add;
-        idx.seg(r, pb, pe, list, add);
-        for (int p = pb; p < pe; ++p) {
-            float a[H];
-            load_row(a, A_in + ((int64_t)list[p] + add) * H);
+        for (int r = 0; r < MP_R; ++r) { row[r] = tile * MP_ROWS + r * MP_TPB + threadIdx.x; ok[r] = idx.valid(row[r]); }
+        if (!(ok[0] || ok[1])) continue;
+        float h[MP_R][H], agg[MP_R][H];
 #pragma unroll
-            for (int j = 0; j < H; ++j) agg[j] += selu_f(a[j] + t[j]);
+        for (int r = 0; r < MP_R; ++r) {
+            if (ok[r]) load_row(h[r], h_in + row[r] * H);
+            else {
+#pragma unroll
+                for (int j = 0; j < H; ++j) h[r][j] = 0.f;
+            }
+            store_row(myh[r], h[r]);
+#pragma unroll
+            for (int j = 0; j < H; ++j) agg[r][j] = 0.f;
         }
-        // GRUCell, reset_after=True (Keras recurrent_v2 GRUCell.call, implementation 2)
-        float z[H];
+        // ---- B = bm + h . Wm[20:40]
+#pragma unroll 1
+        for (int jb = 0; jb < H / 4; ++jb) {
+            const ulonglong2 b0 = *reinterpret_cast<const ulonglong2*>(sw + W_MSG_B + 4 * jb);
+            u64 acc[MP_R][2];
 #pragma unroll
-        for (int j = 0; j < H; ++j) z[j] = sw[W_GRU_B + j];
-        mv20<60>(z, agg, sw + W_GRU_K);
-        mv20<60>(z, h, sw + W_GRU_R);
+            for (int r = 0; r < MP_R; ++r) { acc[r][0] = b0.x; acc[r][1] = b0.y; }
 #pragma unroll
-        for (int j = 0; j < H; ++j) z[j] = sigmoid_f(z[j] + sw[W_GRU_B + 60 + j]);
+            for (int k = 0; k < H; ++k) {
+                const ulonglong2 w = *reinterpret_cast<const ulonglong2*>(sw + W_MSG_K + H * H + k * H + 4 * jb);
 #pragma unroll
-        for (int j = 0; j < H; ++j) t[j] = sw[W_GRU_B + 20 + j];
-        mv20<60>(t, agg, sw + W_GRU_K + 20);
-        mv20<60>(t, h, sw + W_GRU_R + 20);
+                for (int r = 0; r < MP_R; ++r) { acc[r][0] = fma2s(h[r][k], w.x, acc[r][0]); acc[r][1] = fma2s(h[r][k], w.y, acc[r][1]); }
+            }
 #pragma unroll
-        for (int j = 0; j < H; ++j) t[j] = sigmoid_f(t[j] + sw[W_GRU_B + 80 + j]);   // r
-        float y[H];
-#pragma unroll
-        for (int j = 0; j < H; ++j) y[j] = sw[W_GRU_B + 100 + j];
-        mv20<60>(y, h, sw + W_GRU_R + 40);
-#pragma unroll
-        for (int j = 0; j < H; ++j) { y[j] *= t[j]; t[j] = sw[W_GRU_B + 40 + j]; }
-        mv20<60>(t, agg, sw + W_GRU_K + 40);
-#pragma unroll
-        for (int j = 0; j < H; ++j) {
-            const float hh = tanhf(t[j] + y[j]);
-            h[j] = z[j] * h[j] + (1.f - z[j]) * hh;
+            for (int r = 0; r < MP_R; ++r) *reinterpret_cast<ulonglong2*>(myb[r] + 4 * jb) = make_ulonglong2(acc[r][0], acc[r][1]);
         }
-        store_row(h_out + r * H, h);
+        // ---- agg = sum over incoming pairs (ascending pair index) of selu(A[first] + B)
+#pragma unroll
+        for (int r = 0; r < MP_R; ++r) {
+            if (!ok[r]) continue;
+            float t[H];
+            load_row(t, myb[r]);
+            int pb, pe; const int* list; int64_t add;
+            idx.seg(row[r], pb, pe, list, add);
+            for (int p = pb; p < pe; ++p) {
+                float a[H];
+                load_row(a, A_in + ((int64_t)list[p] + add) * H);
+#pragma unroll
+                for (int j = 0; j < H; ++j) agg[r][j] += selu_fast(a[j] + t[j]);
+            }
+        }
+        // ---- z = sigmoid(agg.Kz + b0z + h.Rz + b1z)   (GRUCell, reset_after=True)
+#pragma unroll 1
+        for (int jb = 0; jb < H / 4; ++jb) {
+            const ulonglong2 b0 = *reinterpret_cast<const ulonglong2*>(sw + W_GRU_B + 4 * jb);
+            u64 acc[MP_R][2];
+#pragma unroll
+            for (int r = 0; r < MP_R; ++r) { acc[r][0] = b0.x; acc[r][1] = b0.y; }
+#pragma unroll
+            for (int k = 0; k < H; ++k) {
+                const ulonglong2 wk = *reinterpret_cast<const ulonglong2*>(sw + W_GRU_K + k * 60 + 4 * jb);
+                const ulonglong2 wr = *reinterpret_cast<const ulonglong2*>(sw + W_GRU_R + k * 60 + 4 * jb);
+#pragma unroll
+                for (int r = 0; r < MP_R; ++r) {
+                    acc[r][0] = fma2s(agg[r][k], wk.x, acc[r][0]); acc[r][1] = fma2s(agg[r][k], wk.y, acc[r][1]);
+                    acc[r][0] = fma2s(h[r][k], wr.x, acc[r][0]); acc[r][1] = fma2s(h[r][k], wr.y, acc[r][1]);
+                }
+            }
+            const float4 b1 = *reinterpret_cast<const float4*>(sw + W_GRU_B + 60 + 4 * jb);
+#pragma unroll
+            for (int r = 0; r < MP_R; ++r) {
+                float v0, v1, v2, v3;
+                unpack2(acc[r][0], v0, v1); unpack2(acc[r][1], v2, v3);
+                *reinterpret_cast<float4*>(myb[r] + 4 * jb) =
+                    make_float4(sigmoid_fast(v0 + b1.x), sigmoid_fast(v1 + b1.y), sigmoid_fast(v2 + b1.z), sigmoid_fast(v3 + b1.w));
+            }
+        }
+        // ---- r, candidate state and the new h, four outputs at a time
+#pragma unroll 1
+        for (int jb = 0; jb < H / 4; ++jb) {
+            const ulonglong2 br = *reinterpret_cast<const ulonglong2*>(sw + W_GRU_B + 20 + 4 * jb);
+            const ulonglong2 bx = *reinterpret_cast<const ulonglong2*>(sw + W_GRU_B + 40 + 4 * jb);
+            const ulonglong2 by = *reinterpret_cast<const ulonglong2*>(sw + W_GRU_B + 100 + 4 * jb);
+            u64 ar[MP_R][2], ax[MP_R][2], ay[MP_R][2];
+#pragma unroll
+            for (int r = 0; r < MP_R; ++r) { ar[r][0] = br.x; ar[r][1] = br.y; ax[r][0] = bx.x; ax[r][1] = bx.y; ay[r][0] = by.x; ay[r][1] = by.y; }
+#pragma unroll
+            for (int k = 0; k < H; ++k) {
+                const ulonglong2 kr = *reinterpret_cast<const ulonglong2*>(sw + W_GRU_K + k * 60 + 20 + 4 * jb);
+                const ulonglong2 kh = *reinterpret_cast<const ulonglong2*>(sw + W_GRU_K + k * 60 + 40 + 4 * jb);
+                const ulonglong2 rr = *reinterpret_cast<const ulonglong2*>(sw + W_GRU_R + k * 60 + 20 + 4 * jb);
+                const ulonglong2 rh = *reinterpret_cast<const ulonglong2*>(sw + W_GRU_R + k * 60 + 40 + 4 * jb);
+#pragma unroll
+                for (int r = 0; r < MP_R; ++r) {
+                    ar[r][0] = fma2s(agg[r][k], kr.x, ar[r][0]); ar[r][1] = fma2s(agg[r][k], kr.y, ar[r][1]);
+                    ar[r][0] = fma2s(h[r][k], rr.x, ar[r][0]); ar[r][1] = fma2s(h[r][k], rr.y, ar[r][1]);
+                    ax[r][0] = fma2s(agg[r][k], kh.x, ax[r][0]); ax[r][1] = fma2s(agg[r][k], kh.y, ax[r][1]);
+                    ay[r][0] = fma2s(h[r][k], rh.x, ay[r][0]); ay[r][1] = fma2s(h[r][k], rh.y, ay[r][1]);
+                }
+            }
+            const float4 b1r = *reinterpret_cast<const float4*>(sw + W_GRU_B + 80 + 4 * jb);
+#pragma unroll
+            for (int r = 0; r < MP_R; ++r) {
+                float rv[4], xv[4], yv[4];
+                unpack2(ar[r][0], rv[0], rv[1]); unpack2(ar[r][1], rv[2], rv[3]);
+                unpack2(ax[r][0], xv[0], xv[1]); unpack2(ax[r][1], xv[2], xv[3]);
+                unpack2(ay[r][0], yv[0], yv[1]); unpack2(ay[r][1], yv[2], yv[3]);
+                const float4 z = *reinterpret_cast<const float4*>(myb[r] + 4 * jb);
+                const float4 ho = *reinterpret_cast<const float4*>(myh[r] + 4 * jb);
+                const float b1[4] = {b1r.x, b1r.y, b1r.z, b1r.w};
+                const float zz[4] = {z.x, z.y, z.z, z.w};
+                const float hh0[4] = {ho.x, ho.y, ho.z, ho.w};
+                float hn[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float rg = sigmoid_fast(rv[i] + b1[i]);
+                    const float cand = tanh_fast(xv[i] + rg * yv[i]);
+                    hn[i] = zz[i] * hh0[i] + (1.f - zz[i]) * cand;
+                }
+                const float4 o = make_float4(hn[0], hn[1], hn[2], hn[3]);
+                *reinterpret_cast<float4*>(myh[r] + 4 * jb) = o;
+                if (ok[r]) *reinterpret_cast<float4*>(h_out + row[r] * H + 4 * jb) = o;
+            }
+        }
+        // ---- next iteration's message operand A' = h' . Wm[0:20]
         if (!LAST) {
 #pragma unroll
-            for (int j = 0; j < H; ++j) t[j] = 0.f;
-            mv20<H>(t, h, sw + W_MSG_K);
-            store_row(A_out + r * H, t);
+            for (int r = 0; r < MP_R; ++r) load_row(h[r], myh[r]);
+#pragma unroll 1
+            for (int jb = 0; jb < H / 4; ++jb) {
+                u64 acc[MP_R][2];
+#pragma unroll
+                for (int r = 0; r < MP_R; ++r) { acc[r][0] = 0ull; acc[r][1] = 0ull; }
+#pragma unroll
+                for (int k = 0; k < H; ++k) {
+                    const ulonglong2 w = *reinterpret_cast<const ulonglong2*>(sw + W_MSG_K + k * H + 4 * jb);
+#pragma unroll
+                    for (int r = 0; r < MP_R; ++r) { acc[r][0] = fma2s(h[r][k], w.x, acc[r][0]); acc[r][1] = fma2s(h[r][k], w.y, acc[r][1]); }
+                }
+#pragma unroll
+                for (int r = 0; r < MP_R; ++r)
+                    if (ok[r]) *reinterpret_cast<ulonglong2*>(A_out + row[r] * H + 4 * jb) = make_ulonglong2(acc[r][0], acc[r][1]);
+            }
         }
     }
 }
