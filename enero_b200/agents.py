@@ -1,0 +1,96 @@
+"""Agent and episode drivers of script_eval_on_single_topology.py, on the GPU engine.
+
+    PPOMIDDROUTING_SP.pred_action_node_distrib_sp   script :83-129   -> enero_decide_batch
+    play_middRout_games_sp                           script :162-188
+    play_DRL_GNN_sp_hill_climbing_games              script :473-509  -> k_local_search
+    play_sp_hill_climbing_games                      script :437-471  -> k_local_search (mode 1)
+"""
+from __future__ import annotations
+
+import time as tt
+
+import numpy as np
+
+from . import gym_graph
+from .models import ActorModel
+
+SEED = 9
+hparamsDRLSP = {'l2': 0.005, 'dropout_rate': 0.1, 'link_state_dim': 20, 'readout_units': 20,
+                'learning_rate': 0.0002, 'T': 5}
+
+
+class PPOMIDDROUTING_SP:
+    def __init__(self, env_training, actor=None):
+        self.K = env_training.K
+        self.actor = actor if actor is not None else ActorModel(hparamsDRLSP)
+        if not self.actor.built:
+            self.actor.build()
+        self.listQValues = None
+        self.softMaxQValues = None
+
+    def pred_action_node_distrib_sp(self, env, source, destination):
+        """Probabilities over the candidate middlepoints of (source, destination) given the
+        environment's current link loads; one fused launch sequence instead of K' feature
+        builds + ~70 eager TF ops."""
+        t = env.topology
+        loads = np.ascontiguousarray(env.edge_state[:, 0][None])
+        sd = np.array([[source, destination]], dtype=np.int32)
+        bw = np.array([env.TM[source][destination]], dtype=np.float64)
+        logits, probs, nK, action = self.actor.context.decide_batch(t, loads, sd, bw)
+        k = int(nK[0])
+        self.listQValues = logits[:1, :k]
+        self.softMaxQValues = probs[:1, :k]
+        return probs[0, :k], {"num_candidates": k, "logits": logits[0, :k]}
+
+
+def play_middRout_games_sp(tm_id, env_middRout_sp, agent, timesteps):
+    """script_eval_on_single_topology.py:162-188, same return tuple."""
+    demand, source, destination = env_middRout_sp.reset(tm_id)
+    initMaxUti = env_middRout_sp.edgeMaxUti[2]
+    OSPF_init = initMaxUti
+    best_routing = env_middRout_sp.sp_middlepoints_step.copy()
+    list_of_demands_to_change = env_middRout_sp.list_eligible_demands
+    timesteps.append((0, initMaxUti))
+    start = tt.time()
+    time_start_DRL = start
+    while 1:
+        action_dist, _ = agent.pred_action_node_distrib_sp(env_middRout_sp, source, destination)
+        action = np.argmax(action_dist)
+        reward, done, _, demand, source, destination, maxLinkUti, _, _ = env_middRout_sp.step(action, demand, source, destination)
+        if maxLinkUti[2] < initMaxUti:
+            initMaxUti = maxLinkUti[2]
+            best_routing = env_middRout_sp.sp_middlepoints_step.copy()
+            timesteps.append((tt.time() - time_start_DRL, initMaxUti))
+        if done:
+            break
+    end = tt.time()
+    return initMaxUti, end - start, OSPF_init, best_routing, list_of_demands_to_change, time_start_DRL
+
+
+def _make_env15(dataset_folder, topology_name, percentage_demands, K=100):
+    env = gym_graph.make('GraphEnv-v15')
+    env.seed(SEED)
+    env.generate_environment(dataset_folder, topology_name, 100, K, percentage_demands)
+    return env
+
+
+def play_DRL_GNN_sp_hill_climbing_games(tm_id, best_routing, list_of_demands_to_change, timesteps, time_start_DRL,
+                                        dataset_folder, topology_name, percentage_demands=0.15, env=None):
+    """script :473-509 -> (final maxUti, seconds)."""
+    env = env if env is not None else _make_env15(dataset_folder, topology_name, percentage_demands)
+    start = tt.time()
+    env.reset_DRL_hill_sp(tm_id, best_routing, list_of_demands_to_change)
+    final, moves = env.local_search()
+    end = tt.time()
+    for (_, _, _, val) in moves:
+        timesteps.append((end - time_start_DRL, val))
+    return final, end - start
+
+
+def play_sp_hill_climbing_games(tm_id, dataset_folder, topology_name, percentage_demands=0.15, env=None):
+    """script :437-471 -> (final maxUti, seconds)."""
+    env = env if env is not None else _make_env15(dataset_folder, topology_name, percentage_demands)
+    start = tt.time()
+    env.reset_hill_sp(tm_id)
+    final, _ = env.local_search()
+    return final, tt.time() - start

@@ -211,6 +211,53 @@ def read_index(path: str):
     return entries
 
 
+def _block(items, restart_interval=16):
+    out, restarts, prev = bytearray(), [], b""
+    for i, (k, v) in enumerate(items):
+        shared = 0
+        if i % restart_interval == 0:
+            restarts.append(len(out))
+        else:
+            n = min(len(prev), len(k))
+            while shared < n and prev[shared] == k[shared]:
+                shared += 1
+        out += _put_varint(shared) + _put_varint(len(k) - shared) + _put_varint(len(v)) + k[shared:] + v
+        prev = k
+    if not restarts:
+        restarts = [0]
+    for r in restarts:
+        out += struct.pack("<I", r)
+    out += struct.pack("<I", len(restarts))
+    return bytes(out)
+
+
+def _with_trailer(block: bytes) -> bytes:
+    return block + b"\x00" + struct.pack("<I", mask_crc(crc32c(block + b"\x00")))
+
+
+def _short_successor(key: bytes) -> bytes:
+    """leveldb BytewiseComparator::FindShortSuccessor."""
+    for i, c in enumerate(key):
+        if c != 0xFF:
+            return key[:i] + bytes([c + 1])
+    return key
+
+
+def _write_table(items) -> bytes:
+    data = _block(items)
+    out = bytearray(_with_trailer(data))
+    meta_off = len(out)
+    meta = _block([])
+    out += _with_trailer(meta)
+    idx_off = len(out)
+    handle = _put_varint(0) + _put_varint(len(data))
+    idx = _block([(_short_successor(items[-1][0]), handle)])
+    out += _with_trailer(idx)
+    foot = _put_varint(meta_off) + _put_varint(len(meta)) + _put_varint(idx_off) + _put_varint(len(idx))
+    foot += b"\x00" * (40 - len(foot)) + struct.pack("<Q", _MAGIC)
+    return bytes(out + foot)
+
+
 class Bundle:
     """In-memory view of one checkpoint: ``tensors[key] -> np.ndarray | bytes``."""
 
@@ -235,22 +282,56 @@ class Bundle:
             e = _parse_entry(idx[key])
             raw = data[e["offset"]:e["offset"] + e["size"]]
             if e["dtype"] == DT_STRING:
-                # scalar string: varint length, 4-byte masked crc of the lengths, bytes
+                # scalar string: varint length, masked crc32c of the length (as uint32), bytes;
+                # entry crc = crc32c(uint32 length | masked length crc | bytes), masked
                 ln, p = _get_varint(raw, 0)
                 val = bytes(raw[p + 4:p + 4 + ln])
                 if verify:
-                    c = crc32c(struct.pack("<Q", ln)) if False else None  # lengths crc layout is TF-internal
-                    _ = c
+                    lcrc = mask_crc(crc32c(struct.pack("<I", ln)))
+                    if struct.unpack_from("<I", raw, p)[0] != lcrc:
+                        raise ValueError("string length crc mismatch for %s" % key)
+                    c = crc32c(val, crc32c(struct.pack("<I", lcrc), crc32c(struct.pack("<I", ln))))
+                    if mask_crc(c) != e["crc32c"]:
+                        raise ValueError("crc32c mismatch for %s" % key)
             else:
                 if verify and mask_crc(crc32c(raw)) != e["crc32c"]:
                     raise ValueError("crc32c mismatch for %s" % key)
                 val = np.frombuffer(raw, dtype=_NP_OF[e["dtype"]]).reshape(e["shape"]).copy()
             b.tensors[key] = val
             b.order.append(key)
-        b._raw_string_entries = {k: (idx[k], data[_parse_entry(idx[k])["offset"]:
-                                                 _parse_entry(idx[k])["offset"] + _parse_entry(idx[k])["size"]])
-                                 for k in idx if _parse_entry(idx[k])["dtype"] == DT_STRING}
         return b
+
+    # ---- writing -----------------------------------------------------------
+    def save(self, prefix: str) -> None:
+        """Writes <prefix>.index and <prefix>.data-00000-of-00001 (single shard).  Data is laid
+        out in ``self.order`` (the shipped files use object-graph traversal order); the index
+        is a one-data-block SSTable with LevelDB prefix compression (restart interval 16)."""
+        data = bytearray()
+        entries = {}
+        for key in self.order:
+            val = self.tensors[key]
+            off = len(data)
+            if isinstance(val, (bytes, bytearray)):
+                ln = len(val)
+                lcrc = mask_crc(crc32c(struct.pack("<I", ln)))
+                blob = _put_varint(ln) + struct.pack("<I", lcrc) + bytes(val)
+                c = crc32c(bytes(val), crc32c(struct.pack("<I", lcrc), crc32c(struct.pack("<I", ln))))
+                entries[key] = _encode_entry(DT_STRING, (), off, len(blob), mask_crc(c))
+            else:
+                arr = np.asarray(val)           # (ascontiguousarray would turn scalars into shape (1,))
+                blob = arr.astype(arr.dtype.newbyteorder("<"), copy=False).tobytes()
+                entries[key] = _encode_entry(_DT_OF[np.dtype(arr.dtype.name)], arr.shape, off, len(blob),
+                                             mask_crc(crc32c(blob)))
+            data += blob
+        items = [(b"", b"\x08\x01\x1a\x02\x08\x01")] + [(k.encode(), entries[k]) for k in sorted(entries)]
+        index = _write_table(items)
+        d = os.path.dirname(prefix)
+        if d:
+            os.makedirs(d, exist_ok=True)
+        with open(prefix + ".data-00000-of-00001", "wb") as fp:
+            fp.write(bytes(data))
+        with open(prefix + ".index", "wb") as fp:
+            fp.write(index)
 
     # ---- ENERO-specific accessors -----------------------------------------
     def model_weights(self):
@@ -278,3 +359,75 @@ def load_actor_weights(prefix: str):
     if not os.path.isfile(prefix + ".index"):
         raise FileNotFoundError(prefix + ".index")
     return Bundle.load(prefix).model_weights()
+
+
+# --------------------------------------------------------------------------
+# tf.train.Checkpoint look-alike for (model=myModel, optimizer=Adam)
+# --------------------------------------------------------------------------
+# order of the tensors inside the shipped .data file (object-graph traversal order)
+_DATA_MODEL_ORDER = (2, 3, 4, 0, 1, 5, 6, 7, 8, 9, 10)      # indices into MODEL_KEYS
+_SCALARS = (("save_counter", np.int64), ("optimizer/iter", np.int64), ("optimizer/beta_1", np.float32),
+            ("optimizer/beta_2", np.float32), ("optimizer/decay", np.float32),
+            ("optimizer/learning_rate", np.float32))
+
+
+def _object_graph_blob() -> bytes:
+    here = os.path.dirname(os.path.abspath(__file__))
+    with open(os.path.join(here, "data", "object_graph_model_optimizer.bin"), "rb") as fp:
+        return fp.read()
+
+
+class Checkpoint:
+    """``tf.train.Checkpoint(model=..., optimizer=...)`` for ENERO's actor / critic
+    (train_Enero_3top_script.py:449-457,714-715; script_eval_on_single_topology.py:607-609).
+
+    ``model`` needs get_weights()/set_weights() (11 tensors, Keras variable order);
+    ``optimizer`` is an enero_b200.optim.Adam (slots keyed by model)."""
+
+    def __init__(self, model=None, optimizer=None):
+        self.model, self.optimizer = model, optimizer
+        self.save_counter = 0
+
+    def restore(self, save_path: str):
+        b = Bundle.load(save_path)
+        if self.model is not None:
+            self.model.set_weights(b.model_weights())
+        sc = b.optimizer_scalars()
+        self.save_counter = sc["save_counter"]
+        if self.optimizer is not None:
+            # restore wins over the constructor's hyper-parameters (SURVEY quirk Q6)
+            self.optimizer.iterations = sc["iter"]
+            self.optimizer.learning_rate = np.float32(sc["learning_rate"])
+            self.optimizer.beta_1 = np.float32(sc["beta_1"])
+            self.optimizer.beta_2 = np.float32(sc["beta_2"])
+            self.optimizer.decay = np.float32(sc["decay"])
+            if self.model is not None:
+                self.optimizer.set_slots(self.model, b.adam_slots("m"), b.adam_slots("v"))
+        return self
+
+    def save(self, file_prefix: str) -> str:
+        self.save_counter += 1
+        path = "%s-%d" % (file_prefix, self.save_counter)
+        b = Bundle()
+        opt = self.optimizer
+        vals = {"save_counter": self.save_counter, "optimizer/iter": opt.iterations,
+                "optimizer/beta_1": opt.beta_1, "optimizer/beta_2": opt.beta_2,
+                "optimizer/decay": opt.decay, "optimizer/learning_rate": opt.learning_rate}
+        for name, dt in _SCALARS:
+            b.tensors[name + _VAL] = np.array(vals[name], dtype=dt)
+            b.order.append(name + _VAL)
+        w = self.model.get_weights()
+        m, v = opt.get_slots(self.model)
+        for suffix, tensors in ((_VAL, w), (_SLOT % "m", m), (_SLOT % "v", v)):
+            for i in _DATA_MODEL_ORDER:
+                key = MODEL_KEYS[i] + suffix
+                b.tensors[key] = np.asarray(tensors[i], dtype=np.float32).reshape(MODEL_SHAPES[i])
+                b.order.append(key)
+        b.tensors[OBJECT_GRAPH_KEY] = _object_graph_blob()
+        b.order.append(OBJECT_GRAPH_KEY)
+        b.save(path)
+        d = os.path.dirname(path)
+        name = os.path.basename(path)
+        with open(os.path.join(d, "checkpoint"), "w") as fp:
+            fp.write('model_checkpoint_path: "%s"\nall_model_checkpoint_paths: "%s"\n' % (name, name))
+        return path

@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "enero_internal.h"
@@ -86,14 +87,24 @@ extern "C" int enero_ctx_create(int device, enero_ctx** out) {
         CUDA_TRY(cudaMalloc(&c->w[i], sizeof(float) * (ENERO_NPARAMS + 3)));
         CUDA_TRY(cudaMemset(c->w[i], 0, sizeof(float) * (ENERO_NPARAMS + 3)));
     }
-    CUDA_TRY(cudaFuncSetAttribute(k_mp_iter<IdxExplicit, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MP_SMEM_BYTES));
-    CUDA_TRY(cudaFuncSetAttribute(k_mp_iter<IdxExplicit, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MP_SMEM_BYTES));
-    CUDA_TRY(cudaFuncSetAttribute(k_mp_iter<IdxTopo, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MP_SMEM_BYTES));
-    CUDA_TRY(cudaFuncSetAttribute(k_mp_iter<IdxTopo, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MP_SMEM_BYTES));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_iter[0][0], k_mp_iter<IdxExplicit, false>, MP_TPB, MP_SMEM_BYTES));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_iter[0][1], k_mp_iter<IdxExplicit, true>, MP_TPB, MP_SMEM_BYTES));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_iter[1][0], k_mp_iter<IdxTopo, false>, MP_TPB, MP_SMEM_BYTES));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_iter[1][1], k_mp_iter<IdxTopo, true>, MP_TPB, MP_SMEM_BYTES));
+    {
+        int r = ENERO_OK;
+        auto setup = [&](auto kern, int& occ) {
+            if (r != ENERO_OK) return;
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MP_SMEM_BYTES) != cudaSuccess ||
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, MP_TPB, MP_SMEM_BYTES) != cudaSuccess) {
+                enero_set_error(std::string("k_mp_iter setup: ") + cudaGetErrorString(cudaGetLastError()));
+                r = ENERO_ERR_CUDA;
+            }
+        };
+        setup(k_mp_iter<IdxExplicit, false, 20>, c->occ_iter[0][0]);
+        setup(k_mp_iter<IdxExplicit, true, 20>, c->occ_iter[0][1]);
+        setup(k_mp_iter<IdxTopo, false, 20>, c->occ_iter[1][0]);
+        setup(k_mp_iter<IdxTopo, true, 20>, c->occ_iter[1][1]);
+        int tmp = 0;
+        setup(k_mp_iter<IdxTopo, false, 3>, tmp);
+        if (r != ENERO_OK) return r;
+    }
     *out = c;
     return ENERO_OK;
 }
@@ -201,8 +212,9 @@ static TopoView view_of(const enero_topo* t) {
 }
 
 // ---- message passing driver ---------------------------------------------------------------
+// sparse_first: the rows of iteration 0 have at most 3 non-zero leading columns (fused feature path)
 template <class IDX>
-static int run_iterations(enero_ctx* c, const IDX& idx, int which, int T, int64_t rows, int idx_kind) {
+static int run_iterations(enero_ctx* c, const IDX& idx, int which, int T, int64_t rows, int idx_kind, bool sparse_first = false) {
     const int64_t ntiles = (rows + MP_ROWS - 1) / MP_ROWS;
     for (int it = 0; it < T; ++it) {
         const bool last = (it == T - 1);
@@ -217,8 +229,11 @@ static int run_iterations(enero_ctx* c, const IDX& idx, int which, int T, int64_
             CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
             CUDA_TRY(cudaEventRecord(e0, c->stream));
         }
-        if (last) k_mp_iter<IDX, true><<<grid, MP_TPB, MP_SMEM_BYTES, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles);
-        else k_mp_iter<IDX, false><<<grid, MP_TPB, MP_SMEM_BYTES, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles);
+        if (last) k_mp_iter<IDX, true, 20><<<grid, MP_TPB, MP_SMEM_BYTES, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles);
+        else if (it == 0 && sparse_first) {
+            if constexpr (std::is_same<IDX, IdxTopo>::value)
+                k_mp_iter<IdxTopo, false, 3><<<grid, MP_TPB, MP_SMEM_BYTES, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles);
+        } else k_mp_iter<IDX, false, 20><<<grid, MP_TPB, MP_SMEM_BYTES, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles);
         LAUNCH_CHECK(c);
         if (c->prof) { CUDA_TRY(cudaEventRecord(e1, c->stream)); c->prof_ev.emplace_back(e0, e1); }
     }
@@ -310,7 +325,7 @@ static int decide_dev(enero_ctx* c, enero_topo* t, int B, const double* loads, c
     k_features<<<(int)((rows + MP_TPB - 1) / MP_TPB), MP_TPB, 0, st>>>(tv, B, RPD, sd, bw, nK, c->util.as<float>(), c->w[ENERO_ACTOR],
                                                                      c->h[0].as<float>(), c->A[0].as<float>()); LAUNCH_CHECK(c);
     IdxTopo idx{rows, d.E, d.off_f, d.off_s, RPD, nK, d.in_off, d.in_first};
-    TRY(run_iterations(c, idx, ENERO_ACTOR, T, rows, 1));
+    TRY(run_iterations(c, idx, ENERO_ACTOR, T, rows, 1, T > 1));
     GraphsTopo gr{B, d.Kmax, d.E, RPD, nK};
     k_readout<GraphsTopo><<<(B * d.Kmax + 3) / 4, 128, 0, st>>>(gr, c->w[ENERO_ACTOR], c->h[T & 1].as<float>(), logits); LAUNCH_CHECK(c);
     k_policy<<<(B + 3) / 4, 128, 0, st>>>(B, d.Kmax, nK, logits, probs, action); LAUNCH_CHECK(c);
@@ -338,7 +353,7 @@ static int value_dev(enero_ctx* c, enero_topo* t, int B, const double* loads, fl
     k_features_critic<<<(int)((rows + MP_TPB - 1) / MP_TPB), MP_TPB, 0, st>>>(tv, B, c->util.as<float>(), c->w[ENERO_CRITIC],
                                                                             c->h[0].as<float>(), c->A[0].as<float>()); LAUNCH_CHECK(c);
     IdxTopo idx{rows, d.E, d.off_f, d.off_s, d.E, c->ones.as<int>(), d.in_off, d.in_first};
-    TRY(run_iterations(c, idx, ENERO_CRITIC, T, rows, 1));
+    TRY(run_iterations(c, idx, ENERO_CRITIC, T, rows, 1, T > 1));
     GraphsTopo gr{B, 1, d.E, d.E, c->ones.as<int>()};
     k_readout<GraphsTopo><<<(B + 3) / 4, 128, 0, st>>>(gr, c->w[ENERO_CRITIC], c->h[T & 1].as<float>(), values); LAUNCH_CHECK(c);
     return ENERO_OK;

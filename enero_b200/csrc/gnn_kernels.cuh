@@ -139,7 +139,10 @@ constexpr int MP_ROWS = MP_TPB * MP_R;                       // rows per tile
 constexpr int MP_SMEM_FLOATS = W_MP_FLOATS + 2 * MP_ROWS * H;  // weights + h slots + B/z slots
 constexpr size_t MP_SMEM_BYTES = sizeof(float) * MP_SMEM_FLOATS;
 
-template <class IDX, bool LAST>
+// KH = number of leading link-state columns that can be non-zero on entry: 20 in general, 3 for the
+// first iteration of the fused decision path, whose input rows are [util, cap, mark, 0 x 17]
+// (every h-side mat-vec then needs 3 instead of 20 k-steps; adding exact zeros changes no bit).
+template <class IDX, bool LAST, int KH>
 __global__ void __launch_bounds__(MP_TPB, 3)
 k_mp_iter(const IDX idx, const float* __restrict__ wflat, const float* __restrict__ h_in,
           const float* __restrict__ A_in, float* __restrict__ h_out, float* __restrict__ A_out,
@@ -180,7 +183,7 @@ k_mp_iter(const IDX idx, const float* __restrict__ wflat, const float* __restric
 #pragma unroll
             for (int r = 0; r < MP_R; ++r) { acc[r][0] = b0.x; acc[r][1] = b0.y; }
 #pragma unroll
-            for (int k = 0; k < H; ++k) {
+            for (int k = 0; k < KH; ++k) {
                 const ulonglong2 w = *reinterpret_cast<const ulonglong2*>(sw + W_MSG_K + H * H + k * H + 4 * jb);
 #pragma unroll
                 for (int r = 0; r < MP_R; ++r) { acc[r][0] = fma2s(h[r][k], w.x, acc[r][0]); acc[r][1] = fma2s(h[r][k], w.y, acc[r][1]); }
@@ -213,11 +216,12 @@ k_mp_iter(const IDX idx, const float* __restrict__ wflat, const float* __restric
 #pragma unroll
             for (int k = 0; k < H; ++k) {
                 const ulonglong2 wk = *reinterpret_cast<const ulonglong2*>(sw + W_GRU_K + k * 60 + 4 * jb);
-                const ulonglong2 wr = *reinterpret_cast<const ulonglong2*>(sw + W_GRU_R + k * 60 + 4 * jb);
 #pragma unroll
-                for (int r = 0; r < MP_R; ++r) {
-                    acc[r][0] = fma2s(agg[r][k], wk.x, acc[r][0]); acc[r][1] = fma2s(agg[r][k], wk.y, acc[r][1]);
-                    acc[r][0] = fma2s(h[r][k], wr.x, acc[r][0]); acc[r][1] = fma2s(h[r][k], wr.y, acc[r][1]);
+                for (int r = 0; r < MP_R; ++r) { acc[r][0] = fma2s(agg[r][k], wk.x, acc[r][0]); acc[r][1] = fma2s(agg[r][k], wk.y, acc[r][1]); }
+                if (k < KH) {
+                    const ulonglong2 wr = *reinterpret_cast<const ulonglong2*>(sw + W_GRU_R + k * 60 + 4 * jb);
+#pragma unroll
+                    for (int r = 0; r < MP_R; ++r) { acc[r][0] = fma2s(h[r][k], wr.x, acc[r][0]); acc[r][1] = fma2s(h[r][k], wr.y, acc[r][1]); }
                 }
             }
             const float4 b1 = *reinterpret_cast<const float4*>(sw + W_GRU_B + 60 + 4 * jb);
@@ -242,14 +246,19 @@ k_mp_iter(const IDX idx, const float* __restrict__ wflat, const float* __restric
             for (int k = 0; k < H; ++k) {
                 const ulonglong2 kr = *reinterpret_cast<const ulonglong2*>(sw + W_GRU_K + k * 60 + 20 + 4 * jb);
                 const ulonglong2 kh = *reinterpret_cast<const ulonglong2*>(sw + W_GRU_K + k * 60 + 40 + 4 * jb);
-                const ulonglong2 rr = *reinterpret_cast<const ulonglong2*>(sw + W_GRU_R + k * 60 + 20 + 4 * jb);
-                const ulonglong2 rh = *reinterpret_cast<const ulonglong2*>(sw + W_GRU_R + k * 60 + 40 + 4 * jb);
 #pragma unroll
                 for (int r = 0; r < MP_R; ++r) {
                     ar[r][0] = fma2s(agg[r][k], kr.x, ar[r][0]); ar[r][1] = fma2s(agg[r][k], kr.y, ar[r][1]);
-                    ar[r][0] = fma2s(h[r][k], rr.x, ar[r][0]); ar[r][1] = fma2s(h[r][k], rr.y, ar[r][1]);
                     ax[r][0] = fma2s(agg[r][k], kh.x, ax[r][0]); ax[r][1] = fma2s(agg[r][k], kh.y, ax[r][1]);
-                    ay[r][0] = fma2s(h[r][k], rh.x, ay[r][0]); ay[r][1] = fma2s(h[r][k], rh.y, ay[r][1]);
+                }
+                if (k < KH) {
+                    const ulonglong2 rr = *reinterpret_cast<const ulonglong2*>(sw + W_GRU_R + k * 60 + 20 + 4 * jb);
+                    const ulonglong2 rh = *reinterpret_cast<const ulonglong2*>(sw + W_GRU_R + k * 60 + 40 + 4 * jb);
+#pragma unroll
+                    for (int r = 0; r < MP_R; ++r) {
+                        ar[r][0] = fma2s(h[r][k], rr.x, ar[r][0]); ar[r][1] = fma2s(h[r][k], rr.y, ar[r][1]);
+                        ay[r][0] = fma2s(h[r][k], rh.x, ay[r][0]); ay[r][1] = fma2s(h[r][k], rh.y, ay[r][1]);
+                    }
                 }
             }
             const float4 b1r = *reinterpret_cast<const float4*>(sw + W_GRU_B + 80 + 4 * jb);

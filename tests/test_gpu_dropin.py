@@ -1,0 +1,115 @@
+"""Drop-in boundary on the GPU: the reference's own usage pattern (gym.make -> generate_environment
+-> checkpoint.restore -> play_middRout_games_sp -> hill climbing; script_eval_on_single_topology.py:
+599-623) against the reference-recorded goldens."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import CASE_NAMES, GOLDEN, load_case
+
+pytestmark = pytest.mark.gpu
+
+hparams = {'l2': 0.005, 'dropout_rate': 0.1, 'link_state_dim': 20, 'readout_units': 20, 'learning_rate': 0.0002, 'T': 5}
+
+
+def _dataset(case, folder):
+    """re-create <folder>/<name>.graph and TM/<name>.<id>.demands from the fixture"""
+    from enero_b200 import datasets as ds
+    os.makedirs(os.path.join(folder, "TM"), exist_ok=True)
+    name = case["name"]
+    open(os.path.join(folder, name + ".graph"), "w").write(case["graph_text"])
+    for tm_id, tm in case["tms"].items():
+        ds.write_demands_file(os.path.join(folder, "TM", "%s.%s.demands" % (name, tm_id)), np.array(tm))
+    if case["sp_seeded"]:
+        json.dump(case["topo"]["paths"], open(os.path.join(folder, "shortest_paths.json"), "w"))
+    return name
+
+
+@pytest.fixture(scope="module")
+def actor():
+    import enero_b200.actorPPOmiddR as actor_mod
+    from enero_b200.checkpoint import Checkpoint
+    from enero_b200.optim import Adam
+    a = actor_mod.myModel(hparams, None, None)
+    a.build()
+    Checkpoint(model=a, optimizer=Adam(learning_rate=2e-4, beta_1=0.9, epsilon=1e-5)).restore(os.path.join(GOLDEN, "ckpt_ACT-1835"))
+    return a
+
+
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_eval_script_flow(name, actor, tmp_path):
+    from enero_b200 import agents, gym_graph
+    case = load_case(name)
+    folder = str(tmp_path)
+    topo_name = _dataset(case, folder)
+    env = gym_graph.make('GraphEnv-v16')
+    env.seed(9)
+    env.generate_environment(folder, topo_name, 100, 100, 0.15)
+    env.top_K_critical_demands = True
+    g = case["topo"]
+    assert (env.numNodes, env.numEdges, env.K, env.firstTrueSize) == (g["N"], g["E"], g["K"], len(g["first"]))
+    assert env.src_dst_k_middlepoints == g["mids"]
+    assert np.asarray(env.first).tolist() == g["first"] and np.asarray(env.second).tolist() == g["second"]
+    agent = agents.PPOMIDDROUTING_SP(env, actor)
+    for ep in case["episodes"]:
+        timesteps = []
+        best, _, ospf, best_routing, demands, t0 = agents.play_middRout_games_sp(ep["tm_id"], env, agent, timesteps)
+        assert (best, ospf) == (ep["best"], ep["ospf"])
+        assert [[int(k.split(":")[0]), int(k.split(":")[1]), m] for k, m in best_routing.items()] == ep["best_routing"]
+        assert [[s, d, float(b)] for s, d, b in demands] == ep["reset"]["elig"]
+        final, _ = agents.play_DRL_GNN_sp_hill_climbing_games(ep["tm_id"], best_routing, demands, timesteps, t0, folder, topo_name)
+        assert final == ep["ls"]["final"]
+        assert timesteps[-1][1] == ep["ls"]["final"] or not ep["ls"]["moves"]
+        if "plain_hill_final" in ep:
+            fin_h, _ = agents.play_sp_hill_climbing_games(ep["tm_id"], folder, topo_name)
+            assert fin_h == ep["plain_hill_final"]
+
+
+def test_reference_style_agent_through_myModel_call(actor, tmp_path):
+    """The reference agent's own feature plumbing (mark_action_sp, old_cummax offsets, concat;
+    script :83-129) feeding actor(link_state, graph_id, first, second, num_edges): logits within
+    1e-5 (norm-wise) of the recorded ones, greedy actions identical, env.step 9-tuples bit-exact."""
+    from enero_b200 import gym_graph
+    case = load_case("tiny12")
+    folder = str(tmp_path)
+    topo_name = _dataset(case, folder)
+    env = gym_graph.make('GraphEnv-v16')
+    env.seed(9)
+    env.generate_environment(folder, topo_name, 100, 100, 0.15)
+    env.top_K_critical_demands = True
+    ep = case["episodes"][0]
+    demand, source, destination = env.reset(ep["tm_id"])
+    assert (float(demand), source, destination) == (ep["reset"]["demand"], ep["reset"]["s"], ep["reset"]["d"])
+    for stp, dc in zip(ep["steps"], ep["decisions"]):
+        mids = env.src_dst_k_middlepoints[str(source) + ':' + str(destination)]
+        feats = []
+        for m in mids:
+            env.mark_action_sp(source, m, source, destination)
+            if m != destination:
+                env.mark_action_sp(m, destination, source, destination)
+            ls = np.zeros((env.numEdges, 20), dtype=np.float32)
+            ls[:, 0] = np.divide(env.edge_state[:, 0], env.edge_state[:, 1]).astype(np.float32)
+            ls[:, 1] = env.link_capacity_feature
+            ls[:, 2] = env.edge_state[:, 2].astype(np.float32)
+            feats.append(ls)
+            env.edge_state[:, 2] = 0
+        first = np.asarray(env.first)[:env.firstTrueSize]
+        second = np.asarray(env.second)[:env.firstTrueSize]
+        offs_f = [k * (int(first.max()) + 1) for k in range(len(feats))]
+        offs_s = [k * (int(second.max()) + 1) for k in range(len(feats))]
+        r = actor(np.concatenate(feats), np.repeat(np.arange(len(feats)), env.numEdges),
+                  np.concatenate([first + o for o in offs_f]), np.concatenate([second + o for o in offs_s]),
+                  env.numEdges * len(feats), training=False)
+        assert r.shape == (len(mids), 1)
+        want = np.array(dc["logits"])
+        assert np.abs(r.reshape(-1) - want).max() <= 1e-5 * max(np.abs(want).max(), 1e-2)
+        action = int(np.argmax(r.reshape(-1)))
+        assert action == stp["action"]
+        reward, done, _, demand, source, destination, mx, _, std = env.step(action, demand, source, destination)
+        assert (float(reward), done, [float(demand), source, destination]) == (stp["reward"], stp["done"], stp["next"])
+        assert [mx[0], mx[1], float(mx[2])] == stp["edge_max"] and float(std) == stp["std"]
+        assert env.edge_state[:, 0].tolist() == stp["loads_after"]
+        if done:
+            break

@@ -1,0 +1,37 @@
+#!/usr/bin/env python
+"""Summarise an .ncu-rep (ncu --set full) into a small CSV for profiles/:  python tools/ncu_summary.py rep out.csv"""
+import csv
+import subprocess
+import sys
+
+KEYS = ['Kernel Name', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
+        'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size', 'launch__occupancy_limit_registers',
+        'launch__occupancy_limit_shared_mem', 'sm__warps_active.avg.pct_of_peak_sustained_active',
+        'smsp__issue_active.avg.pct_of_peak_sustained_active', 'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active',
+        'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed',
+        'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed',
+        'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'lts__t_sector_hit_rate.pct', 'l1tex__t_sector_hit_rate.pct',
+        'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
+        'smsp__thread_inst_executed_per_inst_executed.ratio', 'sm__cycles_elapsed.max',
+        'smsp__inst_executed.sum', 'sm__inst_executed.sum']
+STALLS = 'smsp__pcsamp_warps_issue_stalled_'
+
+
+def main(rep, out):
+    raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr = rows[0]
+    keys = [k for k in KEYS if k in hdr] + sorted(k for k in hdr if k.startswith(STALLS) and not k.endswith('_not_issued'))
+    with open(out, 'w', newline='') as fp:
+        w = csv.writer(fp)
+        w.writerow(['metric', 'unit'] + ['launch%d' % i for i in range(1, len(rows) - 1)])
+        for k in keys:
+            i = hdr.index(k)
+            w.writerow([k] + [r[i] for r in rows[1:]])
+    print(open(out).read())
+
+
+if __name__ == '__main__':
+    main(sys.argv[1], sys.argv[2])
