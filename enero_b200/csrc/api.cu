@@ -18,51 +18,7 @@
 
 using namespace enero;
 
-#define CUDA_TRY(expr)                                                                         \
-    do {                                                                                       \
-        cudaError_t _e = (expr);                                                               \
-        if (_e != cudaSuccess) {                                                               \
-            enero_set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));               \
-            return ENERO_ERR_CUDA;                                                             \
-        }                                                                                      \
-    } while (0)
-#define TRY(expr) do { int _r = (expr); if (_r != ENERO_OK) return _r; } while (0)
-
-static int fail(int code, const std::string& m) { enero_set_error(m); return code; }
-
-struct DevBuf {
-    void* p = nullptr; size_t cap = 0;
-    int ensure(size_t bytes) {
-        if (bytes <= cap) return ENERO_OK;
-        if (p) cudaFree(p);
-        p = nullptr; cap = 0;
-        size_t want = bytes + bytes / 4 + 256;
-        cudaError_t e = cudaMalloc(&p, want);
-        if (e != cudaSuccess) { enero_set_error(std::string("cudaMalloc: ") + cudaGetErrorString(e)); return ENERO_ERR_CUDA; }
-        cap = want;
-        return ENERO_OK;
-    }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
-};
-
-struct enero_ctx {
-    int device = 0;
-    int num_sms = 0;
-    cudaStream_t stream = nullptr;
-    float* w[2] = {nullptr, nullptr};
-    int64_t launches = 0;
-    // scratch of the GNN engine
-    DevBuf h[2], A[2], util, nK, logits, probs, action, in_loads, in_sd, in_bw, ones;
-    DevBuf x_ls, x_gid, x_first, x_second, x_cnt, x_off, x_cur, x_slot, x_src, x_goff, x_err, x_out;
-    int occ_iter[2][2] = {{0, 0}, {0, 0}};   // [indexer][last] resident CTAs/SM of k_mp_iter
-    // optional per-launch CUDA-event timing of the dominant kernel (bench.py roofline leg)
-    bool prof = false;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_ev;
-};
-
-#define LAUNCH_CHECK(ctx)                                                     \
-    do { (ctx)->launches++; CUDA_TRY(cudaGetLastError()); } while (0)
+#include "ctx.cuh"
 
 // ---------------------------------------------------------------------------------------
 extern "C" int enero_device_count(void) {
@@ -84,8 +40,10 @@ extern "C" int enero_ctx_create(int device, enero_ctx** out) {
     c->num_sms = prop.multiProcessorCount;
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {
-        CUDA_TRY(cudaMalloc(&c->w[i], sizeof(float) * (ENERO_NPARAMS + 3)));
-        CUDA_TRY(cudaMemset(c->w[i], 0, sizeof(float) * (ENERO_NPARAMS + 3)));
+        for (float** p : {&c->w[i], &c->grad[i], &c->adam_m[i], &c->adam_v[i]}) {
+            CUDA_TRY(cudaMalloc(p, sizeof(float) * (ENERO_NPARAMS + 3)));
+            CUDA_TRY(cudaMemset(*p, 0, sizeof(float) * (ENERO_NPARAMS + 3)));
+        }
     }
     {
         int r = ENERO_OK;
@@ -113,11 +71,7 @@ extern "C" int enero_ctx_destroy(enero_ctx* c) {
     if (!c) return ENERO_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    for (DevBuf* b : {&c->h[0], &c->h[1], &c->A[0], &c->A[1], &c->util, &c->nK, &c->logits, &c->probs, &c->action,
-                      &c->in_loads, &c->in_sd, &c->in_bw, &c->ones, &c->x_ls, &c->x_gid, &c->x_first, &c->x_second,
-                      &c->x_cnt, &c->x_off, &c->x_cur, &c->x_slot, &c->x_src, &c->x_goff, &c->x_err, &c->x_out})
-        b->release();
-    for (int i = 0; i < 2; ++i) cudaFree(c->w[i]);
+    for (int i = 0; i < 2; ++i) { cudaFree(c->w[i]); cudaFree(c->grad[i]); cudaFree(c->adam_m[i]); cudaFree(c->adam_v[i]); }
     cudaStreamDestroy(c->stream);
     delete c;
     return ENERO_OK;
@@ -182,7 +136,7 @@ static void topo_free_dev(enero_topo* t) {
     cudaSetDevice(t->dev_id);
     TopoDev& d = t->dev;
     cudaFree(d.cap); cudaFree(d.capf); cudaFree(d.in_off); cudaFree(d.in_first);
-    cudaFree(d.sp_off); cudaFree(d.sp_edge); cudaFree(d.mid_off); cudaFree(d.mids);
+    cudaFree(d.sp_off); cudaFree(d.sp_edge); cudaFree(d.mid_off); cudaFree(d.mids); cudaFree(d.out_off); cudaFree(d.out_second);
     d = TopoDev();
     t->dev_id = -1;
 }
@@ -203,6 +157,7 @@ extern "C" int enero_topo_upload(enero_ctx* c, enero_topo* t) {
     TRY(upload_vec(&d.in_off, t->in_off)); TRY(upload_vec(&d.in_first, t->in_first));
     TRY(upload_vec(&d.sp_off, t->sp_off)); TRY(upload_vec(&d.sp_edge, t->sp_edge));
     TRY(upload_vec(&d.mid_off, t->mid_off)); TRY(upload_vec(&d.mids, t->mids));
+    TRY(upload_vec(&d.out_off, t->out_off)); TRY(upload_vec(&d.out_second, t->out_second));
     t->dev_id = c->device;
     return ENERO_OK;
 }
@@ -457,11 +412,6 @@ extern "C" int enero_batch_destroy(enero_batch* b) {
     if (!b) return ENERO_OK;
     cudaSetDevice(b->c->device);
     cudaStreamSynchronize(b->c->stream);
-    for (DevBuf* x : {&b->tm, &b->loads, &b->mid_cur, &b->elig, &b->elig_len, &b->it, &b->cur, &b->cur_bw, &b->done, &b->steps,
-                      &b->max_uti, &b->max_edge, &b->best, &b->best_step, &b->ospf, &b->h_action, &b->h_reward, &b->h_max,
-                      &b->last_reward, &b->logits, &b->probs, &b->nK, &b->action, &b->values, &b->ls_loads, &b->ls_mid,
-                      &b->snap, &b->ls_elig, &b->ls_elig_len, &b->ls_val, &b->ls_nmoves, &b->ls_moves, &b->ls_move_val, &b->ls_max_edge})
-        x->release();
     delete b;
     return ENERO_OK;
 }

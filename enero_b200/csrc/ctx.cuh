@@ -1,0 +1,67 @@
+// Shared host-side definitions of the CUDA translation units (api.cu, train.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "enero_internal.h"
+
+#define CUDA_TRY(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            enero_set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));               \
+            return ENERO_ERR_CUDA;                                                             \
+        }                                                                                      \
+    } while (0)
+#define TRY(expr) do { int _r = (expr); if (_r != ENERO_OK) return _r; } while (0)
+
+static inline int fail(int code, const std::string& m) { enero_set_error(m); return code; }
+
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return ENERO_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { enero_set_error(std::string("cudaMalloc: ") + cudaGetErrorString(e)); return ENERO_ERR_CUDA; }
+        cap = want;
+        return ENERO_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct enero_ctx {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    float* w[2] = {nullptr, nullptr};
+    int64_t launches = 0;
+    // scratch of the GNN engine
+    DevBuf h[2], A[2], util, nK, logits, probs, action, in_loads, in_sd, in_bw, ones;
+    DevBuf x_ls, x_gid, x_first, x_second, x_cnt, x_off, x_cur, x_slot, x_src, x_goff, x_err, x_out;
+    int occ_iter[2][2] = {{0, 0}, {0, 0}};   // [indexer][last] resident CTAs/SM of k_mp_iter
+    // optional per-launch CUDA-event timing of the dominant kernel (bench.py roofline leg)
+    bool prof = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_ev;
+    // training state (train.cu): flat gradients and Adam slots of actor [0] and critic [1]
+    float* grad[2] = {nullptr, nullptr};
+    float* adam_m[2] = {nullptr, nullptr};
+    float* adam_v[2] = {nullptr, nullptr};
+    DevBuf t_rows[16];       // h_0..h_T, A_0..A_{T-1} of a training forward
+    DevBuf t_agg, t_G, t_dB, t_dA, t_B, t_dagg, t_dh[2], t_V, t_dlogit, t_partials, t_iters;
+    DevBuf t_loads, t_sd, t_bw, t_action, t_oldp, t_adv, t_ret, t_logits, t_values, t_nK, t_loss, t_ent, t_closs, t_scalar;
+};
+
+#define LAUNCH_CHECK(ctx)                                                     \
+    do { (ctx)->launches++; CUDA_TRY(cudaGetLastError()); } while (0)
+

@@ -29,6 +29,8 @@ struct TopoDev {               // device mirrors (all int32 unless noted)
     int* sp_edge = nullptr;       // [sp_total]
     int* mid_off = nullptr;       // [N*N+1]
     int* mids = nullptr;          // [mid_total]
+    int* out_off = nullptr;       // [E+1] CSR by `first` (pairs leaving a link), pair order
+    int* out_second = nullptr;    // [P]
 };
 
 struct enero_topo {
@@ -42,6 +44,7 @@ struct enero_topo {
     double max_cap = 0;
     std::vector<int> first, second;             // [P]
     std::vector<int> in_off, in_first;          // CSR by second
+    std::vector<int> out_off, out_second;       // CSR by first
     std::vector<int> sp_off, sp_edge;           // SP as edge lists
     std::vector<int> sp_node_off, sp_node;      // SP as node lists
     std::vector<int> mid_off, mids;

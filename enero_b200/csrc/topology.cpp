@@ -197,6 +197,13 @@ extern "C" int enero_topo_build(int N, int E, const int32_t* edge_src, const int
         t->in_first.resize(t->P);
         { std::vector<int> cur(t->in_off.begin(), t->in_off.end() - 1);
           for (int p = 0; p < t->P; ++p) t->in_first[cur[t->second[p]]++] = t->first[p]; }
+        // CSR by `first` (the transpose, used by the backward pass)
+        t->out_off.assign(E + 1, 0);
+        for (int p = 0; p < t->P; ++p) t->out_off[t->first[p] + 1]++;
+        for (int e = 0; e < E; ++e) t->out_off[e + 1] += t->out_off[e];
+        t->out_second.resize(t->P);
+        { std::vector<int> cur(t->out_off.begin(), t->out_off.end() - 1);
+          for (int p = 0; p < t->P; ++p) t->out_second[cur[t->first[p]]++] = t->second[p]; }
         // shortest paths
         if (sp_off && sp_nodes) {
             t->sp_node_off.assign(sp_off, sp_off + (size_t)N * N + 1);

@@ -1,0 +1,485 @@
+// Backward kernels of the message-passing GNN and the fused PPO loss / clip / Adam step.
+//
+// Reference: train_Enero_3top_script.py:264-324 (_critic_step, _actor_step, _train_step_combined:
+// GradientTape over the actor and critic, clip_by_global_norm(0.5), Adam.apply_gradients).
+//
+// Forward of a training minibatch keeps h_t and A_t = h_t.Wm[0:20] of every iteration (11 row
+// buffers).  Backward runs t = T-1 .. 0 with two row-parallel kernels per iteration:
+//   k_bwd_gates : recompute B, agg, the GRU gates of iteration t; back-propagate dh_{t+1} through the
+//                 GRU; emit dagg, B, the partial dh_t and the gate-gradient rows used for weight grads
+//   k_bwd_msgs  : back-propagate through selu and the two gathers.  dB_i sums over the pairs that
+//                 arrive at row i (CSR by `second`), dA_i over the pairs that leave row i (CSR by `first`) --
+//                 the transposes of the forward gathers, again without atomics.
+// Weight gradients are tall-skinny reductions X^T.D over all rows and iterations: k_wgrad stages
+// 128-row chunks in shared memory, every thread owns ~13 of the 3340 outputs, persistent CTAs write
+// one partial vector each and k_reduce_partials adds them in CTA order (deterministic).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "enero_internal.h"
+#include "env_kernels.cuh"
+#include "gnn_kernels.cuh"
+
+namespace enero {
+
+constexpr int BW_TPB = 128;
+constexpr float SELU_S = 1.0507009873554804934193349852946f;
+constexpr float SELU_SA = 1.7580993408473768599402175208123f;
+__device__ __forceinline__ float selu_grad_fast(float u) { return u < 0.f ? SELU_SA * ex2_approx(u * LOG2E) : SELU_S; }
+
+// out-pairs of a row (CSR by `first`), mirroring IdxTopo::seg
+struct OutTopo {
+    int E, off_f, off_s, RPD;
+    const int* nK; const int* out_off; const int* out_second;
+    __device__ __forceinline__ void seg(int64_t r, int& bg, int& en, int64_t& add) const {
+        const int b = (int)(r / RPD);
+        const int lr = (int)(r - (int64_t)b * RPD);
+        bg = en = 0; add = 0;
+        if (off_f > 0) {
+            const int k = lr / off_f, x = lr - k * off_f;
+            if (k < nK[b]) { bg = out_off[x]; en = out_off[x + 1]; add = (int64_t)b * RPD + (int64_t)k * off_s; }
+        }
+    }
+};
+
+// y[j] (+)= sum_k x[k] * W[k*LD + j]   (forward orientation, 20 outputs)
+template <int LD>
+__device__ __forceinline__ void mv_fwd(float (&acc)[H], const float (&x)[H], const float* __restrict__ W) {
+#pragma unroll
+    for (int k = 0; k < H; ++k) {
+#pragma unroll
+        for (int j = 0; j < H; j += 4) {
+            const float4 w = *reinterpret_cast<const float4*>(W + k * LD + j);
+            acc[j] = fmaf(x[k], w.x, acc[j]); acc[j + 1] = fmaf(x[k], w.y, acc[j + 1]);
+            acc[j + 2] = fmaf(x[k], w.z, acc[j + 2]); acc[j + 3] = fmaf(x[k], w.w, acc[j + 3]);
+        }
+    }
+}
+// y[k] += sum_j d[j] * W[k*LD + j]     (transposed orientation)
+template <int LD>
+__device__ __forceinline__ void mv_bwd(float (&acc)[H], const float (&d)[H], const float* __restrict__ W) {
+#pragma unroll
+    for (int k = 0; k < H; ++k) {
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < H; j += 4) {
+            const float4 w = *reinterpret_cast<const float4*>(W + k * LD + j);
+            s0 = fmaf(d[j], w.x, s0); s1 = fmaf(d[j + 1], w.y, s1);
+            s0 = fmaf(d[j + 2], w.z, s0); s1 = fmaf(d[j + 3], w.w, s1);
+        }
+        acc[k] += s0 + s1;
+    }
+}
+
+// ---- GRU backward of one iteration ------------------------------------------------------------------
+// ht = h_t, At = A_t (forward saves); dhn = dL/dh_{t+1}.  Writes agg_t, gate-gradient rows
+// G = [dpz | dpr | dx | dy], B_t, dagg and the GRU part of dL/dh_t.
+__global__ void __launch_bounds__(BW_TPB)
+k_bwd_gates(const IdxTopo idx, const float* __restrict__ wflat, const float* __restrict__ ht,
+            const float* __restrict__ At, const float* __restrict__ dhn, float* __restrict__ agg_out,
+            float* __restrict__ G_out, float* __restrict__ B_out, float* __restrict__ dagg_out,
+            float* __restrict__ dh_part) {
+    __shared__ __align__(16) float sw[W_MP_FLOATS];
+    for (int i = threadIdx.x; i < W_MP_FLOATS / 4; i += BW_TPB)
+        reinterpret_cast<float4*>(sw)[i] = reinterpret_cast<const float4*>(wflat)[i];
+    __syncthreads();
+    const int64_t r = (int64_t)blockIdx.x * BW_TPB + threadIdx.x;
+    if (!idx.valid(r)) return;
+    float h[H], agg[H], t[H];
+    load_row(h, ht + r * H);
+#pragma unroll
+    for (int j = 0; j < H; ++j) { t[j] = sw[W_MSG_B + j]; agg[j] = 0.f; }
+    mv_fwd<H>(t, h, sw + W_MSG_K + H * H);
+    store_row(B_out + r * H, t);
+    {
+        int pb, pe; const int* list; int64_t add;
+        idx.seg(r, pb, pe, list, add);
+        for (int p = pb; p < pe; ++p) {
+            float a[H];
+            load_row(a, At + ((int64_t)list[p] + add) * H);
+#pragma unroll
+            for (int j = 0; j < H; ++j) agg[j] += selu_fast(a[j] + t[j]);
+        }
+    }
+    store_row(agg_out + r * H, agg);
+    float z[H], rg[H], y[H], c[H];
+#pragma unroll
+    for (int j = 0; j < H; ++j) { z[j] = sw[W_GRU_B + j]; rg[j] = sw[W_GRU_B + 20 + j]; y[j] = sw[W_GRU_B + 100 + j]; c[j] = sw[W_GRU_B + 40 + j]; }
+    mv_fwd<60>(z, agg, sw + W_GRU_K);       mv_fwd<60>(z, h, sw + W_GRU_R);
+    mv_fwd<60>(rg, agg, sw + W_GRU_K + 20); mv_fwd<60>(rg, h, sw + W_GRU_R + 20);
+    mv_fwd<60>(y, h, sw + W_GRU_R + 40);
+    mv_fwd<60>(c, agg, sw + W_GRU_K + 40);
+    float dh[H];
+    load_row(dh, dhn + r * H);
+    float dpz[H], dpr[H], dx[H], dy[H];
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+        const float zz = sigmoid_fast(z[j] + sw[W_GRU_B + 60 + j]);
+        const float rr = sigmoid_fast(rg[j] + sw[W_GRU_B + 80 + j]);
+        const float cc = tanh_fast(c[j] + rr * y[j]);
+        const float g = dh[j];
+        const float dz = g * (h[j] - cc);
+        const float dc = g * (1.f - zz);
+        const float dpc = dc * (1.f - cc * cc);
+        dx[j] = dpc;
+        dy[j] = dpc * rr;
+        dpr[j] = dpc * y[j] * rr * (1.f - rr);
+        dpz[j] = dz * zz * (1.f - zz);
+        dh[j] = g * zz;
+    }
+    store_row(G_out + r * 4 * H, dpz);
+    store_row(G_out + r * 4 * H + H, dpr);
+    store_row(G_out + r * 4 * H + 2 * H, dx);
+    store_row(G_out + r * 4 * H + 3 * H, dy);
+    float dagg[H];
+#pragma unroll
+    for (int j = 0; j < H; ++j) dagg[j] = 0.f;
+    mv_bwd<60>(dagg, dpz, sw + W_GRU_K); mv_bwd<60>(dagg, dpr, sw + W_GRU_K + 20); mv_bwd<60>(dagg, dx, sw + W_GRU_K + 40);
+    mv_bwd<60>(dh, dpz, sw + W_GRU_R);   mv_bwd<60>(dh, dpr, sw + W_GRU_R + 20);   mv_bwd<60>(dh, dy, sw + W_GRU_R + 40);
+    store_row(dagg_out + r * H, dagg);
+    store_row(dh_part + r * H, dh);
+}
+
+// ---- message backward of one iteration -----------------------------------------------------------------
+template <bool NEED_DH>
+__global__ void __launch_bounds__(BW_TPB)
+k_bwd_msgs(const IdxTopo idx, const OutTopo out, const float* __restrict__ wflat, const float* __restrict__ At,
+           const float* __restrict__ B_in, const float* __restrict__ dagg_in, const float* __restrict__ dh_part,
+           float* __restrict__ dB_out, float* __restrict__ dA_out, float* __restrict__ dh_prev) {
+    __shared__ __align__(16) float sw[2 * H * H];
+    for (int i = threadIdx.x; i < 2 * H * H / 4; i += BW_TPB)
+        reinterpret_cast<float4*>(sw)[i] = reinterpret_cast<const float4*>(wflat + W_MSG_K)[i];
+    __syncthreads();
+    const int64_t r = (int64_t)blockIdx.x * BW_TPB + threadIdx.x;
+    if (!idx.valid(r)) return;
+    float B[H], dagg[H], dB[H], dA[H];
+    load_row(B, B_in + r * H);
+    load_row(dagg, dagg_in + r * H);
+#pragma unroll
+    for (int j = 0; j < H; ++j) { dB[j] = 0.f; dA[j] = 0.f; }
+    {
+        int pb, pe; const int* list; int64_t add;
+        idx.seg(r, pb, pe, list, add);
+        for (int p = pb; p < pe; ++p) {
+            float a[H];
+            load_row(a, At + ((int64_t)list[p] + add) * H);
+#pragma unroll
+            for (int j = 0; j < H; ++j) dB[j] += dagg[j] * selu_grad_fast(a[j] + B[j]);
+        }
+    }
+    {
+        float Ai[H];
+        load_row(Ai, At + r * H);
+        int pb, pe; int64_t add;
+        out.seg(r, pb, pe, add);
+        for (int p = pb; p < pe; ++p) {
+            const int64_t dst = (int64_t)out.out_second[p] + add;
+            float bs[H], ds[H];
+            load_row(bs, B_in + dst * H);
+            load_row(ds, dagg_in + dst * H);
+#pragma unroll
+            for (int j = 0; j < H; ++j) dA[j] += ds[j] * selu_grad_fast(Ai[j] + bs[j]);
+        }
+    }
+    store_row(dB_out + r * H, dB);
+    store_row(dA_out + r * H, dA);
+    if (NEED_DH) {
+        float dh[H];
+        load_row(dh, dh_part + r * H);
+        mv_bwd<H>(dh, dB, sw + H * H);     // B = bm + h.Wm[20:40]
+        mv_bwd<H>(dh, dA, sw);             // A = h.Wm[0:20]
+        store_row(dh_prev + r * H, dh);
+    }
+}
+
+// ---- readout backward (one warp per graph) ------------------------------------------------------------------
+// dlogit[graph] -> dL/dh_T rows, and per-graph vectors V = [g | a1 | a2 | dp1 | dp2 | dy] for the weight grads
+__global__ void __launch_bounds__(128)
+k_readout_bwd(const GraphsTopo gr, const float* __restrict__ wflat, const float* __restrict__ hT,
+              const float* __restrict__ dlogit, float* __restrict__ dhT, float* __restrict__ V) {
+    __shared__ float sr[W_R3_B + 1 - W_R1_K];
+    for (int i = threadIdx.x; i <= W_R3_B - W_R1_K; i += blockDim.x) sr[i] = wflat[W_R1_K + i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int64_t r0, r1, o;
+    if (!gr.range(g, r0, r1, o)) return;
+    float acc[H];
+#pragma unroll
+    for (int j = 0; j < H; ++j) acc[j] = 0.f;
+    for (int64_t r = r0 + lane; r < r1; r += 32) {
+        float v[H];
+        load_row(v, hT + r * H);
+#pragma unroll
+        for (int j = 0; j < H; ++j) acc[j] += v[j];
+    }
+#pragma unroll
+    for (int j = 0; j < H; ++j) acc[j] = warp_sum(acc[j]);
+    const float* R1 = sr; const float* B1 = sr + (W_R1_B - W_R1_K);
+    const float* R2 = sr + (W_R2_K - W_R1_K); const float* B2 = sr + (W_R2_B - W_R1_K);
+    const float* R3 = sr + (W_R3_K - W_R1_K);
+    const int j = lane < H ? lane : 0;
+    float p1 = 0.f;
+#pragma unroll
+    for (int k = 0; k < H; ++k) p1 = fmaf(acc[k], R1[k * H + j], p1);
+    p1 += B1[j];
+    const float a1 = selu_f(p1);
+    float p2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < H; ++k) p2 = fmaf(__shfl_sync(0xffffffffu, a1, k), R2[k * H + j], p2);
+    p2 += B2[j];
+    const float a2 = selu_f(p2);
+    const float dy = dlogit[o];
+    const float sg2 = p2 < 0.f ? SELU_SA * expf(p2) : SELU_S;
+    const float dp2 = R3[j] * dy * sg2;                                  // lane j: da2[j] * selu'(p2[j])
+    float da1 = 0.f;                                                     // lane j: sum_m R2[j][m] * dp2[m]
+#pragma unroll
+    for (int m = 0; m < H; ++m) da1 = fmaf(R2[j * H + m], __shfl_sync(0xffffffffu, dp2, m), da1);
+    const float sg1 = p1 < 0.f ? SELU_SA * expf(p1) : SELU_S;
+    const float dp1 = da1 * sg1;
+    float dg = 0.f;
+#pragma unroll
+    for (int m = 0; m < H; ++m) dg = fmaf(R1[j * H + m], __shfl_sync(0xffffffffu, dp1, m), dg);
+    // dL/dh_T of every row of the graph = dg
+    float dgv[H];
+#pragma unroll
+    for (int k = 0; k < H; ++k) dgv[k] = __shfl_sync(0xffffffffu, dg, k);
+    for (int64_t r = r0 + lane; r < r1; r += 32) store_row(dhT + r * H, dgv);
+    if (lane < H) {
+        float* v = V + o * 6 * H;
+        v[lane] = acc[lane]; v[H + lane] = a1; v[2 * H + lane] = a2; v[3 * H + lane] = dp1; v[4 * H + lane] = dp2;
+        v[5 * H + lane] = dy;
+    }
+}
+
+// readout weight gradients: a single CTA walks the graphs in order (deterministic), thread o owns outputs
+// o, o+256, ... of the 861 readout parameters and adds the result into grad[W_R1_K + o].
+__global__ void __launch_bounds__(256)
+k_readout_wgrad(int n_graphs, int Kmax, const int* __restrict__ nK, const float* __restrict__ V, float* __restrict__ grad) {
+    constexpr int NOUT = W_R3_B + 1 - W_R1_K;     // 861
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    __shared__ float sv[6 * H];
+    for (int g = 0; g < n_graphs; ++g) {
+        const int b = g / Kmax, k = g - b * Kmax;
+        if (k >= nK[b]) continue;
+        __syncthreads();
+        if (threadIdx.x < 6 * H) sv[threadIdx.x] = V[(int64_t)g * 6 * H + threadIdx.x];
+        __syncthreads();
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            const int o = threadIdx.x + 256 * m;
+            if (o >= NOUT) break;
+            float v;
+            if (o < 400) v = sv[o / H] * sv[3 * H + o % H];                        // dR1[k][j] = g[k] * dp1[j]
+            else if (o < 420) v = sv[3 * H + o - 400];                             // db1
+            else if (o < 820) v = sv[H + (o - 420) / H] * sv[4 * H + (o - 420) % H];   // dR2 = a1[k] * dp2[j]
+            else if (o < 840) v = sv[4 * H + o - 820];                             // db2
+            else if (o < 860) v = sv[2 * H + o - 840] * sv[5 * H];                 // dR3 = a2[k] * dy
+            else v = sv[5 * H];                                                    // db3
+            acc[m] += v;
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        const int o = threadIdx.x + 256 * m;
+        if (o < NOUT) grad[W_R1_K + o] += acc[m];
+    }
+}
+
+// ---- message / GRU weight gradients -----------------------------------------------------------------------------
+// For every row and iteration: X = [h(20) | agg(20) | 1], D = [dpz dpr dx dy (80) | dB (20) | dA (20)].
+// Output o of the 3340 message+GRU parameters is sum over rows of X[xc(o)] * D[dc(o)].
+struct WgradIter { const float* h; const float* agg; const float* G; const float* dB; const float* dA; };
+constexpr int WG_TPB = 256, WG_ROWS = 64, WG_XW = 41, WG_DW = 120, WG_PER = 14;   // ceil(3340 / 256)
+
+__device__ __forceinline__ void wgrad_cols(int o, int& xc, int& dc) {
+    if (o < 400) { xc = o / H; dc = 100 + o % H; }                         // dWm[0:20]   = h^T dA
+    else if (o < 800) { xc = (o - 400) / H; dc = 80 + (o - 400) % H; }     // dWm[20:40]  = h^T dB
+    else if (o < 820) { xc = 40; dc = 80 + (o - 800); }                    // dbm         = sum dB
+    else if (o < 2020) { const int q = o - 820; xc = 20 + q / 60; dc = q % 60; }           // dK = agg^T [dpz dpr dx]
+    else if (o < 3220) { const int q = o - 2020; const int j = q % 60; xc = q / 60; dc = j < 40 ? j : j + 20; }  // dR = h^T [dpz dpr dy]
+    else if (o < 3280) { xc = 40; dc = o - 3220; }                         // db0 = sum [dpz dpr dx]
+    else { const int j = o - 3280; xc = 40; dc = j < 40 ? j : j + 20; }    // db1 = sum [dpz dpr dy]
+}
+
+__global__ void __launch_bounds__(WG_TPB)
+k_wgrad(const IdxTopo idx, int T, const WgradIter* __restrict__ iters, int64_t ntiles, float* __restrict__ partials) {
+    __shared__ float sx[WG_ROWS * WG_XW];
+    __shared__ float sd[WG_ROWS * (WG_DW + 1)];
+    __shared__ unsigned char s_ok[WG_ROWS];
+    int xc[WG_PER], dc[WG_PER];
+    float acc[WG_PER];
+#pragma unroll
+    for (int m = 0; m < WG_PER; ++m) {
+        const int o = threadIdx.x + WG_TPB * m;
+        acc[m] = 0.f; xc[m] = 40; dc[m] = 0;
+        if (o < W_MP_FLOATS) wgrad_cols(o, xc[m], dc[m]);
+    }
+    for (int64_t tile = blockIdx.x; tile < ntiles * T; tile += gridDim.x) {
+        const int t = (int)(tile / ntiles);
+        const int64_t r0 = (tile - (int64_t)t * ntiles) * WG_ROWS;
+        const WgradIter it = iters[t];
+        __syncthreads();
+        if (threadIdx.x < WG_ROWS) s_ok[threadIdx.x] = idx.valid(r0 + threadIdx.x) ? 1 : 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < WG_ROWS * 160; i += WG_TPB) {
+            const int row = i / 160, c = i - row * 160;
+            const int64_t r = r0 + row;
+            float v = 0.f;
+            if (s_ok[row]) {
+                if (c < 20) v = it.h[r * H + c];
+                else if (c < 40) v = it.agg[r * H + c - 20];
+                else if (c < 120) v = it.G[r * 4 * H + c - 40];
+                else if (c < 140) v = it.dB[r * H + c - 120];
+                else v = it.dA[r * H + c - 140];
+            }
+            if (c < 40) sx[row * WG_XW + c] = v; else sd[row * (WG_DW + 1) + c - 40] = v;
+        }
+        if (threadIdx.x < WG_ROWS) sx[threadIdx.x * WG_XW + 40] = s_ok[threadIdx.x] ? 1.f : 0.f;
+        __syncthreads();
+        for (int row = 0; row < WG_ROWS; ++row) {
+            const float* px = sx + row * WG_XW;
+            const float* pd = sd + row * (WG_DW + 1);
+#pragma unroll
+            for (int m = 0; m < WG_PER; ++m) acc[m] = fmaf(px[xc[m]], pd[dc[m]], acc[m]);
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < WG_PER; ++m) {
+        const int o = threadIdx.x + WG_TPB * m;
+        if (o < W_MP_FLOATS) partials[(int64_t)blockIdx.x * W_MP_FLOATS + o] = acc[m];
+    }
+}
+
+__global__ void k_reduce_partials(int n_part, const float* __restrict__ partials, float* __restrict__ grad) {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= W_MP_FLOATS) return;
+    float s = 0.f;
+    for (int p = 0; p < n_part; ++p) s += partials[(int64_t)p * W_MP_FLOATS + o];
+    grad[o] += s;
+}
+
+// ---- PPO loss head (one warp per sample) ------------------------------------------------------------------------
+// _actor_step (train script :273-291): ratio, clipped surrogate, entropy; gradient wrt the logits of the
+// minibatch-mean loss  mean(loss) - beta * mean(entropy).  inv_m = 1 / minibatch size.
+__global__ void __launch_bounds__(128)
+k_ppo_actor_head(int n, int Kmax, const int* __restrict__ nK, const float* __restrict__ logits,
+                 const int* __restrict__ action, const float* __restrict__ old_prob, const float* __restrict__ adv,
+                 float inv_m, float beta, float clip, float* __restrict__ dlogit, float* __restrict__ loss_out,
+                 float* __restrict__ ent_out) {
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= n) return;
+    const int k = nK[b];
+    const float* x = logits + (int64_t)b * Kmax;
+    float m = -INFINITY;
+    for (int i = lane; i < k; i += 32) m = fmaxf(m, x[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float s = 0.f;
+    for (int i = lane; i < k; i += 32) s += expf(x[i] - m);
+    s = warp_sum(s);
+    const float inv = 1.f / s, logs = logf(s);
+    float ent = 0.f;
+    for (int i = lane; i < k; i += 32) {
+        const float p = expf(x[i] - m) * inv;
+        const float lp = (x[i] - m) - logs;
+        ent -= p * lp;
+    }
+    ent = warp_sum(ent);
+    const int a = action[b];
+    const float pa = expf(x[a] - m) * inv;
+    const float ratio = expf(logf(pa) - logf(old_prob[b]));
+    const float A = adv[b];
+    const float surr1 = -ratio * A;
+    const float rc = fminf(fmaxf(ratio, 1.f - clip), 1.f + clip);
+    const float surr2 = -rc * A;
+    // tf.maximum sends the gradient to surr1 when surr1 >= surr2; clip_by_value passes it inside [lo, hi]
+    float dr;
+    if (surr1 >= surr2) dr = -A;
+    else dr = (ratio >= 1.f - clip && ratio <= 1.f + clip) ? -A : 0.f;
+    for (int i = lane; i < Kmax; i += 32) {
+        float g = 0.f;
+        if (i < k) {
+            const float p = expf(x[i] - m) * inv;
+            const float lp = (x[i] - m) - logs;
+            g = dr * ratio * ((i == a ? 1.f : 0.f) - p);          // d loss / d logit_i
+            g += beta * p * (lp + ent);                           // - beta * d entropy / d logit_i
+            g *= inv_m;
+        }
+        dlogit[(int64_t)b * Kmax + i] = g;
+    }
+    if (lane == 0) { loss_out[b] = fmaxf(surr1, surr2); ent_out[b] = ent; }
+}
+
+// _critic_step (train script :264-271): (ret - V)^2
+__global__ void k_ppo_critic_head(int n, const float* __restrict__ value, const float* __restrict__ ret, float inv_m,
+                                  float* __restrict__ dvalue, float* __restrict__ loss_out) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n) return;
+    const float d = ret[b] - value[b];
+    loss_out[b] = d * d;
+    dvalue[b] = -2.f * d * inv_m;
+}
+
+// ---- clip_by_global_norm + Adam for both models (single CTA) ----------------------------------------------------
+// tf.clip_by_global_norm (train script :319): scale = clip * min(1/norm, 1/clip) over all 22 tensors;
+// Keras Adam as TF's ApplyAdam kernel: m += (g-m)(1-b1); v += (g^2-v)(1-b2); theta -= m*alpha/(sqrt(v)+eps)
+__global__ void __launch_bounds__(1024)
+k_clip_adam(float* __restrict__ wa, float* __restrict__ wc, float* __restrict__ ga, float* __restrict__ gc,
+            float* __restrict__ ma, float* __restrict__ va, float* __restrict__ mc, float* __restrict__ vc,
+            float alpha, float beta1, float beta2, float eps, float clip_norm, float* __restrict__ norm_out) {
+    __shared__ float red[32];
+    __shared__ float s_scale;
+    float s = 0.f;
+    for (int i = threadIdx.x; i < ENERO_NPARAMS; i += 1024) { s = fmaf(ga[i], ga[i], s); s = fmaf(gc[i], gc[i], s); }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = red[threadIdx.x];
+        v = warp_sum(v);
+        if (threadIdx.x == 0) {
+            const float norm = sqrtf(v);
+            s_scale = clip_norm * fminf(1.f / norm, 1.f / clip_norm);
+            if (norm_out) *norm_out = norm;
+        }
+    }
+    __syncthreads();
+    const float scale = s_scale;
+    for (int i = threadIdx.x; i < 2 * ENERO_NPARAMS; i += 1024) {
+        const bool actor = i < ENERO_NPARAMS;
+        const int k = actor ? i : i - ENERO_NPARAMS;
+        float* w = actor ? wa : wc; float* g = actor ? ga : gc; float* m = actor ? ma : mc; float* v = actor ? va : vc;
+        const float gg = g[k] * scale;
+        const float mm = m[k] + (gg - m[k]) * (1.f - beta1);
+        const float vv = v[k] + (gg * gg - v[k]) * (1.f - beta2);
+        m[k] = mm; v[k] = vv;
+        w[k] = w[k] - (mm * alpha) / (sqrtf(vv) + eps);
+        g[k] = 0.f;
+    }
+}
+
+// ---- GAE (train script :367-377), fp64 like the reference's python floats; one thread, 835 steps -------------------
+__global__ void k_gae(int n, const float* __restrict__ values /*[n+1]*/, const unsigned char* __restrict__ masks,
+                      const double* __restrict__ rewards, double gamma, double lmbda,
+                      double* __restrict__ returns, double* __restrict__ adv) {
+    if (blockIdx.x || threadIdx.x) return;
+    double gae = 0.0;
+    for (int i = n - 1; i >= 0; --i) {
+        const double mk = masks[i] ? 1.0 : 0.0;
+        const double delta = rewards[i] + gamma * (double)values[i + 1] * mk - (double)values[i];
+        gae = delta + gamma * lmbda * mk * gae;
+        returns[i] = gae + (double)values[i];
+    }
+    double mean = 0.0;
+    for (int i = 0; i < n; ++i) { adv[i] = returns[i] - (double)values[i]; mean += adv[i]; }
+    mean /= n;
+    double var = 0.0;
+    for (int i = 0; i < n; ++i) { const double d = adv[i] - mean; var += d * d; }
+    const double sd = sqrt(var / n);
+    for (int i = 0; i < n; ++i) adv[i] = (adv[i] - mean) / (sd + 1e-10);
+}
+
+}  // namespace enero

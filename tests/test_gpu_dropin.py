@@ -55,6 +55,9 @@ def test_eval_script_flow(name, actor, tmp_path):
     agent = agents.PPOMIDDROUTING_SP(env, actor)
     for ep in case["episodes"]:
         timesteps = []
+        # one worker process per TM in the reference (eval_on_single_topology.py:92-94): a fresh env has
+        # an empty sp_middlepoints_step; a re-used one keeps the previous episode's dict (same quirk here)
+        env.sp_middlepoints_step = dict()
         best, _, ospf, best_routing, demands, t0 = agents.play_middRout_games_sp(ep["tm_id"], env, agent, timesteps)
         assert (best, ospf) == (ep["best"], ep["ospf"])
         assert [[int(k.split(":")[0]), int(k.split(":")[1]), m] for k, m in best_routing.items()] == ep["best_routing"]
