@@ -15,6 +15,8 @@ from . import build as _build
 HOST, DEVICE = 0, 1
 ACTOR, CRITIC = 0, 1
 NPARAMS = 4201
+GRAD_STRIDE = 4204
+GRAD_FLOATS = 2 * GRAD_STRIDE + 4
 
 _lib = None
 
@@ -71,6 +73,15 @@ SIGNATURES = {
     "enero_batch_get_best": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "enero_batch_local_search": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "enero_batch_get_ls_eligible": (C.c_int, [_vp, _vp, _vp, C.c_int]),
+    "enero_ppo_grad_buffer": (_vp, [_vp]),
+    "enero_ppo_zero_grad": (C.c_int, [_vp]),
+    "enero_ppo_accumulate": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_float, C.c_float,
+                                       C.c_float, C.c_int]),
+    "enero_ppo_apply": (C.c_int, [_vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64, _vp]),
+    "enero_ppo_grad_download": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "enero_adam_slots_upload": (C.c_int, [_vp, C.c_int, _vp, _vp]),
+    "enero_adam_slots_download": (C.c_int, [_vp, C.c_int, _vp, _vp]),
+    "enero_gae": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, C.c_double, C.c_double, _vp, _vp]),
 }
 
 

@@ -15,6 +15,7 @@
 #include "enero_internal.h"
 #include "env_kernels.cuh"
 #include "gnn_kernels.cuh"
+#include "train_kernels.cuh"
 
 using namespace enero;
 
@@ -40,11 +41,14 @@ extern "C" int enero_ctx_create(int device, enero_ctx** out) {
     c->num_sms = prop.multiProcessorCount;
     CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {
-        for (float** p : {&c->w[i], &c->grad[i], &c->adam_m[i], &c->adam_v[i]}) {
-            CUDA_TRY(cudaMalloc(p, sizeof(float) * (ENERO_NPARAMS + 3)));
-            CUDA_TRY(cudaMemset(*p, 0, sizeof(float) * (ENERO_NPARAMS + 3)));
+        for (float** p : {&c->w[i], &c->adam_m[i], &c->adam_v[i]}) {
+            CUDA_TRY(cudaMalloc(p, sizeof(float) * ENERO_GRAD_STRIDE));
+            CUDA_TRY(cudaMemset(*p, 0, sizeof(float) * ENERO_GRAD_STRIDE));
         }
     }
+    CUDA_TRY(cudaMalloc(&c->gradbuf, sizeof(float) * ENERO_GRAD_FLOATS));
+    CUDA_TRY(cudaMemset(c->gradbuf, 0, sizeof(float) * ENERO_GRAD_FLOATS));
+    c->grad[0] = c->gradbuf; c->grad[1] = c->gradbuf + ENERO_GRAD_STRIDE;
     {
         int r = ENERO_OK;
         auto setup = [&](auto kern, int& occ) {
@@ -63,6 +67,7 @@ extern "C" int enero_ctx_create(int device, enero_ctx** out) {
         setup(k_mp_iter<IdxTopo, false, 3>, tmp);
         if (r != ENERO_OK) return r;
     }
+    CUDA_TRY(cudaFuncSetAttribute(k_bwd_gates, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWG_SMEM_BYTES));
     *out = c;
     return ENERO_OK;
 }
@@ -71,7 +76,8 @@ extern "C" int enero_ctx_destroy(enero_ctx* c) {
     if (!c) return ENERO_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    for (int i = 0; i < 2; ++i) { cudaFree(c->w[i]); cudaFree(c->grad[i]); cudaFree(c->adam_m[i]); cudaFree(c->adam_v[i]); }
+    for (int i = 0; i < 2; ++i) { cudaFree(c->w[i]); cudaFree(c->adam_m[i]); cudaFree(c->adam_v[i]); }
+    cudaFree(c->gradbuf);
     cudaStreamDestroy(c->stream);
     delete c;
     return ENERO_OK;
@@ -733,3 +739,5 @@ extern "C" int enero_batch_get_ls_eligible(enero_batch* b, int32_t* elig, int32_
     }
     return ENERO_OK;
 }
+
+#include "train_api.cuh"

@@ -53,13 +53,16 @@ struct enero_ctx {
     // optional per-launch CUDA-event timing of the dominant kernel (bench.py roofline leg)
     bool prof = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_ev;
-    // training state (train.cu): flat gradients and Adam slots of actor [0] and critic [1]
-    float* grad[2] = {nullptr, nullptr};
+    // training state (train_api.cuh): one contiguous gradient buffer
+    //   [actor ENERO_GRAD_STRIDE | critic ENERO_GRAD_STRIDE | actor-loss sum, entropy sum, critic-loss sum, pad]
+    // so that a sharded PPO step needs exactly one all-reduce; Adam slots of actor [0] and critic [1]
+    float* gradbuf = nullptr;
+    float* grad[2] = {nullptr, nullptr};      // views into gradbuf
     float* adam_m[2] = {nullptr, nullptr};
     float* adam_v[2] = {nullptr, nullptr};
-    DevBuf t_rows[16];       // h_0..h_T, A_0..A_{T-1} of a training forward
-    DevBuf t_agg, t_G, t_dB, t_dA, t_B, t_dagg, t_dh[2], t_V, t_dlogit, t_partials, t_iters;
-    DevBuf t_loads, t_sd, t_bw, t_action, t_oldp, t_adv, t_ret, t_logits, t_values, t_nK, t_loss, t_ent, t_closs, t_scalar;
+    DevBuf t_h[8], t_A[8];   // h_0..h_T, A_0..A_{T-1} of a training forward
+    DevBuf t_agg, t_G, t_dB, t_dA, t_B, t_dagg, t_dhpart, t_dh[2], t_V, t_dlogit, t_partials;
+    DevBuf t_loads, t_sd, t_bw, t_action, t_oldp, t_adv, t_ret, t_logits, t_probs, t_nK, t_loss, t_ent, t_norm;
 };
 
 #define LAUNCH_CHECK(ctx)                                                     \

@@ -1,0 +1,248 @@
+// C-ABI glue of the PPO update (included at the end of api.cu so that the k_mp_iter instantiations,
+// their shared-memory attributes and occupancy live in one translation unit).
+//
+// Reference: train_Enero_3top_script.py:264-324 (_critic_step, _actor_step, _train_step_combined),
+// :326-365 (ppo_update), :367-377 (get_advantages).
+#pragma once
+#include "train_kernels.cuh"
+
+namespace {
+
+struct TrainTopo {           // launch geometry of one model's pass over n samples
+    int n, Kmax, E, RPD; int64_t rows; const int* nK;
+};
+
+int ensure_ones(enero_ctx* c, int B) {
+    if (c->ones.cap >= (size_t)B * 4) return ENERO_OK;
+    TRY(c->ones.ensure((size_t)B * 4));
+    std::vector<int> one((size_t)c->ones.cap / 4, 1);
+    CUDA_TRY(cudaMemcpyAsync(c->ones.p, one.data(), one.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return ENERO_OK;
+}
+
+// forward with saved activations: h_0/A_0 must already be in t_h[0]/t_A[0]
+int train_forward(enero_ctx* c, const IdxTopo& idx, int which, int T, int64_t rows) {
+    const int64_t ntiles = (rows + MP_ROWS - 1) / MP_ROWS;
+    for (int it = 0; it < T; ++it) {
+        const bool last = (it == T - 1);
+        const int occ = std::max(1, c->occ_iter[1][last ? 1 : 0]);
+        const int grid = (int)std::min<int64_t>(ntiles, (int64_t)c->num_sms * occ);
+        const float* hin = c->t_h[it].as<float>();
+        const float* Ain = c->t_A[it].as<float>();
+        float* hout = c->t_h[it + 1].as<float>();
+        float* Aout = last ? nullptr : c->t_A[it + 1].as<float>();
+        if (last) k_mp_iter<IdxTopo, true, 20><<<grid, MP_TPB, MP_SMEM_BYTES, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles);
+        else if (it == 0) k_mp_iter<IdxTopo, false, 3><<<grid, MP_TPB, MP_SMEM_BYTES, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles);
+        else k_mp_iter<IdxTopo, false, 20><<<grid, MP_TPB, MP_SMEM_BYTES, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles);
+        LAUNCH_CHECK(c);
+    }
+    return ENERO_OK;
+}
+
+// backward through the readout and the T message-passing iterations; dlogit [n*Kmax] on device
+int train_backward(enero_ctx* c, enero_topo* t, const TrainTopo& g, int which, int T, const float* dlogit) {
+    const TopoDev& d = t->dev;
+    cudaStream_t st = c->stream;
+    const int64_t rows = g.rows;
+    const size_t rb = (size_t)rows * H * sizeof(float);
+    TRY(c->t_agg.ensure(rb)); TRY(c->t_G.ensure(4 * rb)); TRY(c->t_dB.ensure(rb)); TRY(c->t_dA.ensure(rb));
+    TRY(c->t_B.ensure(rb)); TRY(c->t_dagg.ensure(rb)); TRY(c->t_dhpart.ensure(rb));
+    TRY(c->t_dh[0].ensure(rb)); TRY(c->t_dh[1].ensure(rb));
+    const int n_graphs = g.n * g.Kmax;
+    TRY(c->t_V.ensure((size_t)n_graphs * 6 * H * 4));
+    const int wg_grid = (int)std::min<int64_t>((rows + WG_ROWS - 1) / WG_ROWS, 2 * (int64_t)c->num_sms);
+    TRY(c->t_partials.ensure((size_t)wg_grid * W_MP_FLOATS * 4));
+    IdxTopo idx{rows, g.E, d.off_f, d.off_s, g.RPD, g.nK, d.in_off, d.in_first};
+    OutTopo out{g.E, d.off_f, d.off_s, g.RPD, g.nK, d.out_off, d.out_second};
+    GraphsTopo gr{g.n, g.Kmax, g.E, g.RPD, g.nK};
+    float* grad = c->grad[which];
+    const float* w = c->w[which];
+    k_readout_bwd<<<(n_graphs + 3) / 4, 128, 0, st>>>(gr, w, c->t_h[T].as<float>(), dlogit, c->t_dh[0].as<float>(), c->t_V.as<float>());
+    LAUNCH_CHECK(c);
+    k_readout_wgrad<<<1, 256, 0, st>>>(n_graphs, g.Kmax, g.nK, c->t_V.as<float>(), grad); LAUNCH_CHECK(c);
+    const int bgrid = (int)((rows + BW_TPB - 1) / BW_TPB);
+    int cur = 0;
+    for (int it = T - 1; it >= 0; --it) {
+        const float* ht = c->t_h[it].as<float>();
+        const float* At = c->t_A[it].as<float>();
+        k_bwd_gates<<<bgrid, BW_TPB, BWG_SMEM_BYTES, st>>>(idx, w, ht, At, c->t_dh[cur].as<float>(), c->t_agg.as<float>(), c->t_G.as<float>(),
+                                              c->t_B.as<float>(), c->t_dagg.as<float>(), c->t_dhpart.as<float>());
+        LAUNCH_CHECK(c);
+        if (it > 0)
+            k_bwd_msgs<true><<<bgrid, BW_TPB, 0, st>>>(idx, out, w, At, c->t_B.as<float>(), c->t_dagg.as<float>(), c->t_dhpart.as<float>(),
+                                                       c->t_dB.as<float>(), c->t_dA.as<float>(), c->t_dh[cur ^ 1].as<float>());
+        else
+            k_bwd_msgs<false><<<bgrid, BW_TPB, 0, st>>>(idx, out, w, At, c->t_B.as<float>(), c->t_dagg.as<float>(), c->t_dhpart.as<float>(),
+                                                        c->t_dB.as<float>(), c->t_dA.as<float>(), nullptr);
+        LAUNCH_CHECK(c);
+        WgradIter wi{ht, c->t_agg.as<float>(), c->t_G.as<float>(), c->t_dB.as<float>(), c->t_dA.as<float>()};
+        k_wgrad<<<wg_grid, WG_TPB, 0, st>>>(idx, wi, (rows + WG_ROWS - 1) / WG_ROWS, c->t_partials.as<float>()); LAUNCH_CHECK(c);
+        k_reduce_partials<<<(W_MP_FLOATS + 255) / 256, 256, 0, st>>>(wg_grid, c->t_partials.as<float>(), grad); LAUNCH_CHECK(c);
+        cur ^= 1;
+    }
+    return ENERO_OK;
+}
+
+int ensure_train_rows(enero_ctx* c, int T, int64_t rows) {
+    const size_t rb = (size_t)rows * H * sizeof(float);
+    if (T + 1 > 8) return fail(ENERO_ERR_INVALID, "training supports T <= 7");
+    for (int i = 0; i <= T; ++i) TRY(c->t_h[i].ensure(rb));
+    for (int i = 0; i < T; ++i) TRY(c->t_A[i].ensure(rb));
+    return ENERO_OK;
+}
+
+}  // namespace
+
+extern "C" void* enero_ppo_grad_buffer(enero_ctx* c) { return c ? (void*)c->gradbuf : nullptr; }
+
+extern "C" int enero_ppo_zero_grad(enero_ctx* c) {
+    if (!c) return fail(ENERO_ERR_INVALID, "null ctx");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaMemsetAsync(c->gradbuf, 0, sizeof(float) * ENERO_GRAD_FLOATS, c->stream));
+    return ENERO_OK;
+}
+
+extern "C" int enero_ppo_accumulate(enero_ctx* c, enero_topo* t, int n, const double* loads, const int32_t* sd,
+                                    const double* bw, const int32_t* action, const float* old_prob,
+                                    const float* advantage, const float* ret, float inv_m, float entropy_beta,
+                                    float clipping_val, int ptr_kind) {
+    if (!c || !t || !loads || !sd || !bw || !action || !old_prob || !advantage || !ret || n < 1)
+        return fail(ENERO_ERR_INVALID, "enero_ppo_accumulate: bad argument");
+    TRY(enero_topo_upload(c, t));
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const TopoDev& d = t->dev;
+    const int E = d.E, Kmax = d.Kmax, T = 5;
+    if (ptr_kind == ENERO_HOST) {
+        // validate what a kernel could not report
+        for (int i = 0; i < n; ++i) {
+            const int s = sd[2 * i], dd = sd[2 * i + 1];
+            if (s < 0 || dd < 0 || s >= t->N || dd >= t->N || s == dd) return fail(ENERO_ERR_INVALID, "enero_ppo_accumulate: bad demand");
+            const int k = t->mid_off[s * t->N + dd + 1] - t->mid_off[s * t->N + dd];
+            if (action[i] < 0 || action[i] >= k) return fail(ENERO_ERR_INVALID, "enero_ppo_accumulate: action out of range");
+        }
+        TRY(c->t_loads.ensure((size_t)n * E * 8)); TRY(c->t_sd.ensure((size_t)n * 8)); TRY(c->t_bw.ensure((size_t)n * 8));
+        TRY(c->t_action.ensure((size_t)n * 4)); TRY(c->t_oldp.ensure((size_t)n * 4)); TRY(c->t_adv.ensure((size_t)n * 4));
+        TRY(c->t_ret.ensure((size_t)n * 4));
+        CUDA_TRY(cudaMemcpyAsync(c->t_loads.p, loads, (size_t)n * E * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(c->t_sd.p, sd, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(c->t_bw.p, bw, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(c->t_action.p, action, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(c->t_oldp.p, old_prob, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(c->t_adv.p, advantage, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(c->t_ret.p, ret, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        loads = c->t_loads.as<double>(); sd = c->t_sd.as<int>(); bw = c->t_bw.as<double>();
+        action = c->t_action.as<int>(); old_prob = c->t_oldp.as<float>(); advantage = c->t_adv.as<float>(); ret = c->t_ret.as<float>();
+    }
+    TopoView tv = view_of(t);
+    TRY(c->util.ensure((size_t)n * E * 4)); TRY(c->t_nK.ensure((size_t)n * 4));
+    TRY(c->t_logits.ensure((size_t)n * Kmax * 4)); TRY(c->t_dlogit.ensure((size_t)n * Kmax * 4));
+    TRY(c->t_loss.ensure((size_t)n * 4)); TRY(c->t_ent.ensure((size_t)n * 4));
+    float* sums = c->gradbuf + 2 * ENERO_GRAD_STRIDE;
+    // ---- actor: K' candidate graphs per sample
+    {
+        const int RPD = Kmax * E;
+        const int64_t rows = (int64_t)n * RPD;
+        TRY(ensure_train_rows(c, T, rows));
+        int* nK = c->t_nK.as<int>();
+        CUDA_TRY(cudaMemsetAsync(c->t_logits.p, 0, (size_t)n * Kmax * 4, st));
+        k_decision_prep<<<(int)(((int64_t)n * E + 255) / 256), 256, 0, st>>>(tv, n, loads, sd, nullptr, nK, c->util.as<float>()); LAUNCH_CHECK(c);
+        k_features<<<(int)((rows + MP_TPB - 1) / MP_TPB), MP_TPB, 0, st>>>(tv, n, RPD, sd, bw, nK, c->util.as<float>(), c->w[ENERO_ACTOR],
+                                                                         c->t_h[0].as<float>(), c->t_A[0].as<float>()); LAUNCH_CHECK(c);
+        IdxTopo idx{rows, E, d.off_f, d.off_s, RPD, nK, d.in_off, d.in_first};
+        TRY(train_forward(c, idx, ENERO_ACTOR, T, rows));
+        GraphsTopo gr{n, Kmax, E, RPD, nK};
+        k_readout<GraphsTopo><<<(n * Kmax + 3) / 4, 128, 0, st>>>(gr, c->w[ENERO_ACTOR], c->t_h[T].as<float>(), c->t_logits.as<float>()); LAUNCH_CHECK(c);
+        k_ppo_actor_head<<<(n + 3) / 4, 128, 0, st>>>(n, Kmax, nK, c->t_logits.as<float>(), action, old_prob, advantage, inv_m,
+                                                      entropy_beta, clipping_val, c->t_dlogit.as<float>(), c->t_loss.as<float>(),
+                                                      c->t_ent.as<float>()); LAUNCH_CHECK(c);
+        k_sum_into<<<1, 32, 0, st>>>(n, c->t_loss.as<float>(), sums + 0); LAUNCH_CHECK(c);
+        k_sum_into<<<1, 32, 0, st>>>(n, c->t_ent.as<float>(), sums + 1); LAUNCH_CHECK(c);
+        TrainTopo g{n, Kmax, E, RPD, rows, nK};
+        TRY(train_backward(c, t, g, ENERO_ACTOR, T, c->t_dlogit.as<float>()));
+    }
+    // ---- critic: one graph per sample
+    {
+        const int64_t rows = (int64_t)n * E;
+        TRY(ensure_ones(c, n));
+        const int* ones = c->ones.as<int>();
+        k_features_critic<<<(int)((rows + MP_TPB - 1) / MP_TPB), MP_TPB, 0, st>>>(tv, n, c->util.as<float>(), c->w[ENERO_CRITIC],
+                                                                                c->t_h[0].as<float>(), c->t_A[0].as<float>()); LAUNCH_CHECK(c);
+        IdxTopo idx{rows, E, d.off_f, d.off_s, E, ones, d.in_off, d.in_first};
+        TRY(train_forward(c, idx, ENERO_CRITIC, T, rows));
+        GraphsTopo gr{n, 1, E, E, ones};
+        k_readout<GraphsTopo><<<(n + 3) / 4, 128, 0, st>>>(gr, c->w[ENERO_CRITIC], c->t_h[T].as<float>(), c->t_logits.as<float>()); LAUNCH_CHECK(c);
+        k_ppo_critic_head<<<(n + 127) / 128, 128, 0, st>>>(n, c->t_logits.as<float>(), ret, inv_m, c->t_dlogit.as<float>(), c->t_loss.as<float>());
+        LAUNCH_CHECK(c);
+        k_sum_into<<<1, 32, 0, st>>>(n, c->t_loss.as<float>(), sums + 2); LAUNCH_CHECK(c);
+        TrainTopo g{n, 1, E, E, rows, ones};
+        TRY(train_backward(c, t, g, ENERO_CRITIC, T, c->t_dlogit.as<float>()));
+    }
+    if (ptr_kind == ENERO_HOST) CUDA_TRY(cudaStreamSynchronize(st));    // the staging buffers may be reused by the caller
+    return ENERO_OK;
+}
+
+extern "C" int enero_ppo_apply(enero_ctx* c, float lr, float beta1, float beta2, float eps, float clip_norm,
+                               int64_t step, float* grad_norm_host) {
+    if (!c || step < 1 || !(clip_norm > 0)) return fail(ENERO_ERR_INVALID, "enero_ppo_apply: bad argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    // Keras Adam._prepare_local in fp32: lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t)
+    const float t = (float)step;
+    const float alpha = lr * std::sqrt(1.0f - std::pow(beta2, t)) / (1.0f - std::pow(beta1, t));
+    TRY(c->t_norm.ensure(16));
+    k_clip_adam<<<1, 1024, 0, c->stream>>>(c->w[0], c->w[1], c->grad[0], c->grad[1], c->adam_m[0], c->adam_v[0], c->adam_m[1],
+                                           c->adam_v[1], alpha, beta1, beta2, eps, clip_norm, c->t_norm.as<float>());
+    LAUNCH_CHECK(c);
+    CUDA_TRY(cudaMemsetAsync(c->gradbuf + 2 * ENERO_GRAD_STRIDE, 0, 16, c->stream));
+    if (grad_norm_host) {
+        CUDA_TRY(cudaMemcpyAsync(grad_norm_host, c->t_norm.p, 4, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+    }
+    return ENERO_OK;
+}
+
+extern "C" int enero_ppo_grad_download(enero_ctx* c, float* actor, float* critic, float* sums) {
+    if (!c) return fail(ENERO_ERR_INVALID, "null ctx");
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (actor) CUDA_TRY(cudaMemcpyAsync(actor, c->grad[0], sizeof(float) * ENERO_NPARAMS, cudaMemcpyDeviceToHost, c->stream));
+    if (critic) CUDA_TRY(cudaMemcpyAsync(critic, c->grad[1], sizeof(float) * ENERO_NPARAMS, cudaMemcpyDeviceToHost, c->stream));
+    if (sums) CUDA_TRY(cudaMemcpyAsync(sums, c->gradbuf + 2 * ENERO_GRAD_STRIDE, sizeof(float) * 3, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return ENERO_OK;
+}
+
+extern "C" int enero_adam_slots_upload(enero_ctx* c, int which, const float* m, const float* v) {
+    if (!c || !m || !v || which < 0 || which > 1) return fail(ENERO_ERR_INVALID, "enero_adam_slots_upload: bad argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaMemcpyAsync(c->adam_m[which], m, sizeof(float) * ENERO_NPARAMS, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->adam_v[which], v, sizeof(float) * ENERO_NPARAMS, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return ENERO_OK;
+}
+extern "C" int enero_adam_slots_download(enero_ctx* c, int which, float* m, float* v) {
+    if (!c || !m || !v || which < 0 || which > 1) return fail(ENERO_ERR_INVALID, "enero_adam_slots_download: bad argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaMemcpyAsync(m, c->adam_m[which], sizeof(float) * ENERO_NPARAMS, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(v, c->adam_v[which], sizeof(float) * ENERO_NPARAMS, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return ENERO_OK;
+}
+
+extern "C" int enero_gae(enero_ctx* c, int n, const float* values, const uint8_t* masks, const double* rewards,
+                         double gamma, double lmbda, double* returns, double* advantages) {
+    if (!c || n < 1 || !values || !masks || !rewards || !returns || !advantages) return fail(ENERO_ERR_INVALID, "enero_gae: bad argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    DevBuf dv, dm, dr, dret, dadv;
+    TRY(dv.ensure((size_t)(n + 1) * 4)); TRY(dm.ensure(n)); TRY(dr.ensure((size_t)n * 8)); TRY(dret.ensure((size_t)n * 8)); TRY(dadv.ensure((size_t)n * 8));
+    CUDA_TRY(cudaMemcpyAsync(dv.p, values, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(dm.p, masks, n, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(dr.p, rewards, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    k_gae<<<1, 32, 0, st>>>(n, dv.as<float>(), dm.as<unsigned char>(), dr.as<double>(), gamma, lmbda, dret.as<double>(), dadv.as<double>());
+    LAUNCH_CHECK(c);
+    CUDA_TRY(cudaMemcpyAsync(returns, dret.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(advantages, dadv.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return ENERO_OK;
+}

@@ -75,24 +75,53 @@ __device__ __forceinline__ void mv_bwd(float (&acc)[H], const float (&d)[H], con
 // ---- GRU backward of one iteration ------------------------------------------------------------------
 // ht = h_t, At = A_t (forward saves); dhn = dL/dh_{t+1}.  Writes agg_t, gate-gradient rows
 // G = [dpz | dpr | dx | dy], B_t, dagg and the GRU part of dL/dh_t.
+// Mat-vecs run as rolled loops over blocks of four outputs with the reduction index fully unrolled
+// (same code-size discipline as k_mp_iter: a fully unrolled version is ~5000 FMAs of straight-line
+// code that ptxas spills to a 16 KB stack frame); vectors whose block index is dynamic go through
+// per-thread shared-memory slots (80-byte stride: conflict-free LDS/STS.128).
+constexpr int BWG_SMEM_FLOATS = W_MP_FLOATS + 4 * BW_TPB * H;
+constexpr size_t BWG_SMEM_BYTES = sizeof(float) * BWG_SMEM_FLOATS;
+
+__device__ __forceinline__ float4 f4_fma(float x, const float4 w, float4 a) {
+    a.x = fmaf(x, w.x, a.x); a.y = fmaf(x, w.y, a.y); a.z = fmaf(x, w.z, a.z); a.w = fmaf(x, w.w, a.w);
+    return a;
+}
+__device__ __forceinline__ float f4_dot(const float (&d)[H], int j, const float4 w, float s) {
+    s = fmaf(d[j], w.x, s); s = fmaf(d[j + 1], w.y, s); s = fmaf(d[j + 2], w.z, s); s = fmaf(d[j + 3], w.w, s);
+    return s;
+}
+
 __global__ void __launch_bounds__(BW_TPB)
 k_bwd_gates(const IdxTopo idx, const float* __restrict__ wflat, const float* __restrict__ ht,
             const float* __restrict__ At, const float* __restrict__ dhn, float* __restrict__ agg_out,
             float* __restrict__ G_out, float* __restrict__ B_out, float* __restrict__ dagg_out,
             float* __restrict__ dh_part) {
-    __shared__ __align__(16) float sw[W_MP_FLOATS];
+    extern __shared__ __align__(16) float bwg_smem[];
+    float* sw = bwg_smem;
     for (int i = threadIdx.x; i < W_MP_FLOATS / 4; i += BW_TPB)
         reinterpret_cast<float4*>(sw)[i] = reinterpret_cast<const float4*>(wflat)[i];
     __syncthreads();
     const int64_t r = (int64_t)blockIdx.x * BW_TPB + threadIdx.x;
     if (!idx.valid(r)) return;
-    float h[H], agg[H], t[H];
-    load_row(h, ht + r * H);
+    float* slot[4];
 #pragma unroll
-    for (int j = 0; j < H; ++j) { t[j] = sw[W_MSG_B + j]; agg[j] = 0.f; }
-    mv_fwd<H>(t, h, sw + W_MSG_K + H * H);
-    store_row(B_out + r * H, t);
+    for (int q = 0; q < 4; ++q) slot[q] = sw + W_MP_FLOATS + (q * BW_TPB + threadIdx.x) * H;
+    float h[H], agg[H];
+    load_row(h, ht + r * H);
+    // ---- B = bm + h . Wm[20:40]
+#pragma unroll 1
+    for (int jb = 0; jb < H / 4; ++jb) {
+        float4 acc = *reinterpret_cast<const float4*>(sw + W_MSG_B + 4 * jb);
+#pragma unroll
+        for (int k = 0; k < H; ++k) acc = f4_fma(h[k], *reinterpret_cast<const float4*>(sw + W_MSG_K + H * H + k * H + 4 * jb), acc);
+        *reinterpret_cast<float4*>(slot[0] + 4 * jb) = acc;
+        *reinterpret_cast<float4*>(B_out + r * H + 4 * jb) = acc;
+    }
     {
+        float t[H];
+        load_row(t, slot[0]);
+#pragma unroll
+        for (int j = 0; j < H; ++j) agg[j] = 0.f;
         int pb, pe; const int* list; int64_t add;
         idx.seg(r, pb, pe, list, add);
         for (int p = pb; p < pe; ++p) {
@@ -103,42 +132,82 @@ k_bwd_gates(const IdxTopo idx, const float* __restrict__ wflat, const float* __r
         }
     }
     store_row(agg_out + r * H, agg);
-    float z[H], rg[H], y[H], c[H];
+    // ---- gates of four outputs at a time and their local derivatives
+#pragma unroll 1
+    for (int jb = 0; jb < H / 4; ++jb) {
+        float4 z = *reinterpret_cast<const float4*>(sw + W_GRU_B + 4 * jb);
+        float4 rg = *reinterpret_cast<const float4*>(sw + W_GRU_B + 20 + 4 * jb);
+        float4 c = *reinterpret_cast<const float4*>(sw + W_GRU_B + 40 + 4 * jb);
+        float4 y = *reinterpret_cast<const float4*>(sw + W_GRU_B + 100 + 4 * jb);
 #pragma unroll
-    for (int j = 0; j < H; ++j) { z[j] = sw[W_GRU_B + j]; rg[j] = sw[W_GRU_B + 20 + j]; y[j] = sw[W_GRU_B + 100 + j]; c[j] = sw[W_GRU_B + 40 + j]; }
-    mv_fwd<60>(z, agg, sw + W_GRU_K);       mv_fwd<60>(z, h, sw + W_GRU_R);
-    mv_fwd<60>(rg, agg, sw + W_GRU_K + 20); mv_fwd<60>(rg, h, sw + W_GRU_R + 20);
-    mv_fwd<60>(y, h, sw + W_GRU_R + 40);
-    mv_fwd<60>(c, agg, sw + W_GRU_K + 40);
-    float dh[H];
-    load_row(dh, dhn + r * H);
-    float dpz[H], dpr[H], dx[H], dy[H];
+        for (int k = 0; k < H; ++k) {
+            const float* K = sw + W_GRU_K + k * 60 + 4 * jb;
+            const float* R = sw + W_GRU_R + k * 60 + 4 * jb;
+            z = f4_fma(agg[k], *reinterpret_cast<const float4*>(K), z);
+            z = f4_fma(h[k], *reinterpret_cast<const float4*>(R), z);
+            rg = f4_fma(agg[k], *reinterpret_cast<const float4*>(K + 20), rg);
+            rg = f4_fma(h[k], *reinterpret_cast<const float4*>(R + 20), rg);
+            c = f4_fma(agg[k], *reinterpret_cast<const float4*>(K + 40), c);
+            y = f4_fma(h[k], *reinterpret_cast<const float4*>(R + 40), y);
+        }
+        const float4 b1z = *reinterpret_cast<const float4*>(sw + W_GRU_B + 60 + 4 * jb);
+        const float4 b1r = *reinterpret_cast<const float4*>(sw + W_GRU_B + 80 + 4 * jb);
+        const float4 g4 = *reinterpret_cast<const float4*>(dhn + r * H + 4 * jb);
+        const float4 h4 = *reinterpret_cast<const float4*>(ht + r * H + 4 * jb);
+        const float zv[4] = {z.x + b1z.x, z.y + b1z.y, z.z + b1z.z, z.w + b1z.w};
+        const float rv[4] = {rg.x + b1r.x, rg.y + b1r.y, rg.z + b1r.z, rg.w + b1r.w};
+        const float cv[4] = {c.x, c.y, c.z, c.w}, yv[4] = {y.x, y.y, y.z, y.w};
+        const float gv[4] = {g4.x, g4.y, g4.z, g4.w}, hv[4] = {h4.x, h4.y, h4.z, h4.w};
+        float dpz[4], dpr[4], dx[4], dy[4], dhz[4];
 #pragma unroll
-    for (int j = 0; j < H; ++j) {
-        const float zz = sigmoid_fast(z[j] + sw[W_GRU_B + 60 + j]);
-        const float rr = sigmoid_fast(rg[j] + sw[W_GRU_B + 80 + j]);
-        const float cc = tanh_fast(c[j] + rr * y[j]);
-        const float g = dh[j];
-        const float dz = g * (h[j] - cc);
-        const float dc = g * (1.f - zz);
-        const float dpc = dc * (1.f - cc * cc);
-        dx[j] = dpc;
-        dy[j] = dpc * rr;
-        dpr[j] = dpc * y[j] * rr * (1.f - rr);
-        dpz[j] = dz * zz * (1.f - zz);
-        dh[j] = g * zz;
+        for (int i = 0; i < 4; ++i) {
+            const float zz = sigmoid_fast(zv[i]);
+            const float rr = sigmoid_fast(rv[i]);
+            const float cc = tanh_fast(cv[i] + rr * yv[i]);
+            const float dz = gv[i] * (hv[i] - cc);
+            const float dpc = gv[i] * (1.f - zz) * (1.f - cc * cc);
+            dx[i] = dpc;
+            dy[i] = dpc * rr;
+            dpr[i] = dpc * yv[i] * rr * (1.f - rr);
+            dpz[i] = dz * zz * (1.f - zz);
+            dhz[i] = gv[i] * zz;
+        }
+        const float4 o0 = make_float4(dpz[0], dpz[1], dpz[2], dpz[3]), o1 = make_float4(dpr[0], dpr[1], dpr[2], dpr[3]);
+        const float4 o2 = make_float4(dx[0], dx[1], dx[2], dx[3]), o3 = make_float4(dy[0], dy[1], dy[2], dy[3]);
+        *reinterpret_cast<float4*>(slot[0] + 4 * jb) = o0; *reinterpret_cast<float4*>(slot[1] + 4 * jb) = o1;
+        *reinterpret_cast<float4*>(slot[2] + 4 * jb) = o2; *reinterpret_cast<float4*>(slot[3] + 4 * jb) = o3;
+        float* G = G_out + r * 4 * H + 4 * jb;
+        *reinterpret_cast<float4*>(G) = o0; *reinterpret_cast<float4*>(G + H) = o1;
+        *reinterpret_cast<float4*>(G + 2 * H) = o2; *reinterpret_cast<float4*>(G + 3 * H) = o3;
+        *reinterpret_cast<float4*>(dh_part + r * H + 4 * jb) = make_float4(dhz[0], dhz[1], dhz[2], dhz[3]);
     }
-    store_row(G_out + r * 4 * H, dpz);
-    store_row(G_out + r * 4 * H + H, dpr);
-    store_row(G_out + r * 4 * H + 2 * H, dx);
-    store_row(G_out + r * 4 * H + 3 * H, dy);
-    float dagg[H];
+    // ---- dagg = [dpz dpr dx] . K^T ; dh += [dpz dpr dy] . R^T, four rows of K / R at a time
+    float dpz[H], dpr[H], dx[H], dy[H];
+    load_row(dpz, slot[0]); load_row(dpr, slot[1]); load_row(dx, slot[2]); load_row(dy, slot[3]);
+#pragma unroll 1
+    for (int kb = 0; kb < H / 4; ++kb) {
+        float da[4], dhh[4];
 #pragma unroll
-    for (int j = 0; j < H; ++j) dagg[j] = 0.f;
-    mv_bwd<60>(dagg, dpz, sw + W_GRU_K); mv_bwd<60>(dagg, dpr, sw + W_GRU_K + 20); mv_bwd<60>(dagg, dx, sw + W_GRU_K + 40);
-    mv_bwd<60>(dh, dpz, sw + W_GRU_R);   mv_bwd<60>(dh, dpr, sw + W_GRU_R + 20);   mv_bwd<60>(dh, dy, sw + W_GRU_R + 40);
-    store_row(dagg_out + r * H, dagg);
-    store_row(dh_part + r * H, dh);
+        for (int kk = 0; kk < 4; ++kk) {
+            const float* K = sw + W_GRU_K + (4 * kb + kk) * 60;
+            const float* R = sw + W_GRU_R + (4 * kb + kk) * 60;
+            float s0 = 0.f, s1 = 0.f, u0 = 0.f, u1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < H; j += 4) {
+                s0 = f4_dot(dpz, j, *reinterpret_cast<const float4*>(K + j), s0);
+                s1 = f4_dot(dpr, j, *reinterpret_cast<const float4*>(K + 20 + j), s1);
+                s0 = f4_dot(dx, j, *reinterpret_cast<const float4*>(K + 40 + j), s0);
+                u0 = f4_dot(dpz, j, *reinterpret_cast<const float4*>(R + j), u0);
+                u1 = f4_dot(dpr, j, *reinterpret_cast<const float4*>(R + 20 + j), u1);
+                u0 = f4_dot(dy, j, *reinterpret_cast<const float4*>(R + 40 + j), u0);
+            }
+            da[kk] = s0 + s1; dhh[kk] = u0 + u1;
+        }
+        *reinterpret_cast<float4*>(dagg_out + r * H + 4 * kb) = make_float4(da[0], da[1], da[2], da[3]);
+        float4 prev = *reinterpret_cast<float4*>(dh_part + r * H + 4 * kb);
+        prev.x += dhh[0]; prev.y += dhh[1]; prev.z += dhh[2]; prev.w += dhh[3];
+        *reinterpret_cast<float4*>(dh_part + r * H + 4 * kb) = prev;
+    }
 }
 
 // ---- message backward of one iteration -----------------------------------------------------------------
@@ -304,7 +373,7 @@ __device__ __forceinline__ void wgrad_cols(int o, int& xc, int& dc) {
 }
 
 __global__ void __launch_bounds__(WG_TPB)
-k_wgrad(const IdxTopo idx, int T, const WgradIter* __restrict__ iters, int64_t ntiles, float* __restrict__ partials) {
+k_wgrad(const IdxTopo idx, const WgradIter it, int64_t ntiles, float* __restrict__ partials) {
     __shared__ float sx[WG_ROWS * WG_XW];
     __shared__ float sd[WG_ROWS * (WG_DW + 1)];
     __shared__ unsigned char s_ok[WG_ROWS];
@@ -316,10 +385,8 @@ k_wgrad(const IdxTopo idx, int T, const WgradIter* __restrict__ iters, int64_t n
         acc[m] = 0.f; xc[m] = 40; dc[m] = 0;
         if (o < W_MP_FLOATS) wgrad_cols(o, xc[m], dc[m]);
     }
-    for (int64_t tile = blockIdx.x; tile < ntiles * T; tile += gridDim.x) {
-        const int t = (int)(tile / ntiles);
-        const int64_t r0 = (tile - (int64_t)t * ntiles) * WG_ROWS;
-        const WgradIter it = iters[t];
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t r0 = tile * WG_ROWS;
         __syncthreads();
         if (threadIdx.x < WG_ROWS) s_ok[threadIdx.x] = idx.valid(r0 + threadIdx.x) ? 1 : 0;
         __syncthreads();
@@ -421,6 +488,14 @@ __global__ void k_ppo_critic_head(int n, const float* __restrict__ value, const 
     const float d = ret[b] - value[b];
     loss_out[b] = d * d;
     dvalue[b] = -2.f * d * inv_m;
+}
+
+// dst += sum(x[0..n)) in a fixed order (one warp: lane-strided partial sums, then the shuffle tree)
+__global__ void k_sum_into(int n, const float* __restrict__ x, float* __restrict__ dst) {
+    float s = 0.f;
+    for (int i = threadIdx.x; i < n; i += 32) s += x[i];
+    s = warp_sum(s);
+    if (threadIdx.x == 0) *dst += s;
 }
 
 // ---- clip_by_global_norm + Adam for both models (single CTA) ----------------------------------------------------

@@ -37,6 +37,8 @@ extern "C" {
 
 #define ENERO_H 20            /* link_state_dim  (train_Enero_3top_script.py:83) */
 #define ENERO_NPARAMS 4201    /* parameters per model, Keras variable order (:238-248) */
+#define ENERO_GRAD_STRIDE 4204  /* floats between the actor and critic halves of the gradient buffer */
+#define ENERO_GRAD_FLOATS (2 * ENERO_GRAD_STRIDE + 4)
 
 typedef struct enero_ctx enero_ctx;
 typedef struct enero_topo enero_topo;
@@ -162,6 +164,41 @@ int enero_batch_local_search(enero_batch* b, int mode, const int32_t* routing, c
                              int32_t* moves, double* move_val);
 /* critical demands chosen by the last enero_batch_local_search reset: elig int32[B,Dcap,2] */
 int enero_batch_get_ls_eligible(enero_batch* b, int32_t* elig, int32_t* elig_len, int cap);
+
+/* ---- PPO update (train_Enero_3top_script.py:264-377) ---------------------------------------
+ * The gradient buffer is one device array fp32[ENERO_GRAD_FLOATS]:
+ *   [0, 4201)                       d total_loss / d actor weights   (Keras variable order)
+ *   [STRIDE, STRIDE + 4201)         d total_loss / d critic weights
+ *   [2*STRIDE + 0 / 1 / 2]          sum of actor sample losses / entropies / critic sample losses
+ * A rank of a sharded PPO step all-reduces (sum) exactly this array, then every rank applies. */
+void* enero_ppo_grad_buffer(enero_ctx* ctx);
+int enero_ppo_zero_grad(enero_ctx* ctx);
+/* _train_step_combined (train script :293-315), gradient part, for n samples that share one topology:
+ * actor forward over the K' candidate graphs of demand sd[i] (bandwidth bw[i]) on link loads loads[i]
+ * (the same state pred_action_distrib_sp saw), critic forward on the same loads, the per-sample losses
+ * of _actor_step (:273-291) / _critic_step (:264-271), and the backward pass.  Adds the gradient of
+ *   inv_m * sum_i [ loss_i - entropy_beta * entropy_i + critic_loss_i ]
+ * and the three loss sums into the gradient buffer (inv_m = 1 / minibatch size gives reduce_mean).
+ * loads fp64[n,E]; sd int32[n,2]; bw fp64[n]; action int32[n]; old_prob fp32[n] = old policy's
+ * probability of the action; advantage, ret fp32[n].  All pointers host (ENERO_HOST) or device. */
+int enero_ppo_accumulate(enero_ctx* ctx, enero_topo* topo, int n, const double* loads, const int32_t* sd,
+                         const double* bw, const int32_t* action, const float* old_prob,
+                         const float* advantage, const float* ret, float inv_m, float entropy_beta,
+                         float clipping_val, int ptr_kind);
+/* tf.clip_by_global_norm(grad, clip_norm) over all 22 tensors + Adam.apply_gradients (train script
+ * :317-320; Keras Adam dense update).  `step` = optimizer.iterations + 1.  Zeroes the gradient buffer.
+ * grad_norm_host (nullable) receives the global norm before clipping. */
+int enero_ppo_apply(enero_ctx* ctx, float lr, float beta1, float beta2, float eps, float clip_norm,
+                    int64_t step, float* grad_norm_host);
+/* host copies of the gradient buffer halves (any pointer may be NULL): actor/critic fp32[4201], sums fp32[3] */
+int enero_ppo_grad_download(enero_ctx* ctx, float* actor, float* critic, float* sums);
+/* Adam slot variables m, v of one model, flat fp32[4201] (checkpoint .OPTIMIZER_SLOT entries) */
+int enero_adam_slots_upload(enero_ctx* ctx, int which, const float* m, const float* v);
+int enero_adam_slots_download(enero_ctx* ctx, int which, float* m, float* v);
+/* get_advantages (train script :367-377): GAE over n steps in fp64.  values fp32[n+1], masks u8[n],
+ * rewards fp64[n] -> returns fp64[n], advantages fp64[n] ((adv - mean) / (std + 1e-10)).  Host pointers. */
+int enero_gae(enero_ctx* ctx, int n, const float* values, const uint8_t* masks, const double* rewards,
+              double gamma, double lmbda, double* returns, double* advantages);
 
 #ifdef __cplusplus
 }

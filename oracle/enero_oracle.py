@@ -498,7 +498,11 @@ def local_search(env: Env15, current):
 # PPO pieces (train_Enero_3top_script.py:264-377)
 # ==========================================================================
 def get_advantages(values, masks, rewards, gamma=0.99, lmbda=0.95):
-    """train_Enero_3top_script.py:367-377 (python floats / numpy, as written)."""
+    """train_Enero_3top_script.py:367-377.  The reference runs under numpy 1.19.5
+    (requirements.txt:41), where `python float * np.float32 scalar` promotes to float64; under
+    numpy >= 2 (NEP 50) the same expression would stay float32, so the critic values are widened
+    explicitly to keep the reference's arithmetic."""
+    values = [np.float64(v) for v in values]
     returns = []
     gae = 0
     for i in reversed(range(len(rewards))):

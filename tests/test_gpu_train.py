@@ -1,0 +1,187 @@
+"""GPU parity of the PPO update (kernel family 5: backward kernels, PPO loss head, global-norm
+clip + Adam, GAE) against the torch-CPU restatement in oracle/ppo_torch.py.
+
+Tolerances (fp32, written here as north_star asks): a gradient tensor entry is a sum of many
+products of O(1) activations, so errors are measured against the largest magnitude of the flat
+gradient: |got - want| <= GRAD_RTOL * max|want|.  The forward/backward kernels use MUFU
+ex2/rcp approximations (about 1e-6 relative per transcendental), hence 1e-4 rather than 1e-5 for
+gradients; losses, the clip scale and the Adam update are compared at 1e-5.
+"""
+import numpy as np
+import pytest
+
+from conftest import case_graph_file, load_case
+from oracle import enero_oracle as orc
+from oracle import ppo_torch as ppo_o
+
+pytestmark = pytest.mark.gpu
+
+GRAD_RTOL = 1e-4
+RTOL = 1e-5
+BETA = 0.01
+
+
+def _critic_weights(weights):
+    rng = np.random.default_rng(7)
+    return {k: (weights[k] + rng.normal(0, 0.05, weights[k].shape)).astype(np.float32) for k in orc.WEIGHT_NAMES}
+
+
+def _rollout(name, weights, n_samples, seed, tmp):
+    """n_samples decisions with sampled actions on the oracle env; returns (gpu topology, oracle samples,
+    gpu sample records)."""
+    from enero_b200.topology import Topology
+    case = load_case(name)
+    gf = case_graph_file(case, tmp)
+    topo, ot = Topology(gf, K=100), orc.Topology(gf, K=100)
+    rng = np.random.default_rng(seed)
+    tm_ids = sorted(case["tms"].keys())
+    o_samples, g_samples = [], []
+    ti = 0
+    while len(o_samples) < n_samples:
+        tm = np.array(case["tms"][tm_ids[ti % len(tm_ids)]])
+        ti += 1
+        env = orc.Env16(ot)
+        _, s, d = env.reset(tm)
+        while len(o_samples) < n_samples:
+            probs, batch, _ = orc.pred_action_distrib(weights, env, s, d)
+            a = int(rng.choice(len(probs), p=probs.astype(np.float64) / probs.astype(np.float64).sum()))
+            onehot = np.zeros(len(probs), np.float32)
+            onehot[a] = 1.0
+            # a perturbed "old" policy so that ratios land on both sides of the clip interval
+            oldp = probs * np.exp(rng.normal(0, 0.15, len(probs))).astype(np.float32)
+            oldp = (oldp / oldp.sum()).astype(np.float32)
+            adv = np.float32(rng.normal())
+            ret = np.float32(rng.normal())
+            smp = dict(batch)
+            smp.update(link_state_critic=env.critic_features(), first_critic=ot.first, second_critic=ot.second,
+                       num_edges_critic=ot.E, old_act=onehot, old_policy_probs=oldp, advantage=adv)
+            smp["return"] = ret
+            o_samples.append(smp)
+            g = {"topology": topo, "loads": env.loads.copy(), "sd": (s, d), "bw": float(env.tm[s, d]),
+                 "action": a, "old_prob": np.float32(oldp[a]), "advantage": adv, "return": ret}
+            g_samples.append(g)
+            _, done, _, _, s, d, _, _, _ = env.step(a)
+            if done:
+                break
+    return topo, o_samples, g_samples
+
+
+@pytest.fixture(scope="module")
+def agent(weights):
+    from enero_b200.ppo import PPOActorCritic
+    from enero_b200.runtime import Context
+    ctx = Context(0)
+    ag = PPOActorCritic(context=ctx, entropy_beta=BETA)
+    ag.actor.set_weights([weights[k] for k in orc.WEIGHT_NAMES])
+    cw = _critic_weights(weights)
+    ag.critic.set_weights([cw[k] for k in orc.WEIGHT_NAMES])
+    yield ag, cw
+    ctx.close()
+
+
+def _assert_grad(got, want, what):
+    scale = float(np.abs(want).max())
+    err = float(np.abs(got.astype(np.float64) - want.astype(np.float64)).max())
+    assert err <= GRAD_RTOL * scale, "%s: max |diff| %.3e > %.1e * %.3e" % (what, err, GRAD_RTOL, scale)
+
+
+@pytest.mark.parametrize("names,n", [(("tri9",), 6), (("tiny12",), 9), (("eli20", "zoo30"), 7)])
+def test_minibatch_gradients(agent, weights, names, n, tmp_path_factory):
+    """_train_step_combined's tape.gradient over one minibatch (train script :293-317), including a
+    minibatch that mixes topologies (the 835-sample buffer holds three)."""
+    ag, cw = agent
+    o_all, g_all = [], []
+    for i, name in enumerate(names):
+        _, o, g = _rollout(name, weights, n, 11 + i, tmp_path_factory.mktemp("r" + name))
+        o_all += o
+        g_all += g
+    ag.memory = g_all
+    ga, gc, sums = ag.gradients(np.arange(len(g_all)))
+    wa, wc = ppo_o.to_params(weights), ppo_o.to_params(cw)
+    oa, oc, al, cl, ent = ppo_o.gradients(wa, wc, o_all, BETA)
+    m = len(g_all)
+    np.testing.assert_allclose(sums[1] / m, ent, rtol=RTOL)
+    np.testing.assert_allclose(sums[0] / m - BETA * sums[1] / m, al, rtol=RTOL, atol=1e-6)
+    np.testing.assert_allclose(sums[2] / m, cl, rtol=RTOL)
+    _assert_grad(ga, oa, "actor gradient")
+    _assert_grad(gc, oc, "critic gradient")
+    # per-tensor check so that a small tensor cannot hide behind a large one
+    o = 0
+    for k in orc.WEIGHT_NAMES:
+        sz = weights[k].size
+        if np.abs(oa[o:o + sz]).max() > 1e-3 * np.abs(oa).max():
+            _assert_grad(ga[o:o + sz], oa[o:o + sz], "actor " + k)
+        if np.abs(oc[o:o + sz]).max() > 1e-3 * np.abs(oc).max():
+            _assert_grad(gc[o:o + sz], oc[o:o + sz], "critic " + k)
+        o += sz
+    ag.memory = []
+
+
+def test_train_steps_match_oracle(agent, weights, tmp_path_factory):
+    """three consecutive _train_step_combined calls (gradient, clip_by_global_norm(0.5), Adam) leave the
+    same weights and slots as the oracle's restatement of Keras Adam."""
+    ag, cw = agent
+    _, o, g = _rollout("eli20", weights, 12, 5, tmp_path_factory.mktemp("steps"))
+    ag.memory = g
+    wa, wc = ppo_o.to_params(weights), ppo_o.to_params(cw)
+    fa = ppo_o.flat([weights[k] for k in orc.WEIGHT_NAMES])
+    fc = ppo_o.flat([cw[k] for k in orc.WEIGHT_NAMES])
+    slots = [np.zeros_like(fa) for _ in range(4)]       # ma, va, mc, vc
+    lr = float(ag.optimizer.learning_rate)
+    import torch
+    for step, inds in enumerate(([0, 1, 2, 3], [4, 5, 6, 7, 8], [9, 10, 11, 0]), start=1):
+        got = ag._train_step_combined(np.array(inds))
+        oa, oc, al, cl, ent = ppo_o.gradients(wa, wc, [o[i] for i in inds], BETA)
+        (ca, cc), norm = ppo_o.clip_by_global_norm([oa, oc], 0.5)
+        np.testing.assert_allclose(ag.last_grad_norm, norm, rtol=1e-4)
+        np.testing.assert_allclose(got, (al, cl, ent), rtol=1e-4, atol=1e-6)
+        fa, slots[0], slots[1] = ppo_o.adam_step(fa, slots[0], slots[1], ca, lr, step)
+        fc, slots[2], slots[3] = ppo_o.adam_step(fc, slots[2], slots[3], cc, lr, step)
+        with torch.no_grad():
+            for w, f in ((wa, fa), (wc, fc)):
+                off = 0
+                for k in orc.WEIGHT_NAMES:
+                    sz = w[k].numel()
+                    w[k].copy_(torch.tensor(f[off:off + sz]).reshape(w[k].shape))
+                    off += sz
+    ga = np.concatenate([w.reshape(-1) for w in ag.context.download_weights(0)])
+    gc = np.concatenate([w.reshape(-1) for w in ag.context.download_weights(1)])
+    # three Adam steps of at most lr each: compare the *updates*, not just the weights
+    fa0 = ppo_o.flat([weights[k] for k in orc.WEIGHT_NAMES])
+    fc0 = ppo_o.flat([cw[k] for k in orc.WEIGHT_NAMES])
+    assert np.abs((ga - fa0) - (fa - fa0)).max() <= 2e-2 * np.abs(fa - fa0).max()
+    assert np.abs((gc - fc0) - (fc - fc0)).max() <= 2e-2 * np.abs(fc - fc0).max()
+    np.testing.assert_allclose(ga, fa, rtol=0, atol=3 * lr * 2e-2)
+    m, v = ag.download_slots(0)
+    gm = np.concatenate([x.reshape(-1) for x in m])
+    assert np.abs(gm - slots[0]).max() <= 1e-3 * np.abs(slots[0]).max()
+    # restore the module-scoped agent for other tests
+    ag.actor.set_weights([weights[k] for k in orc.WEIGHT_NAMES])
+    ag.critic.set_weights([cw[k] for k in orc.WEIGHT_NAMES])
+    ag.memory = []
+
+
+def test_gae(agent):
+    """get_advantages (train script :367-377) in fp64."""
+    from enero_b200.ppo import get_advantages
+    ag, _ = agent
+    rng = np.random.default_rng(3)
+    n = 835
+    values = [np.float32(v) for v in rng.normal(0, 1, n + 1)]
+    masks = [bool(b) for b in (rng.random(n) > 0.02)]
+    rewards = [np.float64(np.around(r, 2)) for r in rng.normal(0, 0.5, n)]
+    want_ret, want_adv = orc.get_advantages(values, masks, rewards)
+    ret, adv = get_advantages(values, masks, rewards, context=ag.context)
+    np.testing.assert_allclose(ret, np.array(want_ret, dtype=np.float64), rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(adv, want_adv, rtol=1e-10, atol=1e-12)
+
+
+def test_accumulate_rejects_bad_action(agent, weights, tmp_path_factory):
+    from enero_b200._lib import EneroError
+    ag, _ = agent
+    _, _, g = _rollout("tri9", weights, 2, 1, tmp_path_factory.mktemp("bad"))
+    g[0]["action"] = 999
+    ag.memory = g
+    with pytest.raises(EneroError):
+        ag.gradients(np.arange(2))
+    ag.memory = []
