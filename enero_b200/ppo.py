@@ -21,6 +21,7 @@ import numpy as np
 from . import _lib
 from .models import ActorModel, CriticModel
 from .optim import Adam
+from .parallel import shard_indices
 
 # train_Enero_3top_script.py:28-87
 MINI_BATCH_SIZE = 55
@@ -142,7 +143,7 @@ class PPOActorCritic:
         if self._pg is not None:
             import torch.distributed as dist
             rank, world = dist.get_rank(self._pg), dist.get_world_size(self._pg)
-            mine = inds[rank::world]
+            mine = shard_indices(inds, rank, world)
         _lib.check(self._lib.enero_ppo_zero_grad(self.context.handle))
         if len(mine):
             self._accumulate(self._group_by_topology(mine), 1.0 / m)
@@ -193,11 +194,25 @@ class PPOActorCritic:
         fm, fv = flatten_weights(m), flatten_weights(v)
         _lib.check(self._lib.enero_adam_slots_upload(self.context.handle, which, _lib.ptr(fm), _lib.ptr(fv)))
 
+    def load_optimizer_state(self):
+        """after Checkpoint.restore: push the restored Adam slots of both models to the device"""
+        for which, model in ((_lib.ACTOR, self.actor), (_lib.CRITIC, self.critic)):
+            m, v = self.optimizer.get_slots(model)
+            self.upload_slots(which, m, v)
+
+    def store_optimizer_state(self):
+        """before Checkpoint.save: pull weights and Adam slots of both models back to the host objects"""
+        for which, model in ((_lib.ACTOR, self.actor), (_lib.CRITIC, self.critic)):
+            model.sync_from_device()
+            m, v = self.download_slots(which)
+            self.optimizer.set_slots(model, m, v)
+
     def download_slots(self, which):
         from .runtime import unflatten_weights
         fm, fv = np.zeros(_lib.NPARAMS, np.float32), np.zeros(_lib.NPARAMS, np.float32)
         _lib.check(self._lib.enero_adam_slots_download(self.context.handle, which, _lib.ptr(fm), _lib.ptr(fv)))
         return unflatten_weights(fm), unflatten_weights(fv)
+
 
 
 def _device_view(ptr, n_floats, device):

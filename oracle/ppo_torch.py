@@ -103,7 +103,7 @@ def gradients(wa, wc, samples, entropy_beta):
     total.backward()
     ga = flat([wa[k].grad.numpy() if wa[k].grad is not None else np.zeros(tuple(wa[k].shape)) for k in orc.WEIGHT_NAMES])
     gc = flat([wc[k].grad.numpy() if wc[k].grad is not None else np.zeros(tuple(wc[k].shape)) for k in orc.WEIGHT_NAMES])
-    return ga, gc, float(al), float(cl), float(ent)
+    return ga, gc, float(al.detach()), float(cl.detach()), float(ent.detach())
 
 
 def clip_by_global_norm(grads, clip_norm):
