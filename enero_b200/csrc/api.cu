@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <type_traits>
@@ -15,6 +16,7 @@
 #include "enero_internal.h"
 #include "env_kernels.cuh"
 #include "gnn_kernels.cuh"
+#include "mp_tile_kernel.cuh"
 #include "train_kernels.cuh"
 
 using namespace enero;
@@ -49,6 +51,7 @@ extern "C" int enero_ctx_create(int device, enero_ctx** out) {
     CUDA_TRY(cudaMalloc(&c->gradbuf, sizeof(float) * ENERO_GRAD_FLOATS));
     CUDA_TRY(cudaMemset(c->gradbuf, 0, sizeof(float) * ENERO_GRAD_FLOATS));
     c->grad[0] = c->gradbuf; c->grad[1] = c->gradbuf + ENERO_GRAD_STRIDE;
+    CUDA_TRY(cudaMalloc(&c->tile_ctr, 16 * sizeof(int)));
     {
         int r = ENERO_OK;
         auto setup = [&](auto kern, int& occ) {
@@ -68,6 +71,10 @@ extern "C" int enero_ctx_create(int device, enero_ctx** out) {
         if (r != ENERO_OK) return r;
     }
     CUDA_TRY(cudaFuncSetAttribute(k_bwd_gates, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWG_SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(k_mp_tile<false, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize, MP_TILE_SMEM_MAX));
+    CUDA_TRY(cudaFuncSetAttribute(k_mp_tile<true, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize, MP_TILE_SMEM_MAX));
+    CUDA_TRY(cudaFuncSetAttribute(k_mp_tile<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, MP_TILE_SMEM_MAX));
+    if (const char* e = std::getenv("ENERO_MP_TPB")) c->tile_tpb_override = std::atoi(e);
     *out = c;
     return ENERO_OK;
 }
@@ -77,7 +84,7 @@ extern "C" int enero_ctx_destroy(enero_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (int i = 0; i < 2; ++i) { cudaFree(c->w[i]); cudaFree(c->adam_m[i]); cudaFree(c->adam_v[i]); }
-    cudaFree(c->gradbuf);
+    cudaFree(c->gradbuf); cudaFree(c->tile_ctr);
     cudaStreamDestroy(c->stream);
     delete c;
     return ENERO_OK;
@@ -173,30 +180,110 @@ static TopoView view_of(const enero_topo* t) {
 }
 
 // ---- message passing driver ---------------------------------------------------------------
+
+// CTA size / graphs per tile of k_mp_tile for a topology, or tpb = 0 when the generic k_mp_iter should run
+// (no pairs, graphs larger than a tile, or too few candidate graphs per decision to fill the slots).
+struct TileCfg { int tpb = 0, G = 0, TPD = 0, ctas = 0; size_t smem = 0; };
+static TileCfg mp_tile_config(const enero_ctx* c, int E, int off_f, int off_s, int Kmax) {
+    TileCfg best; double best_score = 0.0;
+    // measured slower than k_mp_iter on B200: opt-in through ENERO_MP_TPB
+    if (off_f <= 0 || off_s <= 0 || Kmax < 2 || c->tile_tpb_override <= 0) return best;
+    for (int tpb = 128; tpb <= 256; tpb += 32) {
+        if (c->tile_tpb_override > 0 && tpb != c->tile_tpb_override) continue;
+        const int slots = MP_R * tpb;
+        const int G = std::min(slots / off_s, Kmax);
+        if (G < 1 || Kmax * (E - off_s) > slots) continue;
+        const size_t smem = mp_tile_smem_bytes(tpb, G * off_f);
+        if (smem > (size_t)MP_TILE_SMEM_MAX) continue;
+        const int ctas = (int)std::min<size_t>((size_t)(233472 / (smem + 1024)), (size_t)(65536 / (168 * tpb)));
+        if (ctas < 1) continue;
+        const double util = (double)G * off_s / slots;
+        const double warps = ctas * tpb / 32.0;
+        const double score = util * std::sqrt(std::min(1.0, warps / 12.0));
+        if (util >= 0.6 && score > best_score) {
+            best_score = score; best.tpb = tpb; best.G = G; best.TPD = (Kmax + G - 1) / G + 1; best.ctas = ctas; best.smem = smem;
+        }
+    }
+    return best;
+}
+
+// a zeroed tile counter for the next k_mp_iter launch (re-zeroed in batches of 16 on the stream)
+static int next_tile_counter(enero_ctx* c, int** out) {
+    if (c->tile_ctr_next >= 16) {
+        CUDA_TRY(cudaMemsetAsync(c->tile_ctr, 0, 16 * sizeof(int), c->stream));
+        c->tile_ctr_next = 0;
+    }
+    *out = c->tile_ctr + c->tile_ctr_next++;
+    return ENERO_OK;
+}
+
+template <bool LAST, int KH>
+static void launch_tile(enero_ctx* c, const TileCfg& cfg, const TileTopo& tt, int which, const float* hin, const float* Ain,
+                        float* hout, float* Aout) {
+    const int ntiles = tt.B * cfg.TPD;
+    const int grid = std::min(ntiles, c->num_sms * cfg.ctas);
+    k_mp_tile<LAST, KH><<<grid, cfg.tpb, cfg.smem, c->stream>>>(tt, c->w[which], hin, Ain, hout, Aout, ntiles);
+}
+
+// one message-passing iteration of the implicit (per-topology) row space
+static int launch_topo_iteration(enero_ctx* c, const IdxTopo& idx, int which, bool last, bool sparse, const float* hin,
+                                 const float* Ain, float* hout, float* Aout) {
+    const int Kmax = idx.RPD / idx.E;
+    const TileCfg cfg = mp_tile_config(c, idx.E, idx.off_f, idx.off_s, Kmax);
+    const int64_t B = idx.total / idx.RPD;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (c->prof) {
+        CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+        CUDA_TRY(cudaEventRecord(e0, c->stream));
+    }
+    if (cfg.tpb > 0 && B * cfg.TPD < ((int64_t)1 << 31)) {
+        TileTopo tt{(int)B, idx.E, idx.off_f, idx.off_s, idx.RPD, cfg.G, cfg.TPD, idx.nK, idx.in_off, idx.in_first};
+        if (last) launch_tile<true, 20>(c, cfg, tt, which, hin, Ain, hout, Aout);
+        else if (sparse) launch_tile<false, 3>(c, cfg, tt, which, hin, Ain, hout, Aout);
+        else launch_tile<false, 20>(c, cfg, tt, which, hin, Ain, hout, Aout);
+    } else {
+        const int64_t ntiles = (idx.total + MP_ROWS - 1) / MP_ROWS;
+        const int occ = std::max(1, c->occ_iter[1][last ? 1 : 0]);
+        const int grid = (int)std::min<int64_t>(ntiles, (int64_t)c->num_sms * occ);
+        int* ctr = nullptr;
+        TRY(next_tile_counter(c, &ctr));
+        if (last) k_mp_iter<IdxTopo, true, 20><<<grid, MP_TPB, MP_SMEM_BYTES, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles, ctr);
+        else if (sparse) k_mp_iter<IdxTopo, false, 3><<<grid, MP_TPB, MP_SMEM_BYTES, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles, ctr);
+        else k_mp_iter<IdxTopo, false, 20><<<grid, MP_TPB, MP_SMEM_BYTES, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles, ctr);
+    }
+    LAUNCH_CHECK(c);
+    if (c->prof) { CUDA_TRY(cudaEventRecord(e1, c->stream)); c->prof_ev.emplace_back(e0, e1); }
+    return ENERO_OK;
+}
+
 // sparse_first: the rows of iteration 0 have at most 3 non-zero leading columns (fused feature path)
 template <class IDX>
 static int run_iterations(enero_ctx* c, const IDX& idx, int which, int T, int64_t rows, int idx_kind, bool sparse_first = false) {
     const int64_t ntiles = (rows + MP_ROWS - 1) / MP_ROWS;
+    if (rows >= (int64_t)1 << 31) return fail(ENERO_ERR_INVALID, "more than 2^31 link-state rows in one launch: split the batch");
     for (int it = 0; it < T; ++it) {
         const bool last = (it == T - 1);
-        const int occ = std::max(1, c->occ_iter[idx_kind][last ? 1 : 0]);
-        const int grid = (int)std::min<int64_t>(ntiles, (int64_t)c->num_sms * occ);
         const float* hin = c->h[it & 1].as<float>();
         const float* Ain = c->A[it & 1].as<float>();
         float* hout = c->h[(it + 1) & 1].as<float>();
         float* Aout = c->A[(it + 1) & 1].as<float>();
-        cudaEvent_t e0 = nullptr, e1 = nullptr;
-        if (c->prof) {
-            CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
-            CUDA_TRY(cudaEventRecord(e0, c->stream));
+        if constexpr (std::is_same<IDX, IdxTopo>::value) {
+            TRY(launch_topo_iteration(c, idx, which, last, it == 0 && sparse_first && !last, hin, Ain, hout, Aout));
+        } else {
+            const int occ = std::max(1, c->occ_iter[idx_kind][last ? 1 : 0]);
+            const int grid = (int)std::min<int64_t>(ntiles, (int64_t)c->num_sms * occ);
+            cudaEvent_t e0 = nullptr, e1 = nullptr;
+            if (c->prof) {
+                CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+                CUDA_TRY(cudaEventRecord(e0, c->stream));
+            }
+            int* ctr = nullptr;
+            TRY(next_tile_counter(c, &ctr));
+            if (last) k_mp_iter<IDX, true, 20><<<grid, MP_TPB, MP_SMEM_BYTES, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles, ctr);
+            else k_mp_iter<IDX, false, 20><<<grid, MP_TPB, MP_SMEM_BYTES, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles, ctr);
+            LAUNCH_CHECK(c);
+            if (c->prof) { CUDA_TRY(cudaEventRecord(e1, c->stream)); c->prof_ev.emplace_back(e0, e1); }
         }
-        if (last) k_mp_iter<IDX, true, 20><<<grid, MP_TPB, MP_SMEM_BYTES, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles);
-        else if (it == 0 && sparse_first) {
-            if constexpr (std::is_same<IDX, IdxTopo>::value)
-                k_mp_iter<IdxTopo, false, 3><<<grid, MP_TPB, MP_SMEM_BYTES, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles);
-        } else k_mp_iter<IDX, false, 20><<<grid, MP_TPB, MP_SMEM_BYTES, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles);
-        LAUNCH_CHECK(c);
-        if (c->prof) { CUDA_TRY(cudaEventRecord(e1, c->stream)); c->prof_ev.emplace_back(e0, e1); }
     }
     return ENERO_OK;
 }

@@ -63,6 +63,12 @@ __device__ __forceinline__ void store_row(float* __restrict__ p, const float (&v
 }
 
 // ---- row-space indexers -------------------------------------------------------
+struct RowRef {            // what k_mp_iter needs to know about one link-state row
+    bool ok;               // live row
+    int pb, pe;            // its incoming pairs: list[pb..pe)
+    const int* list;       // source rows (before `add`)
+    int64_t add;
+};
 // Explicit: arbitrary first/second of the signature-compatible path, as a CSR by
 // destination row built on device (stable in pair order).
 struct IdxExplicit {
@@ -70,8 +76,13 @@ struct IdxExplicit {
     const int* seg_off;   // [n+1]
     const int* src;       // [p] source rows in CSR order
     __device__ __forceinline__ bool valid(int64_t r) const { return r < n; }
+    __device__ __forceinline__ bool in_range(int64_t r) const { return r < n; }
     __device__ __forceinline__ void seg(int64_t r, int& b, int& e, const int*& list, int64_t& add) const {
         b = seg_off[r]; e = seg_off[r + 1]; list = src; add = 0;
+    }
+    __device__ __forceinline__ void ref(int64_t r, RowRef& o) const {
+        o.ok = r < n; o.pb = o.pe = 0; o.list = src; o.add = 0;
+        if (o.ok) { o.pb = seg_off[r]; o.pe = seg_off[r + 1]; }
     }
 };
 // Implicit: B decisions of one topology, decision b owns padded rows [b*RPD, (b+1)*RPD),
@@ -85,6 +96,7 @@ struct IdxTopo {
     const int* nK;        // [B]
     const int* in_off;    // [E+1]
     const int* in_first;  // [P]
+    __device__ __forceinline__ bool in_range(int64_t r) const { return r < total; }
     __device__ __forceinline__ bool valid(int64_t r) const {
         if (r >= total) return false;
         const int b = (int)(r / RPD);
@@ -97,6 +109,22 @@ struct IdxTopo {
         if (off_s > 0) {
             const int k = lr / off_s, x = lr - k * off_s;
             if (k < nK[b]) { bg = in_off[x]; en = in_off[x + 1]; add = (int64_t)b * RPD + (int64_t)k * off_f; }
+        }
+    }
+    // valid() + seg() in one go with 32-bit arithmetic (the host guarantees total < 2^31 for this path;
+    // the 64-bit divisions of the separate calls cost ~7 % of the kernel, profiles/r01_v3_*)
+    __device__ __forceinline__ void ref(int64_t r64, RowRef& o) const {
+        o.ok = false; o.pb = o.pe = 0; o.list = in_first; o.add = 0;
+        if (r64 >= total) return;
+        const unsigned r = (unsigned)r64;
+        const unsigned b = r / (unsigned)RPD;
+        const unsigned lr = r - b * (unsigned)RPD;
+        const int nk = nK[b];
+        if (lr >= (unsigned)(nk * E)) return;
+        o.ok = true;
+        if (off_s > 0) {
+            const unsigned k = lr / (unsigned)off_s, x = lr - k * (unsigned)off_s;
+            if ((int)k < nk) { o.pb = in_off[x]; o.pe = in_off[x + 1]; o.add = (int64_t)(b * (unsigned)RPD + k * (unsigned)off_f); }
         }
     }
 };
@@ -112,6 +140,14 @@ __device__ __forceinline__ u64 fma2s(float x, u64 w, u64 c) {
     return d;
 }
 
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ void prefetch_row_l1(const float* p) {
+    asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
+    asm volatile("prefetch.global.L1 [%0];" :: "l"(p + H - 1));
+}
+
 // fast transcendental forms (MUFU.EX2 / MUFU.RCP); relative error ~1e-6, see DESIGN.md
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -121,6 +157,17 @@ __device__ __forceinline__ float selu_fast(float x) {
     const float scale_alpha = 1.7580993408473768599402175208123f;
     const float e = ex2_approx(x * LOG2E);
     return x < 0.f ? fmaf(scale_alpha, e, -scale_alpha) : scale * x;
+}
+// selu_fast on two lanes: the packed add/mul/fma round each lane exactly like the scalar forms
+__device__ __forceinline__ u64 selu_fast2(u64 x) {
+    const float scale = 1.0507009873554804934193349852946f;
+    const float scale_alpha = 1.7580993408473768599402175208123f;
+    float xl, xh, ml, mh, nl, nh, pl, ph;
+    unpack2(x, xl, xh);
+    unpack2(mul2(x, pack2(LOG2E, LOG2E)), ml, mh);
+    unpack2(fma2(pack2(ex2_approx(ml), ex2_approx(mh)), pack2(scale_alpha, scale_alpha), pack2(-scale_alpha, -scale_alpha)), nl, nh);
+    unpack2(mul2(x, pack2(scale, scale)), pl, ph);
+    return pack2(xl < 0.f ? nl : pl, xh < 0.f ? nh : ph);
 }
 __device__ __forceinline__ float sigmoid_fast(float x) { return rcp_approx(1.f + ex2_approx(-LOG2E * x)); }
 __device__ __forceinline__ float tanh_fast(float x) { return fmaf(-2.f, rcp_approx(1.f + ex2_approx((2.f * LOG2E) * x)), 1.f); }
@@ -139,6 +186,154 @@ constexpr int MP_ROWS = MP_TPB * MP_R;                       // rows per tile
 constexpr int MP_SMEM_FLOATS = W_MP_FLOATS + 2 * MP_ROWS * H;  // weights + h slots + B/z slots
 constexpr size_t MP_SMEM_BYTES = sizeof(float) * MP_SMEM_FLOATS;
 
+// ---- the FMA phases of one message-passing iteration, shared by k_mp_iter and k_mp_tile ---------------
+// B = bm + h . Wm[20:40]  ->  myb slots
+template <int KH>
+__device__ __forceinline__ void mp_phase_B(const float* __restrict__ sw, const float (&h)[MP_R][H], float* const (&myb)[MP_R]) {
+#pragma unroll 1
+    for (int jb = 0; jb < H / 4; ++jb) {
+        const ulonglong2 b0 = *reinterpret_cast<const ulonglong2*>(sw + W_MSG_B + 4 * jb);
+        u64 acc[MP_R][2];
+#pragma unroll
+        for (int r = 0; r < MP_R; ++r) { acc[r][0] = b0.x; acc[r][1] = b0.y; }
+#pragma unroll
+        for (int k = 0; k < KH; ++k) {
+            const ulonglong2 w = *reinterpret_cast<const ulonglong2*>(sw + W_MSG_K + H * H + k * H + 4 * jb);
+#pragma unroll
+            for (int r = 0; r < MP_R; ++r) { acc[r][0] = fma2s(h[r][k], w.x, acc[r][0]); acc[r][1] = fma2s(h[r][k], w.y, acc[r][1]); }
+        }
+#pragma unroll
+        for (int r = 0; r < MP_R; ++r) *reinterpret_cast<ulonglong2*>(myb[r] + 4 * jb) = make_ulonglong2(acc[r][0], acc[r][1]);
+    }
+}
+
+// agg += selu(a + B) for one gathered operand row (packed f32x2 lanes, rounding identical to the scalar form)
+__device__ __forceinline__ void mp_accumulate(u64 (&agg2)[H / 2], const float (&a)[H], const float* __restrict__ myb) {
+#pragma unroll
+    for (int jb = 0; jb < H / 4; ++jb) {
+        const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(myb + 4 * jb);
+        agg2[2 * jb] = add2(agg2[2 * jb], selu_fast2(add2(pack2(a[4 * jb], a[4 * jb + 1]), t.x)));
+        agg2[2 * jb + 1] = add2(agg2[2 * jb + 1], selu_fast2(add2(pack2(a[4 * jb + 2], a[4 * jb + 3]), t.y)));
+    }
+}
+
+// z = sigmoid(agg.Kz + b0z + h.Rz + b1z)   (GRUCell, reset_after=True)  ->  myb slots
+template <int KH>
+__device__ __forceinline__ void mp_phase_z(const float* __restrict__ sw, const float (&h)[MP_R][H], const float (&agg)[MP_R][H],
+                                           float* const (&myb)[MP_R]) {
+#pragma unroll 1
+    for (int jb = 0; jb < H / 4; ++jb) {
+        const ulonglong2 b0 = *reinterpret_cast<const ulonglong2*>(sw + W_GRU_B + 4 * jb);
+        u64 acc[MP_R][2];
+#pragma unroll
+        for (int r = 0; r < MP_R; ++r) { acc[r][0] = b0.x; acc[r][1] = b0.y; }
+#pragma unroll
+        for (int k = 0; k < H; ++k) {
+            const ulonglong2 wk = *reinterpret_cast<const ulonglong2*>(sw + W_GRU_K + k * 60 + 4 * jb);
+#pragma unroll
+            for (int r = 0; r < MP_R; ++r) { acc[r][0] = fma2s(agg[r][k], wk.x, acc[r][0]); acc[r][1] = fma2s(agg[r][k], wk.y, acc[r][1]); }
+            if (k < KH) {
+                const ulonglong2 wr = *reinterpret_cast<const ulonglong2*>(sw + W_GRU_R + k * 60 + 4 * jb);
+#pragma unroll
+                for (int r = 0; r < MP_R; ++r) { acc[r][0] = fma2s(h[r][k], wr.x, acc[r][0]); acc[r][1] = fma2s(h[r][k], wr.y, acc[r][1]); }
+            }
+        }
+        const float4 b1 = *reinterpret_cast<const float4*>(sw + W_GRU_B + 60 + 4 * jb);
+#pragma unroll
+        for (int r = 0; r < MP_R; ++r) {
+            float v0, v1, v2, v3;
+            unpack2(acc[r][0], v0, v1); unpack2(acc[r][1], v2, v3);
+            *reinterpret_cast<float4*>(myb[r] + 4 * jb) =
+                make_float4(sigmoid_fast(v0 + b1.x), sigmoid_fast(v1 + b1.y), sigmoid_fast(v2 + b1.z), sigmoid_fast(v3 + b1.w));
+        }
+    }
+}
+
+// r, candidate state and the new h, four outputs at a time: new h -> myh slots (and hout[r] + 4*jb if non-null)
+template <int KH>
+__device__ __forceinline__ void mp_phase_rh(const float* __restrict__ sw, const float (&h)[MP_R][H], const float (&agg)[MP_R][H],
+                                            float* const (&myh)[MP_R], float* const (&myb)[MP_R], float* const (&hout)[MP_R]) {
+#pragma unroll 1
+    for (int jb = 0; jb < H / 4; ++jb) {
+        const ulonglong2 br = *reinterpret_cast<const ulonglong2*>(sw + W_GRU_B + 20 + 4 * jb);
+        const ulonglong2 bx = *reinterpret_cast<const ulonglong2*>(sw + W_GRU_B + 40 + 4 * jb);
+        const ulonglong2 by = *reinterpret_cast<const ulonglong2*>(sw + W_GRU_B + 100 + 4 * jb);
+        u64 ar[MP_R][2], ax[MP_R][2], ay[MP_R][2];
+#pragma unroll
+        for (int r = 0; r < MP_R; ++r) { ar[r][0] = br.x; ar[r][1] = br.y; ax[r][0] = bx.x; ax[r][1] = bx.y; ay[r][0] = by.x; ay[r][1] = by.y; }
+#pragma unroll
+        for (int k = 0; k < H; ++k) {
+            const ulonglong2 kr = *reinterpret_cast<const ulonglong2*>(sw + W_GRU_K + k * 60 + 20 + 4 * jb);
+            const ulonglong2 kh = *reinterpret_cast<const ulonglong2*>(sw + W_GRU_K + k * 60 + 40 + 4 * jb);
+#pragma unroll
+            for (int r = 0; r < MP_R; ++r) {
+                ar[r][0] = fma2s(agg[r][k], kr.x, ar[r][0]); ar[r][1] = fma2s(agg[r][k], kr.y, ar[r][1]);
+                ax[r][0] = fma2s(agg[r][k], kh.x, ax[r][0]); ax[r][1] = fma2s(agg[r][k], kh.y, ax[r][1]);
+            }
+            if (k < KH) {
+                const ulonglong2 rr = *reinterpret_cast<const ulonglong2*>(sw + W_GRU_R + k * 60 + 20 + 4 * jb);
+                const ulonglong2 rh = *reinterpret_cast<const ulonglong2*>(sw + W_GRU_R + k * 60 + 40 + 4 * jb);
+#pragma unroll
+                for (int r = 0; r < MP_R; ++r) {
+                    ar[r][0] = fma2s(h[r][k], rr.x, ar[r][0]); ar[r][1] = fma2s(h[r][k], rr.y, ar[r][1]);
+                    ay[r][0] = fma2s(h[r][k], rh.x, ay[r][0]); ay[r][1] = fma2s(h[r][k], rh.y, ay[r][1]);
+                }
+            }
+        }
+        const float4 b1r = *reinterpret_cast<const float4*>(sw + W_GRU_B + 80 + 4 * jb);
+#pragma unroll
+        for (int r = 0; r < MP_R; ++r) {
+            float rv[4], xv[4], yv[4];
+            unpack2(ar[r][0], rv[0], rv[1]); unpack2(ar[r][1], rv[2], rv[3]);
+            unpack2(ax[r][0], xv[0], xv[1]); unpack2(ax[r][1], xv[2], xv[3]);
+            unpack2(ay[r][0], yv[0], yv[1]); unpack2(ay[r][1], yv[2], yv[3]);
+            const float4 z = *reinterpret_cast<const float4*>(myb[r] + 4 * jb);
+            const float4 ho = *reinterpret_cast<const float4*>(myh[r] + 4 * jb);
+            const float b1[4] = {b1r.x, b1r.y, b1r.z, b1r.w};
+            const float zz[4] = {z.x, z.y, z.z, z.w};
+            const float hh0[4] = {ho.x, ho.y, ho.z, ho.w};
+            float hn[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float rg = sigmoid_fast(rv[i] + b1[i]);
+                const float cand = tanh_fast(xv[i] + rg * yv[i]);
+                hn[i] = zz[i] * hh0[i] + (1.f - zz[i]) * cand;
+            }
+            const float4 o = make_float4(hn[0], hn[1], hn[2], hn[3]);
+            *reinterpret_cast<float4*>(myh[r] + 4 * jb) = o;
+            if (hout[r]) *reinterpret_cast<float4*>(hout[r] + 4 * jb) = o;
+        }
+    }
+}
+
+// next iteration's message operand A' = h' . Wm[0:20]  ->  aout[r] + 4*jb (skipped if null)
+__device__ __forceinline__ void mp_phase_A(const float* __restrict__ sw, float* const (&myh)[MP_R], float* const (&aout)[MP_R]) {
+    float h[MP_R][H];
+#pragma unroll
+    for (int r = 0; r < MP_R; ++r) load_row(h[r], myh[r]);
+#pragma unroll 1
+    for (int jb = 0; jb < H / 4; ++jb) {
+        u64 acc[MP_R][2];
+#pragma unroll
+        for (int r = 0; r < MP_R; ++r) { acc[r][0] = 0ull; acc[r][1] = 0ull; }
+#pragma unroll
+        for (int k = 0; k < H; ++k) {
+            const ulonglong2 w = *reinterpret_cast<const ulonglong2*>(sw + W_MSG_K + k * H + 4 * jb);
+#pragma unroll
+            for (int r = 0; r < MP_R; ++r) { acc[r][0] = fma2s(h[r][k], w.x, acc[r][0]); acc[r][1] = fma2s(h[r][k], w.y, acc[r][1]); }
+        }
+#pragma unroll
+        for (int r = 0; r < MP_R; ++r)
+            if (aout[r]) *reinterpret_cast<ulonglong2*>(aout[r] + 4 * jb) = make_ulonglong2(acc[r][0], acc[r][1]);
+    }
+}
+
+template <class IDX, bool LAST, int KH>
+__device__ __forceinline__ void mp_tile_body(const IDX& idx, const float* __restrict__ sw, float* const (&myh)[MP_R],
+                                             float* const (&myb)[MP_R], const float* __restrict__ h_in,
+                                             const float* __restrict__ A_in, float* __restrict__ h_out,
+                                             float* __restrict__ A_out, int64_t tile);
+
 // KH = number of leading link-state columns that can be non-zero on entry: 20 in general, 3 for the
 // first iteration of the fused decision path, whose input rows are [util, cap, mark, 0 x 17]
 // (every h-side mat-vec then needs 3 instead of 20 k-steps; adding exact zeros changes no bit).
@@ -146,7 +341,7 @@ template <class IDX, bool LAST, int KH>
 __global__ void __launch_bounds__(MP_TPB, 3)
 k_mp_iter(const IDX idx, const float* __restrict__ wflat, const float* __restrict__ h_in,
           const float* __restrict__ A_in, float* __restrict__ h_out, float* __restrict__ A_out,
-          int64_t ntiles) {
+          int64_t ntiles, int* __restrict__ tile_counter) {
     extern __shared__ __align__(16) float mp_smem[];
     float* sw = mp_smem;
     float* sh = mp_smem + W_MP_FLOATS;                // [MP_R][128][20]  h (old, then new)
@@ -158,12 +353,37 @@ k_mp_iter(const IDX idx, const float* __restrict__ wflat, const float* __restric
 #pragma unroll
     for (int r = 0; r < MP_R; ++r) { myh[r] = sh + (r * MP_TPB + threadIdx.x) * H; myb[r] = sb + (r * MP_TPB + threadIdx.x) * H; }
 
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        int64_t row[MP_R]; bool ok[MP_R];
+    // Tiles are handed out through a global counter: a static stride leaves the CTAs with unequal numbers
+    // of live tiles (the padded rows past nK*E of every decision are empty), which cost ~13 % in idle
+    // tails (sm__warps_active 16.3 % of a possible 18.75 % in profiles/r01_v4_*).
+    __shared__ int s_next[2];
+    int64_t tile = blockIdx.x;
+    for (int turn = 0; tile < ntiles; ++turn) {
+        if (threadIdx.x == 0) s_next[turn & 1] = (int)gridDim.x + atomicAdd(tile_counter, 1);
+        const int64_t this_tile = tile;
+        __syncthreads();
+        tile = s_next[turn & 1];
+        mp_tile_body<IDX, LAST, KH>(idx, sw, myh, myb, h_in, A_in, h_out, A_out, this_tile);
+    }
+}
+
+template <class IDX, bool LAST, int KH>
+__device__ __forceinline__ void mp_tile_body(const IDX& idx, const float* __restrict__ sw, float* const (&myh)[MP_R],
+                                             float* const (&myb)[MP_R], const float* __restrict__ h_in,
+                                             const float* __restrict__ A_in, float* __restrict__ h_out,
+                                             float* __restrict__ A_out, int64_t tile) {
+    {
+        int64_t row[MP_R]; bool ok[MP_R]; RowRef ref[MP_R];
 #pragma unroll
-        for (int r = 0; r < MP_R; ++r) { row[r] = tile * MP_ROWS + r * MP_TPB + threadIdx.x; ok[r] = idx.valid(row[r]); }
-        if (!(ok[0] || ok[1])) continue;
-        float h[MP_R][H], agg[MP_R][H];
+        for (int r = 0; r < MP_R; ++r) { row[r] = tile * MP_ROWS + r * MP_TPB + threadIdx.x; idx.ref(row[r], ref[r]); ok[r] = ref[r].ok; }
+        if (!(ok[0] || ok[1])) return;
+        // pull exactly the message operands this thread will gather into L1 while the B mat-vec runs
+        // (prefetch.global.L1 takes no register and never blocks; rows shared by several threads coalesce)
+#pragma unroll
+        for (int r = 0; r < MP_R; ++r)
+            for (int p = ref[r].pb; p < ref[r].pe; ++p) prefetch_row_l1(A_in + ((int64_t)ref[r].list[p] + ref[r].add) * H);
+        float h[MP_R][H];
+        u64 agg2[MP_R][H / 2];
 #pragma unroll
         for (int r = 0; r < MP_R; ++r) {
             if (ok[r]) load_row(h[r], h_in + row[r] * H);
@@ -173,138 +393,49 @@ k_mp_iter(const IDX idx, const float* __restrict__ wflat, const float* __restric
             }
             store_row(myh[r], h[r]);
 #pragma unroll
-            for (int j = 0; j < H; ++j) agg[r][j] = 0.f;
+            for (int j = 0; j < H / 2; ++j) agg2[r][j] = 0ull;
         }
         // ---- B = bm + h . Wm[20:40]
-#pragma unroll 1
-        for (int jb = 0; jb < H / 4; ++jb) {
-            const ulonglong2 b0 = *reinterpret_cast<const ulonglong2*>(sw + W_MSG_B + 4 * jb);
-            u64 acc[MP_R][2];
-#pragma unroll
-            for (int r = 0; r < MP_R; ++r) { acc[r][0] = b0.x; acc[r][1] = b0.y; }
-#pragma unroll
-            for (int k = 0; k < KH; ++k) {
-                const ulonglong2 w = *reinterpret_cast<const ulonglong2*>(sw + W_MSG_K + H * H + k * H + 4 * jb);
-#pragma unroll
-                for (int r = 0; r < MP_R; ++r) { acc[r][0] = fma2s(h[r][k], w.x, acc[r][0]); acc[r][1] = fma2s(h[r][k], w.y, acc[r][1]); }
-            }
-#pragma unroll
-            for (int r = 0; r < MP_R; ++r) *reinterpret_cast<ulonglong2*>(myb[r] + 4 * jb) = make_ulonglong2(acc[r][0], acc[r][1]);
-        }
+        mp_phase_B<KH>(sw, h, myb);
         // ---- agg = sum over incoming pairs (ascending pair index) of selu(A[first] + B)
-#pragma unroll
-        for (int r = 0; r < MP_R; ++r) {
-            if (!ok[r]) continue;
-            float t[H];
-            load_row(t, myb[r]);
-            int pb, pe; const int* list; int64_t add;
-            idx.seg(row[r], pb, pe, list, add);
-            for (int p = pb; p < pe; ++p) {
-                float a[H];
-                load_row(a, A_in + ((int64_t)list[p] + add) * H);
-#pragma unroll
-                for (int j = 0; j < H; ++j) agg[r][j] += selu_fast(a[j] + t[j]);
-            }
-        }
-        // ---- z = sigmoid(agg.Kz + b0z + h.Rz + b1z)   (GRUCell, reset_after=True)
-#pragma unroll 1
-        for (int jb = 0; jb < H / 4; ++jb) {
-            const ulonglong2 b0 = *reinterpret_cast<const ulonglong2*>(sw + W_GRU_B + 4 * jb);
-            u64 acc[MP_R][2];
-#pragma unroll
-            for (int r = 0; r < MP_R; ++r) { acc[r][0] = b0.x; acc[r][1] = b0.y; }
-#pragma unroll
-            for (int k = 0; k < H; ++k) {
-                const ulonglong2 wk = *reinterpret_cast<const ulonglong2*>(sw + W_GRU_K + k * 60 + 4 * jb);
-#pragma unroll
-                for (int r = 0; r < MP_R; ++r) { acc[r][0] = fma2s(agg[r][k], wk.x, acc[r][0]); acc[r][1] = fma2s(agg[r][k], wk.y, acc[r][1]); }
-                if (k < KH) {
-                    const ulonglong2 wr = *reinterpret_cast<const ulonglong2*>(sw + W_GRU_R + k * 60 + 4 * jb);
-#pragma unroll
-                    for (int r = 0; r < MP_R; ++r) { acc[r][0] = fma2s(h[r][k], wr.x, acc[r][0]); acc[r][1] = fma2s(h[r][k], wr.y, acc[r][1]); }
-                }
-            }
-            const float4 b1 = *reinterpret_cast<const float4*>(sw + W_GRU_B + 60 + 4 * jb);
-#pragma unroll
-            for (int r = 0; r < MP_R; ++r) {
-                float v0, v1, v2, v3;
-                unpack2(acc[r][0], v0, v1); unpack2(acc[r][1], v2, v3);
-                *reinterpret_cast<float4*>(myb[r] + 4 * jb) =
-                    make_float4(sigmoid_fast(v0 + b1.x), sigmoid_fast(v1 + b1.y), sigmoid_fast(v2 + b1.z), sigmoid_fast(v3 + b1.w));
-            }
-        }
-        // ---- r, candidate state and the new h, four outputs at a time
-#pragma unroll 1
-        for (int jb = 0; jb < H / 4; ++jb) {
-            const ulonglong2 br = *reinterpret_cast<const ulonglong2*>(sw + W_GRU_B + 20 + 4 * jb);
-            const ulonglong2 bx = *reinterpret_cast<const ulonglong2*>(sw + W_GRU_B + 40 + 4 * jb);
-            const ulonglong2 by = *reinterpret_cast<const ulonglong2*>(sw + W_GRU_B + 100 + 4 * jb);
-            u64 ar[MP_R][2], ax[MP_R][2], ay[MP_R][2];
-#pragma unroll
-            for (int r = 0; r < MP_R; ++r) { ar[r][0] = br.x; ar[r][1] = br.y; ax[r][0] = bx.x; ax[r][1] = bx.y; ay[r][0] = by.x; ay[r][1] = by.y; }
-#pragma unroll
-            for (int k = 0; k < H; ++k) {
-                const ulonglong2 kr = *reinterpret_cast<const ulonglong2*>(sw + W_GRU_K + k * 60 + 20 + 4 * jb);
-                const ulonglong2 kh = *reinterpret_cast<const ulonglong2*>(sw + W_GRU_K + k * 60 + 40 + 4 * jb);
+        // The two rows of the thread walk their pair lists in lock step so that two independent gathers
+        // are in flight per step (each row still adds its pairs in ascending order); the SELU arithmetic
+        // runs on packed f32x2 lanes (half the issue slots of the scalar form).
+        {
+            const int steps = max(ref[0].pe - ref[0].pb, ref[1].pe - ref[1].pb);
+            for (int s = 0; s < steps; ++s) {
+                float a[MP_R][H];
+                bool on[MP_R];
 #pragma unroll
                 for (int r = 0; r < MP_R; ++r) {
-                    ar[r][0] = fma2s(agg[r][k], kr.x, ar[r][0]); ar[r][1] = fma2s(agg[r][k], kr.y, ar[r][1]);
-                    ax[r][0] = fma2s(agg[r][k], kh.x, ax[r][0]); ax[r][1] = fma2s(agg[r][k], kh.y, ax[r][1]);
+                    on[r] = ref[r].pb + s < ref[r].pe;
+                    if (on[r]) load_row(a[r], A_in + ((int64_t)ref[r].list[ref[r].pb + s] + ref[r].add) * H);
                 }
-                if (k < KH) {
-                    const ulonglong2 rr = *reinterpret_cast<const ulonglong2*>(sw + W_GRU_R + k * 60 + 20 + 4 * jb);
-                    const ulonglong2 rh = *reinterpret_cast<const ulonglong2*>(sw + W_GRU_R + k * 60 + 40 + 4 * jb);
 #pragma unroll
-                    for (int r = 0; r < MP_R; ++r) {
-                        ar[r][0] = fma2s(h[r][k], rr.x, ar[r][0]); ar[r][1] = fma2s(h[r][k], rr.y, ar[r][1]);
-                        ay[r][0] = fma2s(h[r][k], rh.x, ay[r][0]); ay[r][1] = fma2s(h[r][k], rh.y, ay[r][1]);
-                    }
+                for (int r = 0; r < MP_R; ++r) {
+                    if (!on[r]) continue;
+                    mp_accumulate(agg2[r], a[r], myb[r]);
                 }
-            }
-            const float4 b1r = *reinterpret_cast<const float4*>(sw + W_GRU_B + 80 + 4 * jb);
-#pragma unroll
-            for (int r = 0; r < MP_R; ++r) {
-                float rv[4], xv[4], yv[4];
-                unpack2(ar[r][0], rv[0], rv[1]); unpack2(ar[r][1], rv[2], rv[3]);
-                unpack2(ax[r][0], xv[0], xv[1]); unpack2(ax[r][1], xv[2], xv[3]);
-                unpack2(ay[r][0], yv[0], yv[1]); unpack2(ay[r][1], yv[2], yv[3]);
-                const float4 z = *reinterpret_cast<const float4*>(myb[r] + 4 * jb);
-                const float4 ho = *reinterpret_cast<const float4*>(myh[r] + 4 * jb);
-                const float b1[4] = {b1r.x, b1r.y, b1r.z, b1r.w};
-                const float zz[4] = {z.x, z.y, z.z, z.w};
-                const float hh0[4] = {ho.x, ho.y, ho.z, ho.w};
-                float hn[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float rg = sigmoid_fast(rv[i] + b1[i]);
-                    const float cand = tanh_fast(xv[i] + rg * yv[i]);
-                    hn[i] = zz[i] * hh0[i] + (1.f - zz[i]) * cand;
-                }
-                const float4 o = make_float4(hn[0], hn[1], hn[2], hn[3]);
-                *reinterpret_cast<float4*>(myh[r] + 4 * jb) = o;
-                if (ok[r]) *reinterpret_cast<float4*>(h_out + row[r] * H + 4 * jb) = o;
             }
         }
+        // h was held in registers for the B mat-vec only; reload it for the GRU so the gather loop above
+        // does not have to keep 40 more registers alive
+        float agg[MP_R][H];
+#pragma unroll
+        for (int r = 0; r < MP_R; ++r) {
+            load_row(h[r], myh[r]);
+#pragma unroll
+            for (int j = 0; j < H / 2; ++j) unpack2(agg2[r][j], agg[r][2 * j], agg[r][2 * j + 1]);
+        }
+        // ---- z = sigmoid(agg.Kz + b0z + h.Rz + b1z)   (GRUCell, reset_after=True)
+        mp_phase_z<KH>(sw, h, agg, myb);
+        // ---- r, candidate state and the new h, four outputs at a time
+        float* hout[MP_R]; float* aout[MP_R];
+#pragma unroll
+        for (int r = 0; r < MP_R; ++r) { hout[r] = ok[r] ? h_out + row[r] * H : nullptr; aout[r] = (ok[r] && !LAST) ? A_out + row[r] * H : nullptr; }
+        mp_phase_rh<KH>(sw, h, agg, myh, myb, hout);
         // ---- next iteration's message operand A' = h' . Wm[0:20]
-        if (!LAST) {
-#pragma unroll
-            for (int r = 0; r < MP_R; ++r) load_row(h[r], myh[r]);
-#pragma unroll 1
-            for (int jb = 0; jb < H / 4; ++jb) {
-                u64 acc[MP_R][2];
-#pragma unroll
-                for (int r = 0; r < MP_R; ++r) { acc[r][0] = 0ull; acc[r][1] = 0ull; }
-#pragma unroll
-                for (int k = 0; k < H; ++k) {
-                    const ulonglong2 w = *reinterpret_cast<const ulonglong2*>(sw + W_MSG_K + k * H + 4 * jb);
-#pragma unroll
-                    for (int r = 0; r < MP_R; ++r) { acc[r][0] = fma2s(h[r][k], w.x, acc[r][0]); acc[r][1] = fma2s(h[r][k], w.y, acc[r][1]); }
-                }
-#pragma unroll
-                for (int r = 0; r < MP_R; ++r)
-                    if (ok[r]) *reinterpret_cast<ulonglong2*>(A_out + row[r] * H + 4 * jb) = make_ulonglong2(acc[r][0], acc[r][1]);
-            }
-        }
+        if (!LAST) mp_phase_A(sw, myh, aout);
     }
 }
 

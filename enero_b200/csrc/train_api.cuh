@@ -23,19 +23,11 @@ int ensure_ones(enero_ctx* c, int B) {
 
 // forward with saved activations: h_0/A_0 must already be in t_h[0]/t_A[0]
 int train_forward(enero_ctx* c, const IdxTopo& idx, int which, int T, int64_t rows) {
-    const int64_t ntiles = (rows + MP_ROWS - 1) / MP_ROWS;
+    if (rows >= (int64_t)1 << 31) return fail(ENERO_ERR_INVALID, "more than 2^31 link-state rows in one launch: split the minibatch");
     for (int it = 0; it < T; ++it) {
         const bool last = (it == T - 1);
-        const int occ = std::max(1, c->occ_iter[1][last ? 1 : 0]);
-        const int grid = (int)std::min<int64_t>(ntiles, (int64_t)c->num_sms * occ);
-        const float* hin = c->t_h[it].as<float>();
-        const float* Ain = c->t_A[it].as<float>();
-        float* hout = c->t_h[it + 1].as<float>();
-        float* Aout = last ? nullptr : c->t_A[it + 1].as<float>();
-        if (last) k_mp_iter<IdxTopo, true, 20><<<grid, MP_TPB, MP_SMEM_BYTES, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles);
-        else if (it == 0) k_mp_iter<IdxTopo, false, 3><<<grid, MP_TPB, MP_SMEM_BYTES, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles);
-        else k_mp_iter<IdxTopo, false, 20><<<grid, MP_TPB, MP_SMEM_BYTES, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles);
-        LAUNCH_CHECK(c);
+        TRY(launch_topo_iteration(c, idx, which, last, it == 0 && !last, c->t_h[it].as<float>(), c->t_A[it].as<float>(),
+                                  c->t_h[it + 1].as<float>(), last ? nullptr : c->t_A[it + 1].as<float>()));
     }
     return ENERO_OK;
 }
