@@ -289,7 +289,7 @@ def run_ours(args, rank, world, local_rank):
             t0 = time.perf_counter()
             eb2.reset(tms_e)                          # H2D of the traffic matrices, loads on device, demand lists
             eb2.run_greedy()                          # all decisions, device resident
-            best, ospf, routing = eb2.best()          # D2H of the results
+            best, ospf, routing, n_routing = eb2.best_arrays()   # D2H of the results
             ctx.sync()
             dt = time.perf_counter() - t0
             if rep:                                    # first repetition warms allocations
@@ -334,7 +334,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=1024, help="episodes per GPU")
-    ap.add_argument("--e2e-batch", type=int, default=256)
+    ap.add_argument("--e2e-batch", type=int, default=1024)
     ap.add_argument("--cpu-decisions", type=int, default=300)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])

@@ -103,14 +103,19 @@ class EpisodeBatch:
         _lib.check(self._lib.enero_batch_get_history(self._h, _lib.ptr(a), _lib.ptr(r), _lib.ptr(m)))
         return a, r, m
 
-    def best(self):
-        """-> (best max-uti[B], ospf[B], routing list per episode [(s,d,mid), ...])."""
+    def best_arrays(self):
+        """-> (best max-uti[B], ospf[B], routing int32[B,Dmax,3] = (s,d,mid) in insertion order, n[B])."""
         best = np.zeros(self.B)
         ospf = np.zeros(self.B)
         routing = np.zeros((self.B, self.Dmax, 3), dtype=np.int32)
         n = np.zeros(self.B, dtype=np.int32)
         _lib.check(self._lib.enero_batch_get_best(self._h, _lib.ptr(best), _lib.ptr(ospf), _lib.ptr(routing), _lib.ptr(n)))
-        return best, ospf, [[tuple(int(v) for v in routing[b, k]) for k in range(n[b])] for b in range(self.B)]
+        return best, ospf, routing, n
+
+    def best(self):
+        """-> (best max-uti[B], ospf[B], routing list per episode [(s,d,mid), ...])."""
+        best, ospf, routing, n = self.best_arrays()
+        return best, ospf, [[tuple(v) for v in routing[b, :n[b]].tolist()] for b in range(self.B)]
 
     # ---- Env15 + HILL_CLIMBING ----------------------------------------------------------------
     def local_search(self, routing=None, mode: int = 0, max_moves: int = 4096, want_moves: bool = True):
@@ -152,8 +157,8 @@ def run_enero(ctx: Context, topo: Topology, tms, percentage_demands: float = 0.1
     try:
         eb.reset(tms)
         eb.run_greedy()
-        best, ospf, routing = eb.best()
-        out = {"ospf": ospf, "drl": best, "routing": routing, "decisions": eb.state()["steps"]}
+        best, ospf, routing, n_routing = eb.best_arrays()
+        out = {"ospf": ospf, "drl": best, "routing": routing, "n_routing": n_routing, "decisions": eb.state()["steps"]}
         if local_search:
             ls = eb.local_search(None, mode=0, want_moves=False)
             out["enero"] = ls["final"]

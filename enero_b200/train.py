@@ -1,0 +1,264 @@
+"""Training loop of train_Enero_3top_script.py (:379-722) on the GPU engine: rollouts on three
+topologies with per-topology sample quotas, bootstrap value, GAE, ``ppo_update`` (8 epochs x
+minibatches of 55), greedy evaluation on 20 TMs x 3 topologies, the tagged log-line protocol
+(``a,`` ``c,`` ``;,`` ``+,`` ``<,`` ``>,`` ``ENTR,`` ``REW,`` ``lr,`` ``MAX REWD: x REWD_ID: n,``),
+``ckpt_ACT-n`` / ``ckpt_CRT-n`` checkpoints and the ``(max_reward, lr)`` pickle.
+
+Differences from the reference, all in how the work is laid out, none in what is computed:
+  * the 60 greedy evaluation episodes run as three device-resident batches of 20 instead of 60
+    sequential Python episodes;
+  * with a process group, every rank owns the rollouts of the topologies ``rank::world`` (per-topology
+    numpy RNG streams), the sample records are all-gathered (a few KB each), and each PPO minibatch is
+    split over the ranks with one gradient all-reduce per Adam step.
+"""
+from __future__ import annotations
+
+import os
+import pickle
+import random
+import tempfile
+import time
+
+import numpy as np
+
+from . import datasets as ds
+from . import gym_graph
+from .checkpoint import Checkpoint
+from .engine import EpisodeBatch
+from .ppo import ENTROPY_BETA, PPOActorCritic, get_advantages, hparams
+
+SEED = 9
+EVALUATION_EPISODES = 20
+DECAY_STEPS = 60
+DECAY_RATE = 0.96
+ENTROPY_STEP = 60
+QUOTA_MULTIPLIERS = (5, 4, 6)       # num_samples_top{1,2,3} = ceil(pct * N(N-1)) * {5,4,6}   (train script :39-41)
+
+
+def decayed_learning_rate(step, base=0.0002):
+    """train script :97-101"""
+    lr = base * (DECAY_RATE ** (step / DECAY_STEPS))
+    return 10e-5 if lr < 10e-5 else lr
+
+
+class TrainingRun:
+    def __init__(self, ctx, train_envs, eval_envs, quotas, percentage_demands=0.15, learning_rate=None,
+                 entropy_beta=ENTROPY_BETA, log_path=None, checkpoint_dir=None, counter=1, max_reward=-1000.0,
+                 process_group=None, eval_episodes=EVALUATION_EPISODES):
+        self.ctx = ctx
+        self.train_envs, self.eval_envs, self.quotas = list(train_envs), list(eval_envs), list(quotas)
+        self.pct = percentage_demands
+        self.entropy_beta = entropy_beta
+        self.lr = hparams['learning_rate'] if learning_rate is None else learning_rate
+        self.agent = PPOActorCritic(context=ctx, buff_size=sum(self.quotas), learning_rate=self.lr,
+                                    entropy_beta=entropy_beta, process_group=process_group)
+        self.pg = process_group
+        self.log = open(log_path, "a") if log_path else None
+        self.checkpoint_dir = checkpoint_dir
+        self.counter = counter
+        self.max_reward = max_reward
+        self.reward_id = 0
+        self.eval_episodes = eval_episodes
+        self.training_tm_ids = list(range(100))
+        self.checkpoint_actor = Checkpoint(model=self.agent.actor, optimizer=self.agent.optimizer)
+        self.checkpoint_critic = Checkpoint(model=self.agent.critic, optimizer=self.agent.optimizer)
+        random.seed(SEED)
+        np.random.seed(SEED)
+
+    # ---- construction helpers ------------------------------------------------------------------
+    @classmethod
+    def synthetic(cls, ctx, specs, n_train_tms=100, n_eval_tms=EVALUATION_EPISODES, folder=None, **kw):
+        """three synthetic Zoo-shaped datasets (TRAIN / EVALUATE splits like convert_dataset.py:50-70)"""
+        folder = folder or tempfile.mkdtemp(prefix="enero_train_")
+        train_envs, eval_envs, quotas = [], [], []
+        for i, (n, l, seed) in enumerate(specs):
+            name = "syn%d" % i
+            for split, count, first in (("TRAIN", n_train_tms, 2000), ("EVALUATE", n_eval_tms, 5000)):
+                ds.make_synthetic_dataset(os.path.join(folder, name, split), name, n, l, seed, count, first)
+            for split, lst in (("TRAIN", train_envs), ("EVALUATE", eval_envs)):
+                env = gym_graph.make('GraphEnv-v16', context=ctx)
+                env.seed(SEED)
+                env.generate_environment(os.path.join(folder, name, split), name, 100, 100, kw.get("percentage_demands", 0.15))
+                env.top_K_critical_demands = True
+                lst.append(env)
+            quotas.append(int(np.ceil(kw.get("percentage_demands", 0.15) * n * (n - 1))) * QUOTA_MULTIPLIERS[i % 3])
+        run = cls(ctx, train_envs, eval_envs, quotas, **kw)
+        run.training_tm_ids = list(range(n_train_tms))
+        return run
+
+    def restore(self, counter):
+        """train script :452-457"""
+        d = self.checkpoint_dir
+        self.checkpoint_actor.restore(os.path.join(d, "ckpt_ACT-%d" % counter))
+        self.checkpoint_critic.restore(os.path.join(d, "ckpt_CRT-%d" % counter))
+        self.agent.load_optimizer_state()
+
+    # ---- rollouts (train script :483-625) ---------------------------------------------------------
+    def _collect_topology(self, env, quota, rng_choice, sample_tm):
+        buf = {k: [] for k in ("tensors", "critic_features", "actions", "values", "masks", "rewards", "actions_probs")}
+        agent = self.agent
+        reached = False
+        tm_id = sample_tm()
+        while not reached:
+            demand, source, destination = env.reset(tm_id)
+            while 1:
+                action_dist, tensor = agent.pred_action_distrib_sp(env, source, destination)
+                features = agent.critic_get_graph_features(env)
+                q_value = agent.critic_value(features)
+                action = rng_choice(len(action_dist), action_dist)
+                onehot = np.zeros(len(action_dist), dtype=np.float32)
+                onehot[action] = 1.0
+                reward, done, _, new_demand, new_source, new_destination, _, _, _ = env.step(action, demand, source, destination)
+                buf["tensors"].append(tensor)
+                buf["critic_features"].append(features)
+                buf["actions"].append(onehot)
+                buf["values"].append(q_value)
+                buf["masks"].append(not done)
+                buf["rewards"].append(reward)
+                buf["actions_probs"].append(action_dist)
+                demand, source, destination = new_demand, new_source, new_destination
+                if len(buf["tensors"]) == quota:
+                    reached = True
+                    break
+                if done:
+                    break
+        return buf
+
+    def collect(self):
+        """-> the experience buffer of one PPO episode (lists, topology 1 then 2 then 3) + bootstrap value"""
+        world, rank = 1, 0
+        if self.pg is not None:
+            import torch.distributed as dist
+            world, rank = dist.get_world_size(self.pg), dist.get_rank(self.pg)
+        parts = [None] * len(self.train_envs)
+        for i, (env, quota) in enumerate(zip(self.train_envs, self.quotas)):
+            if world == 1:
+                # the reference's global RNGs: random.sample for the TM, np.random.choice for the action
+                choice = lambda n, p: int(np.random.choice(n, p=p))
+                parts[i] = self._collect_topology(env, quota, choice, lambda: random.sample(self.training_tm_ids, 1)[0])
+            elif i % world == rank:
+                rs = np.random.RandomState((SEED, self.counter, i))
+                choice = lambda n, p, rs=rs: int(rs.choice(n, p=p))
+                parts[i] = self._collect_topology(env, quota, choice, lambda rs=rs: int(rs.choice(self.training_tm_ids)))
+        if world > 1:
+            import torch.distributed as dist
+            mine = {i: _portable(p) for i, p in enumerate(parts) if p is not None}
+            gathered = [None] * world
+            dist.all_gather_object(gathered, mine, group=self.pg)
+            for g in gathered:
+                for i, p in g.items():
+                    parts[i] = _attach(p, self.train_envs[i].topology)
+        buf = {k: [] for k in parts[0]}
+        for p in parts:
+            for k in buf:
+                buf[k] += p[k]
+        # bootstrap value of the state the last environment was left in (train script :622-625)
+        last = self.train_envs[-1]
+        if world == 1 or (len(self.train_envs) - 1) % world == rank:
+            boot = float(self.agent.critic_value(self.agent.critic_get_graph_features(last)))
+        else:
+            boot = 0.0
+        if world > 1:
+            import torch.distributed as dist
+            lst = [boot]
+            dist.broadcast_object_list(lst, src=(len(self.train_envs) - 1) % world, group=self.pg)
+            boot = lst[0]
+        buf["values"] = buf["values"] + [np.float32(boot)]
+        return buf
+
+    # ---- greedy evaluation (train script :633-693), batched --------------------------------------------
+    def evaluate(self):
+        rewards, max_uti, uti_std = [], [], []
+        for env in self.eval_envs:
+            tms = np.stack([ds.parse_demands_file(os.path.join(env.dataset_folder_name, "TM", "%s.%d.demands"
+                                                               % (env.graph_topology_name, t)), env.numNodes)
+                            for t in range(self.eval_episodes)])
+            eb = EpisodeBatch(self.ctx, env.topology, tms.shape[0], self.pct)
+            try:
+                eb.reset(tms)
+                eb.run_greedy()
+                st = eb.state()
+                _, r, _ = eb.history()
+                for i in range(tms.shape[0]):
+                    rew = 0
+                    for v in r[i, :st["steps"][i]]:     # rewardAddTest += reward, in step order
+                        rew += v
+                    rewards.append(rew)
+                max_uti += list(st["max_uti"])
+                uti_std += [float(np.std(st["loads"][i])) for i in range(tms.shape[0])]
+            finally:
+                eb.close()
+        return np.array(rewards), np.array(max_uti), np.array(uti_std)
+
+    # ---- one PPO episode ---------------------------------------------------------------------------
+    def _log(self, line):
+        if self.log:
+            self.log.write(line)
+
+    def ppo_episode(self):
+        t0 = time.perf_counter()
+        buf = self.collect()
+        t1 = time.perf_counter()
+        returns, advantages = get_advantages(buf["values"], buf["masks"], buf["rewards"], context=self.ctx)
+        shuffle = np.random.shuffle
+        if self.pg is not None:                     # every rank must draw the same permutations
+            rs = np.random.RandomState((SEED, self.counter, 99))
+            shuffle = rs.shuffle
+        actor_loss, critic_loss = self.agent.ppo_update(buf["actions"], buf["actions_probs"], buf["tensors"],
+                                                        buf["critic_features"], returns, advantages, shuffle=shuffle)
+        self.ctx.sync()
+        t2 = time.perf_counter()
+        self._log("a,%s,\n" % actor_loss)
+        self._log("c,%s,\n" % critic_loss)
+        rewards_test, max_link_uti, uti_std = self.evaluate()
+        t3 = time.perf_counter()
+        eval_mean = float(np.mean(rewards_test))
+        self._log(";,%s,\n" % np.mean(uti_std))
+        self._log("+,%s,\n" % 0.0)
+        self._log("<,%s,\n" % np.amax(max_link_uti))
+        self._log(">,%s,\n" % 0.0)
+        self._log("ENTR,%s,\n" % self.entropy_beta)
+        self._log("REW,%s,\n" % eval_mean)
+        self._log("lr,%s,\n" % self.lr)
+        if eval_mean > self.max_reward:
+            self.max_reward = eval_mean
+            self.reward_id = self.counter
+            self._log("MAX REWD: %s REWD_ID: %s,\n" % (self.max_reward, self.reward_id))
+        if self.log:
+            self.log.flush()
+        if self.checkpoint_dir:
+            os.makedirs(self.checkpoint_dir, exist_ok=True)
+            self.agent.store_optimizer_state()
+            prefix = os.path.join(self.checkpoint_dir, "ckpt")
+            # a restored checkpoint carries save_counter = counter - 1, so save() writes ckpt_*-<counter>
+            self.checkpoint_actor.save_counter = self.counter - 1
+            self.checkpoint_critic.save_counter = self.counter - 1
+            self.checkpoint_actor.save(prefix + "_ACT")
+            self.checkpoint_critic.save(prefix + "_CRT")
+        self.counter += 1
+        n = len(buf["tensors"])
+        steps = 8 * ((n + 54) // 55)
+        return {"samples": n, "adam_steps": steps, "collect_s": t1 - t0, "update_s": t2 - t1, "eval_s": t3 - t2,
+                "actor_loss": actor_loss, "critic_loss": critic_loss, "eval_mean_reward": eval_mean,
+                "eval_max_uti": float(np.amax(max_link_uti)), "update_samples_per_s": 8 * n / (t2 - t1)}
+
+    def save_state(self, path):
+        """train script :720-722"""
+        with open(path, "wb") as f:
+            pickle.dump((self.max_reward, self.lr), f)
+
+
+def _portable(buf):
+    """sample records without the (non-picklable) topology handles"""
+    out = dict(buf)
+    out["tensors"] = [{k: v for k, v in t.items() if k != "topology"} for t in buf["tensors"]]
+    out["critic_features"] = [{k: v for k, v in t.items() if k != "topology"} for t in buf["critic_features"]]
+    return out
+
+
+def _attach(buf, topo):
+    for t in buf["tensors"]:
+        t["topology"] = topo
+    for t in buf["critic_features"]:
+        t["topology"] = topo
+    return buf
