@@ -158,6 +158,9 @@ def run_reference(args, rank, world):
     cores = os.cpu_count() or 1
     # bounded sample: each step = `per` decisions on each of `cores` processes (~0.03-0.05 s per decision)
     import multiprocessing as mp
+    # one single-threaded worker per core (the reference's Pool fan-out): keep BLAS from oversubscribing
+    for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[k] = "1"
     per = 6
     vals = []
     with mp.get_context("spawn").Pool(cores) as pool:

@@ -799,8 +799,7 @@ extern "C" int enero_batch_local_search(enero_batch* b, int mode, const int32_t*
     if (start) CUDA_TRY(cudaMemcpyAsync(start, b->ls_val.p, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
     LsView lv{B, cap, max_moves, b->tm.as<double>(), b->ls_loads.as<double>(), b->ls_mid.as<int>(), b->ls_elig.as<int>(),
               b->ls_elig_len.as<int>(), b->ls_val.as<double>(), b->ls_nmoves.as<int>(), b->ls_moves.as<int>(), b->ls_move_val.as<double>()};
-    const int nw = LS_TPB / 32;
-    const size_t smem = (size_t)E * 16 + nw * 8 + nw * 4 + nw * 8 + (size_t)nw * E + 16;
+    const size_t smem = ls_smem_bytes(E);
     if (smem > 200 * 1024) return fail(ENERO_ERR_INVALID, "enero_batch_local_search: topology too large for the shared-memory LS kernel");
     if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_local_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_local_search<<<B, LS_TPB, smem, st>>>(tv, lv); LAUNCH_CHECK(c);

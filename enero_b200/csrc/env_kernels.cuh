@@ -260,18 +260,28 @@ struct LsView {
     int* n_moves; int* moves; double* move_val;    // [B], [B][max_moves][3], [B][max_moves]
 };
 
-constexpr int LS_TPB = 256;
+constexpr int LS_TPB = 1024;
+constexpr int LS_TOP = 32;       // most utilised links kept per LS iteration (see the move evaluation below)
+
+// dynamic shared memory of k_local_search for a topology with E links
+__host__ __device__ inline size_t ls_smem_bytes(int E) {
+    const int nw = LS_TPB / 32;
+    return (size_t)(3 * E + nw + LS_TOP) * 8 + (size_t)(3 * nw + LS_TOP) * 4 + (size_t)nw * E + 16;
+}
 
 __global__ void __launch_bounds__(LS_TPB)
 k_local_search(TopoView t, LsView ls) {
     extern __shared__ double ls_smem[];
     double* sl = ls_smem;                                // [E] loads
     double* scap = sl + t.E;                             // [E]
-    double* wbest = scap + t.E;                          // [nwarps]
-    int* wbest_i = reinterpret_cast<int*>(wbest + LS_TPB / 32);   // [nwarps] move order key
+    double* su = scap + t.E;                             // [E] scratch: base utilisations during the top-M selection
+    double* wbest = su + t.E;                            // [nwarps]
+    double* top_u = wbest + LS_TPB / 32;                 // [LS_TOP] largest base utilisations, descending
+    int* wbest_i = reinterpret_cast<int*>(top_u + LS_TOP);   // [nwarps] move order key
     int* wbest_m = wbest_i + LS_TPB / 32;                // [nwarps][2] (demand idx, action)
-    signed char* cnt = reinterpret_cast<signed char*>(wbest_m + 2 * (LS_TPB / 32));   // [nwarps][E]
-    __shared__ double s_cur; __shared__ int s_stop; __shared__ int s_bd, s_ba;
+    int* top_e = wbest_m + 2 * (LS_TPB / 32);            // [LS_TOP] their link ids
+    signed char* cnt = reinterpret_cast<signed char*>(top_e + LS_TOP);   // [nwarps][E]
+    __shared__ double s_cur; __shared__ int s_stop; __shared__ int s_bd, s_ba, s_ntop;
 
     const int b = blockIdx.x, NN = t.N * t.N;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = LS_TPB / 32;
@@ -287,6 +297,30 @@ k_local_search(TopoView t, LsView ls) {
     __syncthreads();
 
     while (true) {
+        // ---- the LS_TOP most utilised links of the current loads.  A move changes the load of the links
+        // on the old and the new route only, so its value is max(first top link the move does not touch,
+        // utilisation of the touched links): O(path) instead of O(E) per move, and the same fp64 numbers
+        // as the reference's full rescan (get_value_sp, script :331-339) because max() is exact.
+        for (int e = threadIdx.x; e < t.E; e += LS_TPB) su[e] = sl[e] / scap[e];
+        __syncthreads();
+        if (wid == 0) {
+            const int ntop = min(LS_TOP, t.E);
+            for (int m = 0; m < ntop; ++m) {
+                double bu = -1.0; int be = 0x7fffffff;
+                for (int e = lane; e < t.E; e += 32) { const double u = su[e]; if (u > bu) { bu = u; be = e; } }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double ou = __shfl_xor_sync(0xffffffffu, bu, o);
+                    const int oe = __shfl_xor_sync(0xffffffffu, be, o);
+                    if (ou > bu || (ou == bu && oe < be)) { bu = ou; be = oe; }
+                }
+                if (lane == 0) { top_u[m] = bu; top_e[m] = be; su[be] = -2.0; }
+                __syncwarp();
+            }
+            if (lane == 0) s_ntop = ntop;
+        }
+        __syncthreads();
+        const int ntop = s_ntop;
         // ---- explore the neighbourhood
         double best = 1e300; int best_key = 0x7fffffff, best_d = -1, best_a = -1;
         for (int di = wid; di < nd; di += nw) {
@@ -295,9 +329,9 @@ k_local_search(TopoView t, LsView ls) {
             const double bw = tm[sdi];
             const int m0 = mid_cur[sdi];
             const int k0 = t.mid_off[sdi], k1 = t.mid_off[sdi + 1];
+            const int a0 = (m0 < 0 || m0 == d) ? d : m0;
             // visit counts of the current route, negated (de-allocation, :404-416)
             {
-                const int a0 = (m0 < 0 || m0 == d) ? d : m0;
                 for (int i = t.sp_off[s * t.N + a0] + lane; i < t.sp_off[s * t.N + a0 + 1]; i += 32) mycnt[t.sp_edge[i]] -= 1;
                 __syncwarp();
                 if (a0 != d) { for (int i = t.sp_off[a0 * t.N + d] + lane; i < t.sp_off[a0 * t.N + d + 1]; i += 32) mycnt[t.sp_edge[i]] -= 1; __syncwarp(); }
@@ -308,9 +342,32 @@ k_local_search(TopoView t, LsView ls) {
                 __syncwarp();
                 if (m1 != d) { for (int i = t.sp_off[m1 * t.N + d] + lane; i < t.sp_off[m1 * t.N + d + 1]; i += 32) mycnt[t.sp_edge[i]] += 1; __syncwarp(); }
                 double mx = -1000000.0;
-                for (int e = lane; e < t.E; e += 32) {
-                    const double u = (sl[e] + bw * (double)mycnt[e]) / scap[e];
-                    mx = fmax(mx, u);
+                // untouched links: the first entry of the top list whose visit count is zero
+                const bool untouched = lane < ntop && mycnt[top_e[lane < ntop ? lane : 0]] == 0;
+                const unsigned free_mask = __ballot_sync(0xffffffffu, untouched);
+                if (free_mask != 0u || ntop == t.E) {
+                    if (free_mask != 0u) mx = top_u[__ffs(free_mask) - 1];
+                    // touched links: old route (count < 0) and new route (count > 0)
+                    for (int i = t.sp_off[s * t.N + a0] + lane; i < t.sp_off[s * t.N + a0 + 1]; i += 32) {
+                        const int e = t.sp_edge[i]; mx = fmax(mx, (sl[e] + bw * (double)mycnt[e]) / scap[e]);
+                    }
+                    if (a0 != d)
+                        for (int i = t.sp_off[a0 * t.N + d] + lane; i < t.sp_off[a0 * t.N + d + 1]; i += 32) {
+                            const int e = t.sp_edge[i]; mx = fmax(mx, (sl[e] + bw * (double)mycnt[e]) / scap[e]);
+                        }
+                    for (int i = t.sp_off[s * t.N + m1] + lane; i < t.sp_off[s * t.N + m1 + 1]; i += 32) {
+                        const int e = t.sp_edge[i]; mx = fmax(mx, (sl[e] + bw * (double)mycnt[e]) / scap[e]);
+                    }
+                    if (m1 != d)
+                        for (int i = t.sp_off[m1 * t.N + d] + lane; i < t.sp_off[m1 * t.N + d + 1]; i += 32) {
+                            const int e = t.sp_edge[i]; mx = fmax(mx, (sl[e] + bw * (double)mycnt[e]) / scap[e]);
+                        }
+                } else {
+                    // every top link is touched by this move (very long routes): full rescan
+                    for (int e = lane; e < t.E; e += 32) {
+                        const double u = (sl[e] + bw * (double)mycnt[e]) / scap[e];
+                        mx = fmax(mx, u);
+                    }
                 }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -323,7 +380,6 @@ k_local_search(TopoView t, LsView ls) {
                 if (m1 != d) { for (int i = t.sp_off[m1 * t.N + d] + lane; i < t.sp_off[m1 * t.N + d + 1]; i += 32) mycnt[t.sp_edge[i]] -= 1; __syncwarp(); }
             }
             {
-                const int a0 = (m0 < 0 || m0 == d) ? d : m0;
                 for (int i = t.sp_off[s * t.N + a0] + lane; i < t.sp_off[s * t.N + a0 + 1]; i += 32) mycnt[t.sp_edge[i]] += 1;
                 __syncwarp();
                 if (a0 != d) { for (int i = t.sp_off[a0 * t.N + d] + lane; i < t.sp_off[a0 * t.N + d + 1]; i += 32) mycnt[t.sp_edge[i]] += 1; __syncwarp(); }

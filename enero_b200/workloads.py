@@ -70,7 +70,8 @@ def run_cfg5(ctx, n_topologies=8, n_tms=64, rank=0, world=1, first_seed=1000):
         specs.append((max(4, int(round(l / 1.65))), l, first_seed + i))
     costs = [ds.max_decisions(n) * min(99, n - 1) * (2 * l) * 4.0 for n, l, _ in specs]      # ~ D * K' * (P + E)
     mine = par.shard_by_cost(costs, world)[rank]
-    out = {"topologies": len(mine), "tms": 0, "decisions": 0, "ls_moves": 0, "seconds": 0.0, "build_seconds": 0.0, "links": []}
+    out = {"topologies": len(mine), "tms": 0, "decisions": 0, "ls_moves": 0, "seconds": 0.0, "build_seconds": 0.0, "links": [],
+           "drl_seconds": 0.0, "ls_seconds": 0.0}
     for i in mine:
         n, l, seed = specs[i]
         t0 = time.perf_counter()
@@ -85,6 +86,8 @@ def run_cfg5(ctx, n_topologies=8, n_tms=64, rank=0, world=1, first_seed=1000):
         out["tms"] += n_tms
         out["decisions"] += int(res["decisions"].sum())
         out["ls_moves"] += int(res["ls_moves"].sum())
+        out["drl_seconds"] += float(res["cost_drl"].sum())
+        out["ls_seconds"] += float(res["cost_ls"].sum())
         out["links"].append(topo.E)
         topo.close()
     return out
@@ -133,6 +136,8 @@ def _main():
                               "tms": sum(x["tms"] for x in recs), "seconds": secs,
                               "decisions_per_s": sum(x["decisions"] for x in recs) / secs,
                               "build_seconds": sum(x["build_seconds"] for x in recs),
+                              "drl_seconds": sum(x["drl_seconds"] for x in recs), "ls_seconds": sum(x["ls_seconds"] for x in recs),
+                              "ls_moves": sum(x["ls_moves"] for x in recs),
                               "links": sorted(l for x in recs for l in x["links"])}))
     else:
         import torch.distributed as dist
@@ -141,6 +146,10 @@ def _main():
         if rank == 0:
             print(json.dumps({"workload": "cfg4", "n_gpus": world, "episodes": stats}))
     ctx.close()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
