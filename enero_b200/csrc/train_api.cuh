@@ -44,7 +44,8 @@ int train_backward(enero_ctx* c, enero_topo* t, const TrainTopo& g, int which, i
     const int n_graphs = g.n * g.Kmax;
     TRY(c->t_V.ensure((size_t)n_graphs * 6 * H * 4));
     const int wg_grid = (int)std::min<int64_t>((rows + WG_ROWS - 1) / WG_ROWS, 2 * (int64_t)c->num_sms);
-    TRY(c->t_partials.ensure((size_t)wg_grid * W_MP_FLOATS * 4));
+    const int rw_grid = (n_graphs + RW_CHUNK - 1) / RW_CHUNK;
+    TRY(c->t_partials.ensure(std::max((size_t)wg_grid * WG_PART, (size_t)rw_grid * RW_NOUT) * 4));
     IdxTopo idx{rows, g.E, d.off_f, d.off_s, g.RPD, g.nK, d.in_off, d.in_first};
     OutTopo out{g.E, d.off_f, d.off_s, g.RPD, g.nK, d.out_off, d.out_second};
     GraphsTopo gr{g.n, g.Kmax, g.E, g.RPD, g.nK};
@@ -52,7 +53,8 @@ int train_backward(enero_ctx* c, enero_topo* t, const TrainTopo& g, int which, i
     const float* w = c->w[which];
     k_readout_bwd<<<(n_graphs + 3) / 4, 128, 0, st>>>(gr, w, c->t_h[T].as<float>(), dlogit, c->t_dh[0].as<float>(), c->t_V.as<float>());
     LAUNCH_CHECK(c);
-    k_readout_wgrad<<<1, 256, 0, st>>>(n_graphs, g.Kmax, g.nK, c->t_V.as<float>(), grad); LAUNCH_CHECK(c);
+    k_readout_wgrad<<<rw_grid, 256, 0, st>>>(n_graphs, g.Kmax, g.nK, c->t_V.as<float>(), c->t_partials.as<float>()); LAUNCH_CHECK(c);
+    k_reduce_rows<<<(RW_NOUT + 255) / 256, 256, 0, st>>>(rw_grid, RW_NOUT, c->t_partials.as<float>(), grad + W_R1_K); LAUNCH_CHECK(c);
     const int bgrid = (int)((rows + BW_TPB - 1) / BW_TPB);
     int cur = 0;
     for (int it = T - 1; it >= 0; --it) {
@@ -171,7 +173,8 @@ extern "C" int enero_ppo_accumulate(enero_ctx* c, enero_topo* t, int n, const do
         TrainTopo g{n, 1, E, E, rows, ones};
         TRY(train_backward(c, t, g, ENERO_CRITIC, T, c->t_dlogit.as<float>()));
     }
-    if (ptr_kind == ENERO_HOST) CUDA_TRY(cudaStreamSynchronize(st));    // the staging buffers may be reused by the caller
+    // no synchronisation: H2D copies from pageable host memory have left the caller's buffers when
+    // cudaMemcpyAsync returns, and the device staging buffers are reused in stream order
     return ENERO_OK;
 }
 

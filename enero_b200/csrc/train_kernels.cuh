@@ -322,14 +322,17 @@ k_readout_bwd(const GraphsTopo gr, const float* __restrict__ wflat, const float*
     }
 }
 
-// readout weight gradients: a single CTA walks the graphs in order (deterministic), thread o owns outputs
-// o, o+256, ... of the 861 readout parameters and adds the result into grad[W_R1_K + o].
+// readout weight gradients: CTA c walks graphs [c*RW_CHUNK, (c+1)*RW_CHUNK) in order, thread o owns outputs
+// o, o+256, ... of the 861 readout parameters; the per-CTA partial vectors are added in CTA order by
+// k_reduce_rows (deterministic).
+constexpr int RW_CHUNK = 32;
+constexpr int RW_NOUT = W_R3_B + 1 - W_R1_K;     // 861
 __global__ void __launch_bounds__(256)
-k_readout_wgrad(int n_graphs, int Kmax, const int* __restrict__ nK, const float* __restrict__ V, float* __restrict__ grad) {
-    constexpr int NOUT = W_R3_B + 1 - W_R1_K;     // 861
+k_readout_wgrad(int n_graphs, int Kmax, const int* __restrict__ nK, const float* __restrict__ V, float* __restrict__ partials) {
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     __shared__ float sv[6 * H];
-    for (int g = 0; g < n_graphs; ++g) {
+    const int g0 = blockIdx.x * RW_CHUNK, g1 = min(n_graphs, g0 + RW_CHUNK);
+    for (int g = g0; g < g1; ++g) {
         const int b = g / Kmax, k = g - b * Kmax;
         if (k >= nK[b]) continue;
         __syncthreads();
@@ -338,7 +341,7 @@ k_readout_wgrad(int n_graphs, int Kmax, const int* __restrict__ nK, const float*
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
             const int o = threadIdx.x + 256 * m;
-            if (o >= NOUT) break;
+            if (o >= RW_NOUT) break;
             float v;
             if (o < 400) v = sv[o / H] * sv[3 * H + o % H];                        // dR1[k][j] = g[k] * dp1[j]
             else if (o < 420) v = sv[3 * H + o - 400];                             // db1
@@ -352,15 +355,25 @@ k_readout_wgrad(int n_graphs, int Kmax, const int* __restrict__ nK, const float*
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
         const int o = threadIdx.x + 256 * m;
-        if (o < NOUT) grad[W_R1_K + o] += acc[m];
+        if (o < RW_NOUT) partials[(int64_t)blockIdx.x * RW_NOUT + o] = acc[m];
     }
+}
+// dst[o] += sum_p partials[p * count + o], p ascending
+__global__ void k_reduce_rows(int n_part, int count, const float* __restrict__ partials, float* __restrict__ dst) {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= count) return;
+    float s = 0.f;
+    for (int p = 0; p < n_part; ++p) s += partials[(int64_t)p * count + o];
+    dst[o] += s;
 }
 
 // ---- message / GRU weight gradients -----------------------------------------------------------------------------
 // For every row and iteration: X = [h(20) | agg(20) | 1], D = [dpz dpr dx dy (80) | dB (20) | dA (20)].
 // Output o of the 3340 message+GRU parameters is sum over rows of X[xc(o)] * D[dc(o)].
 struct WgradIter { const float* h; const float* agg; const float* G; const float* dB; const float* dA; };
-constexpr int WG_TPB = 256, WG_ROWS = 64, WG_XW = 41, WG_DW = 120, WG_PER = 14;   // ceil(3340 / 256)
+constexpr int WG_TPB = 256, WG_ROWS = 64;
+constexpr int WG_XP = 48, WG_DP = 128;             // X (41 columns) and D (120 columns) padded to 8x6 and 32x4 thread tiles
+constexpr int WG_PART = WG_XP * WG_DP;             // floats of one CTA's partial outer product
 
 __device__ __forceinline__ void wgrad_cols(int o, int& xc, int& dc) {
     if (o < 400) { xc = o / H; dc = 100 + o % H; }                         // dWm[0:20]   = h^T dA
@@ -372,58 +385,70 @@ __device__ __forceinline__ void wgrad_cols(int o, int& xc, int& dc) {
     else { const int j = o - 3280; xc = 40; dc = j < 40 ? j : j + 20; }    // db1 = sum [dpz dpr dy]
 }
 
+// Per CTA: the full outer product sum_rows X^T D (48 x 128, of which the 3340 parameter gradients are a
+// subset) over its row tiles, register-tiled 6 x 4 per thread: per row a thread reads 6 X values (warp-uniform
+// broadcast) and one float4 of D and issues 24 FMAs.  The previous version looked its 14 scattered
+// (x, d) pairs up in shared memory row by row (2 LDS per FMA) and took 36 % of the PPO step.
 __global__ void __launch_bounds__(WG_TPB)
 k_wgrad(const IdxTopo idx, const WgradIter it, int64_t ntiles, float* __restrict__ partials) {
-    __shared__ float sx[WG_ROWS * WG_XW];
-    __shared__ float sd[WG_ROWS * (WG_DW + 1)];
+    __shared__ __align__(16) float sx[WG_ROWS * WG_XP];
+    __shared__ __align__(16) float sd[WG_ROWS * WG_DP];
     __shared__ unsigned char s_ok[WG_ROWS];
-    int xc[WG_PER], dc[WG_PER];
-    float acc[WG_PER];
+    const int xg = threadIdx.x >> 5, dg = threadIdx.x & 31;
+    float acc[6][4];
 #pragma unroll
-    for (int m = 0; m < WG_PER; ++m) {
-        const int o = threadIdx.x + WG_TPB * m;
-        acc[m] = 0.f; xc[m] = 40; dc[m] = 0;
-        if (o < W_MP_FLOATS) wgrad_cols(o, xc[m], dc[m]);
-    }
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t r0 = tile * WG_ROWS;
         __syncthreads();
         if (threadIdx.x < WG_ROWS) s_ok[threadIdx.x] = idx.valid(r0 + threadIdx.x) ? 1 : 0;
         __syncthreads();
-        for (int i = threadIdx.x; i < WG_ROWS * 160; i += WG_TPB) {
-            const int row = i / 160, c = i - row * 160;
+        for (int i = threadIdx.x; i < WG_ROWS * (WG_XP + WG_DP); i += WG_TPB) {
+            const int row = i / (WG_XP + WG_DP), c = i - row * (WG_XP + WG_DP);
             const int64_t r = r0 + row;
             float v = 0.f;
             if (s_ok[row]) {
                 if (c < 20) v = it.h[r * H + c];
                 else if (c < 40) v = it.agg[r * H + c - 20];
-                else if (c < 120) v = it.G[r * 4 * H + c - 40];
-                else if (c < 140) v = it.dB[r * H + c - 120];
-                else v = it.dA[r * H + c - 140];
+                else if (c == 40) v = 1.f;
+                else if (c < WG_XP) v = 0.f;
+                else if (c < WG_XP + 80) v = it.G[r * 4 * H + c - WG_XP];
+                else if (c < WG_XP + 100) v = it.dB[r * H + c - WG_XP - 80];
+                else if (c < WG_XP + 120) v = it.dA[r * H + c - WG_XP - 100];
             }
-            if (c < 40) sx[row * WG_XW + c] = v; else sd[row * (WG_DW + 1) + c - 40] = v;
+            if (c < WG_XP) sx[row * WG_XP + c] = v; else sd[row * WG_DP + c - WG_XP] = v;
         }
-        if (threadIdx.x < WG_ROWS) sx[threadIdx.x * WG_XW + 40] = s_ok[threadIdx.x] ? 1.f : 0.f;
         __syncthreads();
+#pragma unroll 4
         for (int row = 0; row < WG_ROWS; ++row) {
-            const float* px = sx + row * WG_XW;
-            const float* pd = sd + row * (WG_DW + 1);
+            const float2* px = reinterpret_cast<const float2*>(sx + row * WG_XP + 6 * xg);
+            const float2 x01 = px[0], x23 = px[1], x45 = px[2];
+            const float4 d = *reinterpret_cast<const float4*>(sd + row * WG_DP + 4 * dg);
+            const float x[6] = {x01.x, x01.y, x23.x, x23.y, x45.x, x45.y};
 #pragma unroll
-            for (int m = 0; m < WG_PER; ++m) acc[m] = fmaf(px[xc[m]], pd[dc[m]], acc[m]);
+            for (int i = 0; i < 6; ++i) {
+                acc[i][0] = fmaf(x[i], d.x, acc[i][0]); acc[i][1] = fmaf(x[i], d.y, acc[i][1]);
+                acc[i][2] = fmaf(x[i], d.z, acc[i][2]); acc[i][3] = fmaf(x[i], d.w, acc[i][3]);
+            }
         }
     }
+    float* out = partials + (int64_t)blockIdx.x * WG_PART;
 #pragma unroll
-    for (int m = 0; m < WG_PER; ++m) {
-        const int o = threadIdx.x + WG_TPB * m;
-        if (o < W_MP_FLOATS) partials[(int64_t)blockIdx.x * W_MP_FLOATS + o] = acc[m];
-    }
+    for (int i = 0; i < 6; ++i)
+        *reinterpret_cast<float4*>(out + (6 * xg + i) * WG_DP + 4 * dg) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
 }
 
+// grad[o] += sum over CTAs (ascending) of the (x, d) entry of parameter o
 __global__ void k_reduce_partials(int n_part, const float* __restrict__ partials, float* __restrict__ grad) {
     const int o = blockIdx.x * blockDim.x + threadIdx.x;
     if (o >= W_MP_FLOATS) return;
+    int xc, dc;
+    wgrad_cols(o, xc, dc);
+    const float* p0 = partials + xc * WG_DP + dc;
     float s = 0.f;
-    for (int p = 0; p < n_part; ++p) s += partials[(int64_t)p * W_MP_FLOATS + o];
+    for (int p = 0; p < n_part; ++p) s += p0[(int64_t)p * WG_PART];
     grad[o] += s;
 }
 

@@ -278,3 +278,32 @@ def test_full_size_properties(ctx, tmp_path):
         ls2 = eb.local_search(final_routing, mode=0)
         assert np.array_equal(ls2["start"], ls["final"])
     eb.close()
+
+
+@pytest.mark.parametrize("name,n_tms", [("tiny12", 24), ("eli20", 6)])
+def test_greedy_actions_many_tms(ctx, weights, name, n_tms, tmp_path_factory):
+    """north_star: 'the greedy action sequence and final max link utilisation must be identical on the
+    shipped checkpoint' -- checked on fresh synthetic TMs (not only the recorded golden ones), whole
+    batch at once on the GPU against the oracle one episode at a time, Local Search included."""
+    from enero_b200 import datasets as ds
+    from enero_b200.engine import EpisodeBatch
+    case, topo, ot = _topos(name, tmp_path_factory)
+    gf = case_graph_file(case, tmp_path_factory.mktemp(name + "many"))
+    sigma = ds.sigma_for_mean_utilisation(gf)
+    tms = np.stack([ds.uniform_tm(gf.num_nodes, sigma, 7000 + j) for j in range(n_tms)])
+    eb = EpisodeBatch(ctx, topo, n_tms)
+    eb.reset(tms)
+    eb.run_greedy()
+    best, ospf, routing = eb.best()
+    act, rew, hmax = eb.history()
+    steps = eb.state()["steps"]
+    ls = eb.local_search(None, mode=0)
+    for i in range(n_tms):
+        obest, oospf, orouting, oactions = orc.play_middrout_greedy(weights, orc.Env16(ot), tms[i])
+        assert act[i, :steps[i]].tolist() == oactions, "TM %d: action sequences differ" % i
+        assert (best[i], ospf[i]) == (obest, oospf)
+        e15 = orc.Env15(ot)
+        cur = e15.reset_DRL_hill_sp(tms[i], orouting)
+        ofinal, _ = orc.local_search(e15, cur)
+        assert ls["final"][i] == ofinal
+    eb.close()
