@@ -109,6 +109,9 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------
 # CPU path (oracle): one decision = restated actor over all candidates + env step
 # ------------------------------------------------------------------------------------------
+_WORKER = {}
+
+
 def _cpu_worker(args):
     tm, n_dec, seed = args
     os.environ.setdefault("OMP_NUM_THREADS", "1")
@@ -119,9 +122,10 @@ def _cpu_worker(args):
         pass
     from enero_b200 import datasets as ds            # noqa: F401
     from oracle import enero_oracle as orc
-    wd, _ = load_weights()
-    gf, _ = make_topology()
-    topo = orc.Topology(gf, K=100)
+    if "topo" not in _WORKER:                        # per-process one-off, like the reference's generate_environment
+        _WORKER["wd"] = load_weights()[0]
+        _WORKER["topo"] = orc.Topology(make_topology()[0], K=100)
+    wd, topo = _WORKER["wd"], _WORKER["topo"]
     env = orc.Env16(topo)
     _, s, d = env.reset(tm)
     t0 = time.perf_counter()
@@ -269,8 +273,22 @@ def run_ours(args, rank, world, local_rank):
     achieved = B * bytes_per_dec_iter / (launch_ms / 1000.0) / 1e9 if launch_ms else 0.0
     fp32_peak = 148 * 128 * 2 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6 / 1e12
     fp32_ach = B * flops_per_dec_iter / (launch_ms / 1000.0) / 1e12 if launch_ms else 0.0
+    # measured DRAM traffic of one k_mp_iter launch, from the committed ncu --set full capture (taken at
+    # 1024 episodes per GPU on this workload; scaled linearly with the batch)
+    traffic, traffic_src = None, None
+    prof = os.path.join(ROOT, "profiles", "r01_v5_k_mp_iter_ncu_full.csv")
+    if os.path.isfile(prof):
+        import csv
+        rows = {r[0]: r for r in csv.reader(open(prof)) if r}
+        try:
+            mb = float(rows["dram__bytes_read.sum"][2]) + float(rows["dram__bytes_write.sum"][2])
+            traffic = mb * 1e6 * B / 1024.0
+            traffic_src = "profiles/r01_v5_k_mp_iter_ncu_full.csv (dram__bytes_read.sum + dram__bytes_write.sum, launch 1, x B/1024)"
+        except Exception:
+            traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": None, "kernel": "k_mp_iter<IdxTopo>",
+                "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": B * bytes_per_dec_iter, "kernel": "k_mp_iter<IdxTopo>",
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst)" if peaks else "fallback 6.65 TB/s",
                 "launch_ms": launch_ms, "launches_timed": mp_n,
                 "note": "the kernel is FP32-FMA bound, not HBM bound (SURVEY 8d): see fp32",
