@@ -24,6 +24,7 @@ class EpisodeBatch:
         h = C.c_void_p()
         _lib.check(self._lib.enero_batch_create(ctx.handle, topo.handle, self.B, float(percentage_demands), C.byref(h)))
         self._h = h
+        ctx._adopt(self)
         self.Dmax = int(self._lib.enero_batch_dmax(h))
 
     def close(self):

