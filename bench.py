@@ -354,8 +354,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--batch", type=int, default=1024, help="episodes per GPU")
-    ap.add_argument("--e2e-batch", type=int, default=1024)
+    ap.add_argument("--batch", type=int, default=4096, help="episodes per GPU")
+    ap.add_argument("--e2e-batch", type=int, default=4096)
     ap.add_argument("--cpu-decisions", type=int, default=300)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])

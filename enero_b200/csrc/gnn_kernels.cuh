@@ -208,12 +208,17 @@ __device__ __forceinline__ void mp_phase_B(const float* __restrict__ sw, const f
 }
 
 // agg += selu(a + B) for one gathered operand row (packed f32x2 lanes, rounding identical to the scalar form)
-__device__ __forceinline__ void mp_accumulate(u64 (&agg2)[H / 2], const float (&a)[H], const float* __restrict__ myb) {
+__device__ __forceinline__ void mp_accumulate(u64 (&agg2)[H / 2], const float (&a)[H], const u64 (&t2)[H / 2]) {
+#pragma unroll
+    for (int j = 0; j < H / 2; ++j)
+        agg2[j] = add2(agg2[j], selu_fast2(add2(pack2(a[2 * j], a[2 * j + 1]), t2[j])));
+}
+// the row's B vector as packed pairs, read once from its slot before the gather loop
+__device__ __forceinline__ void mp_load_B(u64 (&t2)[H / 2], const float* __restrict__ myb) {
 #pragma unroll
     for (int jb = 0; jb < H / 4; ++jb) {
         const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(myb + 4 * jb);
-        agg2[2 * jb] = add2(agg2[2 * jb], selu_fast2(add2(pack2(a[4 * jb], a[4 * jb + 1]), t.x)));
-        agg2[2 * jb + 1] = add2(agg2[2 * jb + 1], selu_fast2(add2(pack2(a[4 * jb + 2], a[4 * jb + 3]), t.y)));
+        t2[2 * jb] = t.x; t2[2 * jb + 1] = t.y;
     }
 }
 
@@ -403,6 +408,9 @@ __device__ __forceinline__ void mp_tile_body(const IDX& idx, const float* __rest
         // runs on packed f32x2 lanes (half the issue slots of the scalar form).
         {
             const int steps = max(ref[0].pe - ref[0].pb, ref[1].pe - ref[1].pb);
+            u64 t2[MP_R][H / 2];
+#pragma unroll
+            for (int r = 0; r < MP_R; ++r) mp_load_B(t2[r], myb[r]);
             for (int s = 0; s < steps; ++s) {
                 float a[MP_R][H];
                 bool on[MP_R];
@@ -414,7 +422,7 @@ __device__ __forceinline__ void mp_tile_body(const IDX& idx, const float* __rest
 #pragma unroll
                 for (int r = 0; r < MP_R; ++r) {
                     if (!on[r]) continue;
-                    mp_accumulate(agg2[r], a[r], myb[r]);
+                    mp_accumulate(agg2[r], a[r], t2[r]);
                 }
             }
         }

@@ -164,13 +164,16 @@ k_mp_tile(const TileTopo tt, const float* __restrict__ wflat, const float* __res
         // ---- agg = sum over incoming pairs (ascending pair index) of selu(A[first] + B), operands from stage
         {
             const int steps = max(pe[0] - pb[0], pe[1] - pb[1]);
+            u64 t2[MP_R][H / 2];
+#pragma unroll
+            for (int r = 0; r < MP_R; ++r) mp_load_B(t2[r], myb[r]);
             for (int s = 0; s < steps; ++s) {
 #pragma unroll
                 for (int r = 0; r < MP_R; ++r) {
                     if (pb[r] + s < pe[r]) {
                         float a[H];
                         load_row(a, stage + (tt.in_first[pb[r] + s] + soff[r]) * H);
-                        mp_accumulate(agg2[r], a, myb[r]);
+                        mp_accumulate(agg2[r], a, t2[r]);
                     }
                 }
             }
