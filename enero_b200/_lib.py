@@ -54,6 +54,8 @@ SIGNATURES = {
     "enero_topo_get_middlepoints": (C.c_int, [_vp, _vp, _vp]),
     "enero_topo_get_capacity_feature": (C.c_int, [_vp, _vp]),
     "enero_topo_upload": (C.c_int, [_vp, _vp]),
+    "enero_parse_demands": (C.c_int, [C.c_char_p, C.c_int, _vp]),
+    "enero_parse_demands_batch": (C.c_int, [_p(C.c_char_p), C.c_int, C.c_int, _vp, C.c_int]),
     "enero_gnn_forward": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int, C.c_int, _vp, C.c_int]),
     "enero_decide_batch": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int]),
     "enero_value_batch": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, C.c_int]),

@@ -15,13 +15,13 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libenero_b200.so")
-SOURCES = ("topology.cpp", "api.cu")
+SOURCES = ("topology.cpp", "ingest.cpp", "api.cu")
 HEADERS = ("enero_internal.h", "ctx.cuh", "gnn_kernels.cuh", "mp_tile_kernel.cuh", "env_kernels.cuh", "train_kernels.cuh", "train_api.cuh",
            os.path.join("..", "..", "include", "enero_b200.h"))
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-    "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "-shared", "-cudart", "static",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "-Xcompiler", "-pthread", "-shared", "-cudart", "static",
 ]
 
 

@@ -85,6 +85,21 @@ def parse_demands_file(path: str, num_nodes: int) -> np.ndarray:
     return tm
 
 
+def parse_demands_files(paths, num_nodes: int, threads: int = 0) -> np.ndarray:
+    """many ``.demands`` files -> fp64 [n, N, N], parsed by the library's multi-threaded C++ reader
+    (same accept rules as ``parse_demands_file``)."""
+    import ctypes as C
+
+    from . import _lib
+    lib = _lib.load()
+    paths = [os.fsencode(p) for p in paths]
+    out = np.zeros((len(paths), num_nodes, num_nodes))
+    if paths:
+        arr = (C.c_char_p * len(paths))(*paths)
+        _lib.check(lib.enero_parse_demands_batch(arr, len(paths), int(num_nodes), _lib.ptr(out), int(threads)))
+    return out
+
+
 # --------------------------------------------------------------------------
 # synthetic generators (SURVEY.md section 8d)
 # --------------------------------------------------------------------------

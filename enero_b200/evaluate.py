@@ -138,8 +138,7 @@ def evaluate_topology(ctx: Context, dataset_folder, topology_name, tm_ids, out_f
     topo = Topology.from_dataset(dataset_folder, topology_name, K=K)
     b, e = shard_range(len(tm_ids), rank, world)
     mine = list(tm_ids[b:e])
-    tms = np.stack([ds.parse_demands_file(os.path.join(dataset_folder, "TM", "%s.%s.demands" % (topology_name, t)), topo.N)
-                    for t in mine]) if mine else np.zeros((0, topo.N, topo.N))
+    tms = ds.parse_demands_files([os.path.join(dataset_folder, "TM", "%s.%s.demands" % (topology_name, t)) for t in mine], topo.N)
     res = evaluate_tms(ctx, topo, tms, percentage_demands, plain_hill_climbing, batch) if mine else None
     if out_folder is not None and mine:
         write_records(res, mine, out_folder, differentiation_str, topology_name, topo.E)

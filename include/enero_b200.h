@@ -94,6 +94,13 @@ int enero_topo_get_middlepoints(const enero_topo* topo, int32_t* off, int32_t* m
 int enero_topo_get_capacity_feature(const enero_topo* topo, float* capf);
 int enero_topo_upload(enero_ctx* ctx, enero_topo* topo);
 
+/* ---- dataset ingest (host only) ------------------------------------------------------------
+ * Defo_results._get_traffic_matrix (defo_process_results.py:216-225): skip two header lines, then
+ * `label src dst bw` per line; tm[src][dst] = floor(bw).  tm fp64[N*N] (zero-filled by the callee);
+ * the batch form parses n_files files into tms fp64[n_files,N,N] on n_threads host threads (0 = all). */
+int enero_parse_demands(const char* path, int n_nodes, double* tm);
+int enero_parse_demands_batch(const char* const* paths, int n_files, int n_nodes, double* tms, int n_threads);
+
 /* ---- GNN, signature-compatible path ------------------------------------------
  * actor.myModel.call (actorPPOmiddR.py:42-69) when graph_id != NULL, critic.myModel.call
  * (criticPPO.py:38-64) when graph_id == NULL (single graph, n_graphs must be 1).

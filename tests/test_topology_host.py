@@ -39,3 +39,41 @@ def test_bad_input_fails_loudly(tmp_path):
     gf.links_bw[gf.edge_list()[0]] = 0.0
     with pytest.raises(_lib.EneroError):
         Topology(gf)
+
+
+def test_native_demands_parser_matches_python(tmp_path):
+    """enero_parse_demands_batch == the line-by-line Python parser == defo_process_results.py:216-225"""
+    import os
+    import time
+    from enero_b200 import datasets as ds
+    rng = np.random.default_rng(0)
+    n = 23
+    paths = []
+    for j in range(40):
+        tm = rng.uniform(0, 5000, (n, n))
+        np.fill_diagonal(tm, 0.0)
+        p = os.path.join(str(tmp_path), "t.%d.demands" % j)
+        with open(p, "w") as fp:
+            fp.write("DEMANDS %d\nlabel src dest bw\n" % (n * (n - 1)))
+            k = 0
+            for s in range(n):
+                for d in range(n):
+                    if s != d:
+                        # fractional, exponent and integer spellings: float() / strtod must agree
+                        v = tm[s, d]
+                        txt = ("%.3f" % v) if k % 3 == 0 else (("%.6e" % v) if k % 3 == 1 else str(int(v)))
+                        fp.write("demand_%d %d %d %s\n" % (k, s, d, txt))
+                        k += 1
+        paths.append(p)
+    t0 = time.perf_counter()
+    want = np.stack([ds.parse_demands_file(p, n) for p in paths])
+    t1 = time.perf_counter()
+    got = ds.parse_demands_files(paths, n)
+    t2 = time.perf_counter()
+    assert np.array_equal(got, want)
+    assert (t2 - t1) < (t1 - t0)
+    from enero_b200 import _lib
+    with pytest.raises(_lib.EneroError):
+        ds.parse_demands_files(paths + [os.path.join(str(tmp_path), "missing.demands")], n)
+    with pytest.raises(_lib.EneroError):
+        ds.parse_demands_files(paths[:1], 5)           # node ids out of range for a 5-node topology
