@@ -62,12 +62,16 @@ extern "C" int enero_ctx_create(int device, enero_ctx** out) {
                 r = ENERO_ERR_CUDA;
             }
         };
-        setup(k_mp_iter<IdxExplicit, false, 20>, c->occ_iter[0][0]);
-        setup(k_mp_iter<IdxExplicit, true, 20>, c->occ_iter[0][1]);
-        setup(k_mp_iter<IdxTopo, false, 20>, c->occ_iter[1][0]);
-        setup(k_mp_iter<IdxTopo, true, 20>, c->occ_iter[1][1]);
         int tmp = 0;
-        setup(k_mp_iter<IdxTopo, false, 3>, tmp);
+        setup(k_mp_iter<IdxExplicit, false, 20, true>, c->occ_iter[0][0]);
+        setup(k_mp_iter<IdxExplicit, true, 20, true>, c->occ_iter[0][1]);
+        setup(k_mp_iter<IdxTopo, false, 20, true>, c->occ_iter[1][0]);
+        setup(k_mp_iter<IdxTopo, true, 20, true>, c->occ_iter[1][1]);
+        setup(k_mp_iter<IdxTopo, false, 3, true>, tmp);
+        setup(k_mp_iter<IdxTopo, false, 20, false>, tmp);
+        setup(k_mp_iter<IdxTopo, true, 20, false>, tmp);
+        setup(k_mp_iter<IdxTopo, false, 3, false>, tmp);
+        if (const char* e = std::getenv("ENERO_MP_TMA")) c->mp_tma = std::atoi(e) != 0;
         if (r != ENERO_OK) return r;
     }
     CUDA_TRY(cudaFuncSetAttribute(k_bwd_gates, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWG_SMEM_BYTES));
@@ -242,14 +246,20 @@ static int launch_topo_iteration(enero_ctx* c, const IdxTopo& idx, int which, bo
         else if (sparse) launch_tile<false, 3>(c, cfg, tt, which, hin, Ain, hout, Aout);
         else launch_tile<false, 20>(c, cfg, tt, which, hin, Ain, hout, Aout);
     } else {
-        const int64_t ntiles = (idx.total + MP_ROWS - 1) / MP_ROWS;
+        const int64_t ntiles = (idx.total + MP_WROWS - 1) / MP_WROWS;          // 64-row warp tiles
         const int occ = std::max(1, c->occ_iter[1][last ? 1 : 0]);
-        const int grid = (int)std::min<int64_t>(ntiles, (int64_t)c->num_sms * occ);
+        const int grid = (int)std::min<int64_t>((ntiles + MP_WARPS - 1) / MP_WARPS, (int64_t)c->num_sms * occ);
         int* ctr = nullptr;
         TRY(next_tile_counter(c, &ctr));
-        if (last) k_mp_iter<IdxTopo, true, 20><<<grid, MP_TPB, MP_SMEM_BYTES, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles, ctr);
-        else if (sparse) k_mp_iter<IdxTopo, false, 3><<<grid, MP_TPB, MP_SMEM_BYTES, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles, ctr);
-        else k_mp_iter<IdxTopo, false, 20><<<grid, MP_TPB, MP_SMEM_BYTES, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles, ctr);
+        if (c->mp_tma) {
+            if (last) k_mp_iter<IdxTopo, true, 20, true><<<grid, MP_TPB, MP_SMEM_BYTES, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles, ctr);
+            else if (sparse) k_mp_iter<IdxTopo, false, 3, true><<<grid, MP_TPB, MP_SMEM_BYTES, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles, ctr);
+            else k_mp_iter<IdxTopo, false, 20, true><<<grid, MP_TPB, MP_SMEM_BYTES, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles, ctr);
+        } else {
+            if (last) k_mp_iter<IdxTopo, true, 20, false><<<grid, MP_TPB, MP_SMEM_BYTES, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles, ctr);
+            else if (sparse) k_mp_iter<IdxTopo, false, 3, false><<<grid, MP_TPB, MP_SMEM_BYTES, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles, ctr);
+            else k_mp_iter<IdxTopo, false, 20, false><<<grid, MP_TPB, MP_SMEM_BYTES, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles, ctr);
+        }
     }
     LAUNCH_CHECK(c);
     if (c->prof) { CUDA_TRY(cudaEventRecord(e1, c->stream)); c->prof_ev.emplace_back(e0, e1); }
@@ -259,7 +269,7 @@ static int launch_topo_iteration(enero_ctx* c, const IdxTopo& idx, int which, bo
 // sparse_first: the rows of iteration 0 have at most 3 non-zero leading columns (fused feature path)
 template <class IDX>
 static int run_iterations(enero_ctx* c, const IDX& idx, int which, int T, int64_t rows, int idx_kind, bool sparse_first = false) {
-    const int64_t ntiles = (rows + MP_ROWS - 1) / MP_ROWS;
+    const int64_t ntiles = (rows + MP_WROWS - 1) / MP_WROWS;
     if (rows >= (int64_t)1 << 31) return fail(ENERO_ERR_INVALID, "more than 2^31 link-state rows in one launch: split the batch");
     for (int it = 0; it < T; ++it) {
         const bool last = (it == T - 1);
@@ -271,7 +281,7 @@ static int run_iterations(enero_ctx* c, const IDX& idx, int which, int T, int64_
             TRY(launch_topo_iteration(c, idx, which, last, it == 0 && sparse_first && !last, hin, Ain, hout, Aout));
         } else {
             const int occ = std::max(1, c->occ_iter[idx_kind][last ? 1 : 0]);
-            const int grid = (int)std::min<int64_t>(ntiles, (int64_t)c->num_sms * occ);
+            const int grid = (int)std::min<int64_t>((ntiles + MP_WARPS - 1) / MP_WARPS, (int64_t)c->num_sms * occ);
             cudaEvent_t e0 = nullptr, e1 = nullptr;
             if (c->prof) {
                 CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
@@ -279,8 +289,8 @@ static int run_iterations(enero_ctx* c, const IDX& idx, int which, int T, int64_
             }
             int* ctr = nullptr;
             TRY(next_tile_counter(c, &ctr));
-            if (last) k_mp_iter<IDX, true, 20><<<grid, MP_TPB, MP_SMEM_BYTES, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles, ctr);
-            else k_mp_iter<IDX, false, 20><<<grid, MP_TPB, MP_SMEM_BYTES, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles, ctr);
+            if (last) k_mp_iter<IDX, true, 20, true><<<grid, MP_TPB, MP_SMEM_BYTES, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles, ctr);
+            else k_mp_iter<IDX, false, 20, true><<<grid, MP_TPB, MP_SMEM_BYTES, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles, ctr);
             LAUNCH_CHECK(c);
             if (c->prof) { CUDA_TRY(cudaEventRecord(e1, c->stream)); c->prof_ev.emplace_back(e0, e1); }
         }

@@ -77,6 +77,8 @@ struct IdxExplicit {
     const int* src;       // [p] source rows in CSR order
     __device__ __forceinline__ bool valid(int64_t r) const { return r < n; }
     __device__ __forceinline__ bool in_range(int64_t r) const { return r < n; }
+    __device__ __forceinline__ int64_t rows() const { return n; }
+    __device__ __forceinline__ bool tile_live(int64_t r0, int) const { return r0 < n; }
     __device__ __forceinline__ void seg(int64_t r, int& b, int& e, const int*& list, int64_t& add) const {
         b = seg_off[r]; e = seg_off[r + 1]; list = src; add = 0;
     }
@@ -97,6 +99,16 @@ struct IdxTopo {
     const int* in_off;    // [E+1]
     const int* in_first;  // [P]
     __device__ __forceinline__ bool in_range(int64_t r) const { return r < total; }
+    __device__ __forceinline__ int64_t rows() const { return total; }
+    // does the row range [r0, r0 + n) hold a live row of any decision?
+    __device__ __forceinline__ bool tile_live(int64_t r0, int n) const {
+        const int64_t r1 = r0 + n;                         // exclusive
+        for (int64_t b = r0 / RPD; b * RPD < r1; ++b) {
+            const int64_t lo = b * RPD, hi = lo + (int64_t)nK[b] * E;      // live rows of decision b
+            if (hi > r0 && lo < r1 && hi > lo) return true;
+        }
+        return false;
+    }
     __device__ __forceinline__ bool valid(int64_t r) const {
         if (r >= total) return false;
         const int b = (int)(r / RPD);
@@ -148,6 +160,37 @@ __device__ __forceinline__ void prefetch_row_l1(const float* p) {
     asm volatile("prefetch.global.L1 [%0];" :: "l"(p + H - 1));
 }
 
+// ---- 1-D TMA (cp.async.bulk) and mbarrier helpers ------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+
 // fast transcendental forms (MUFU.EX2 / MUFU.RCP); relative error ~1e-6, see DESIGN.md
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -183,8 +226,8 @@ __device__ __forceinline__ float tanh_fast(float x) { return fmaf(-2.f, rcp_appr
 // stride, which is bank-conflict-free for LDS/STS.128.
 constexpr int MP_R = 2;
 constexpr int MP_ROWS = MP_TPB * MP_R;                       // rows per tile
-constexpr int MP_SMEM_FLOATS = W_MP_FLOATS + 2 * MP_ROWS * H;  // weights + h slots + B/z slots
-constexpr size_t MP_SMEM_BYTES = sizeof(float) * MP_SMEM_FLOATS;
+constexpr int MP_SMEM_FLOATS = W_MP_FLOATS + 2 * MP_ROWS * H;  // weights + h slots + B/z/A' slots
+constexpr size_t MP_SMEM_BYTES = sizeof(float) * MP_SMEM_FLOATS + 8 * (MP_TPB / 32);   // + one mbarrier per warp
 
 // ---- the FMA phases of one message-passing iteration, shared by k_mp_iter and k_mp_tile ---------------
 // B = bm + h . Wm[20:40]  ->  myb slots
@@ -333,70 +376,80 @@ __device__ __forceinline__ void mp_phase_A(const float* __restrict__ sw, float* 
     }
 }
 
-template <class IDX, bool LAST, int KH>
-__device__ __forceinline__ void mp_tile_body(const IDX& idx, const float* __restrict__ sw, float* const (&myh)[MP_R],
-                                             float* const (&myb)[MP_R], const float* __restrict__ h_in,
-                                             const float* __restrict__ A_in, float* __restrict__ h_out,
-                                             float* __restrict__ A_out, int64_t tile);
-
 // KH = number of leading link-state columns that can be non-zero on entry: 20 in general, 3 for the
 // first iteration of the fused decision path, whose input rows are [util, cap, mark, 0 x 17]
 // (every h-side mat-vec then needs 3 instead of 20 k-steps; adding exact zeros changes no bit).
-template <class IDX, bool LAST, int KH>
+//
+// Every WARP is its own pipeline over 64-row tiles handed out by a global counter: no block-wide barrier
+// after the weights are staged.  Block barriers put the four warps of a CTA in the same phase at the same
+// time; measured on B200, three barriers per tile cost 6-8 % because the FMA-dense phases of one warp
+// then no longer overlap the gather / transcendental phases of its neighbours.
+//
+// TMA = true: the slot of row i of a warp's tile is wsh + 20*i, i.e. the slots ARE the tile's rows in
+// global order, so the tile's link states arrive with one bulk asynchronous copy (cp.async.bulk, 1-D TMA,
+// issued by lane 0, awaited on the warp's own mbarrier) and the new link states leave with one bulk
+// store; A' goes through the B/z slots and a warp-cooperative coalesced store.  No 80-byte-stride
+// LDG/STG (~20 L1 wavefronts each) except the operand gathers, whose rows were prefetched into L1.
+// TMA = false: per-thread LDG/STG for everything.
+constexpr int MP_WROWS = 32 * MP_R;          // rows per warp tile
+constexpr int MP_WARPS = MP_TPB / 32;
+
+template <class IDX, bool LAST, int KH, bool TMA>
 __global__ void __launch_bounds__(MP_TPB, 3)
 k_mp_iter(const IDX idx, const float* __restrict__ wflat, const float* __restrict__ h_in,
           const float* __restrict__ A_in, float* __restrict__ h_out, float* __restrict__ A_out,
           int64_t ntiles, int* __restrict__ tile_counter) {
     extern __shared__ __align__(16) float mp_smem[];
     float* sw = mp_smem;
-    float* sh = mp_smem + W_MP_FLOATS;                // [MP_R][128][20]  h (old, then new)
-    float* sb = sh + MP_ROWS * H;                   // [MP_R][128][20]  B, then z
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* wsh = mp_smem + W_MP_FLOATS + warp * (MP_WROWS * H);                      // h (old, then new) of the warp's tile
+    float* wsb = mp_smem + W_MP_FLOATS + MP_ROWS * H + warp * (MP_WROWS * H);        // B, then z, then A'
+    uint64_t* bar = reinterpret_cast<uint64_t*>(mp_smem + W_MP_FLOATS + 2 * MP_ROWS * H) + warp;
     for (int i = threadIdx.x; i < W_MP_FLOATS / 4; i += MP_TPB)
         reinterpret_cast<float4*>(sw)[i] = reinterpret_cast<const float4*>(wflat)[i];
+    if (TMA && lane == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
+    const int64_t total = idx.rows();
     float* myh[MP_R]; float* myb[MP_R];
 #pragma unroll
-    for (int r = 0; r < MP_R; ++r) { myh[r] = sh + (r * MP_TPB + threadIdx.x) * H; myb[r] = sb + (r * MP_TPB + threadIdx.x) * H; }
+    for (int r = 0; r < MP_R; ++r) { myh[r] = wsh + (r * 32 + lane) * H; myb[r] = wsb + (r * 32 + lane) * H; }
+    uint32_t phase = 0u;
 
-    // Tiles are handed out through a global counter: a static stride leaves the CTAs with unequal numbers
-    // of live tiles (the padded rows past nK*E of every decision are empty), which cost ~13 % in idle
-    // tails (sm__warps_active 16.3 % of a possible 18.75 % in profiles/r01_v4_*).
-    __shared__ int s_next[2];
-    int64_t tile = blockIdx.x;
-    for (int turn = 0; tile < ntiles; ++turn) {
-        if (threadIdx.x == 0) s_next[turn & 1] = (int)gridDim.x + atomicAdd(tile_counter, 1);
-        const int64_t this_tile = tile;
-        __syncthreads();
-        tile = s_next[turn & 1];
-        mp_tile_body<IDX, LAST, KH>(idx, sw, myh, myb, h_in, A_in, h_out, A_out, this_tile);
-    }
-}
-
-template <class IDX, bool LAST, int KH>
-__device__ __forceinline__ void mp_tile_body(const IDX& idx, const float* __restrict__ sw, float* const (&myh)[MP_R],
-                                             float* const (&myb)[MP_R], const float* __restrict__ h_in,
-                                             const float* __restrict__ A_in, float* __restrict__ h_out,
-                                             float* __restrict__ A_out, int64_t tile) {
-    {
+    int64_t tile = (int64_t)blockIdx.x * MP_WARPS + warp;
+    while (tile < ntiles) {
+        int nxt = 0;
+        if (lane == 0) nxt = (int)gridDim.x * MP_WARPS + atomicAdd(tile_counter, 1);
+        const int64_t next = __shfl_sync(0xffffffffu, nxt, 0);
+        const int64_t row0 = tile * MP_WROWS;
+        const int nrows = (int)min((int64_t)MP_WROWS, total - row0);
         int64_t row[MP_R]; bool ok[MP_R]; RowRef ref[MP_R];
 #pragma unroll
-        for (int r = 0; r < MP_R; ++r) { row[r] = tile * MP_ROWS + r * MP_TPB + threadIdx.x; idx.ref(row[r], ref[r]); ok[r] = ref[r].ok; }
-        if (!(ok[0] || ok[1])) return;
-        // pull exactly the message operands this thread will gather into L1 while the B mat-vec runs
-        // (prefetch.global.L1 takes no register and never blocks; rows shared by several threads coalesce)
+        for (int r = 0; r < MP_R; ++r) { row[r] = row0 + r * 32 + lane; idx.ref(row[r], ref[r]); ok[r] = ref[r].ok; }
+        if (!__any_sync(0xffffffffu, ok[0] || ok[1])) { tile = next; continue; }
+        if (TMA && lane == 0) {
+            bulk_wait_read0();                               // this lane's previous bulk store has left the slots
+            mbar_expect_tx(bar, (uint32_t)nrows * H * 4);
+            bulk_g2s(wsh, h_in + row0 * H, (uint32_t)nrows * H * 4, bar);
+        }
+        // pull exactly the message operands this thread will gather into L1 while the copy lands and the B
+        // mat-vec runs (prefetch.global.L1 takes no register and never blocks)
 #pragma unroll
         for (int r = 0; r < MP_R; ++r)
             for (int p = ref[r].pb; p < ref[r].pe; ++p) prefetch_row_l1(A_in + ((int64_t)ref[r].list[p] + ref[r].add) * H);
         float h[MP_R][H];
         u64 agg2[MP_R][H / 2];
+        if (TMA) { mbar_wait(bar, phase); phase ^= 1u; }
 #pragma unroll
         for (int r = 0; r < MP_R; ++r) {
-            if (ok[r]) load_row(h[r], h_in + row[r] * H);
+            if (ok[r]) load_row(h[r], TMA ? myh[r] : h_in + row[r] * H);
             else {
 #pragma unroll
                 for (int j = 0; j < H; ++j) h[r][j] = 0.f;
             }
-            store_row(myh[r], h[r]);
+            if (!TMA || !ok[r]) store_row(myh[r], h[r]);
 #pragma unroll
             for (int j = 0; j < H / 2; ++j) agg2[r][j] = 0ull;
         }
@@ -437,14 +490,29 @@ __device__ __forceinline__ void mp_tile_body(const IDX& idx, const float* __rest
         }
         // ---- z = sigmoid(agg.Kz + b0z + h.Rz + b1z)   (GRUCell, reset_after=True)
         mp_phase_z<KH>(sw, h, agg, myb);
-        // ---- r, candidate state and the new h, four outputs at a time
+        // ---- r, candidate state and the new h; then A' = h' . Wm[0:20]
         float* hout[MP_R]; float* aout[MP_R];
 #pragma unroll
-        for (int r = 0; r < MP_R; ++r) { hout[r] = ok[r] ? h_out + row[r] * H : nullptr; aout[r] = (ok[r] && !LAST) ? A_out + row[r] * H : nullptr; }
+        for (int r = 0; r < MP_R; ++r) {
+            hout[r] = (!TMA && ok[r]) ? h_out + row[r] * H : nullptr;
+            aout[r] = TMA ? myb[r] : ((ok[r] && !LAST) ? A_out + row[r] * H : nullptr);
+        }
         mp_phase_rh<KH>(sw, h, agg, myh, myb, hout);
-        // ---- next iteration's message operand A' = h' . Wm[0:20]
         if (!LAST) mp_phase_A(sw, myh, aout);
+        if (TMA) {
+            fence_proxy_async();                             // slot writes visible to the bulk store
+            __syncwarp();
+            if (lane == 0) { bulk_s2g(h_out + row0 * H, wsh, (uint32_t)nrows * H * 4); bulk_commit(); }
+            if (!LAST) {
+                const float4* src = reinterpret_cast<const float4*>(wsb);
+                float4* dst = reinterpret_cast<float4*>(A_out + row0 * H);
+                for (int i = lane; i < nrows * (H / 4); i += 32) dst[i] = src[i];
+            }
+            __syncwarp();
+        }
+        tile = next;
     }
+    if (TMA && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before exit
 }
 
 // A_0 = h_0 . Wm[0:20] for the signature-compatible path (arbitrary link_state)
