@@ -142,6 +142,46 @@ def write_graph_file(path: str, num_nodes: int, links, caps) -> None:
             k += 2
 
 
+def link_failure_variants(links, caps, num_nodes: int, link_failures: int, num_variants: int, seed: int):
+    """generate_link_failure_topologies.py:123-177: ``num_variants`` distinct copies of the topology with
+    ``link_failures`` random bidirectional links removed, keeping only connected graphs; the surviving
+    links keep their order (so edge ids of a variant follow the same insertion rule as the base graph).
+    Returns ``[(links, caps, removed)]``.  The reference draws with ``random.choice``; this generator is
+    seeded separately (offline data preparation, not on the parity path)."""
+    rng = np.random.default_rng(seed)
+    out, seen = [], set()
+    links = list(links)
+    if link_failures >= len(links):
+        raise ValueError("cannot remove %d of %d links" % (link_failures, len(links)))
+    attempts = 0
+    while len(out) < num_variants:
+        attempts += 1
+        if attempts > 200 * max(1, num_variants):
+            raise RuntimeError("could not find %d connected, distinct variants" % num_variants)
+        drop = tuple(sorted(int(i) for i in rng.choice(len(links), size=link_failures, replace=False)))
+        if drop in seen:
+            continue
+        keep = [i for i in range(len(links)) if i not in drop]
+        # connectivity of the undirected remainder (nx.is_connected in the reference)
+        adj = {v: [] for v in range(num_nodes)}
+        for i in keep:
+            a, b = links[i]
+            adj[a].append(b)
+            adj[b].append(a)
+        stack, reached = [0], {0}
+        while stack:
+            v = stack.pop()
+            for u in adj[v]:
+                if u not in reached:
+                    reached.add(u)
+                    stack.append(u)
+        if len(reached) != num_nodes:
+            continue
+        seen.add(drop)
+        out.append(([links[i] for i in keep], [caps[i] for i in keep], [links[i] for i in drop]))
+    return out
+
+
 def uniform_tm(num_nodes: int, sigma: float, seed: int) -> np.ndarray:
     rng = np.random.default_rng(seed)
     tm = np.floor(rng.uniform(0.5, 1.0, size=(num_nodes, num_nodes)) * sigma)

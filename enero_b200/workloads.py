@@ -61,24 +61,39 @@ def run_cfg3(ctx, n_tms=10000, rank=0, world=1, batch=2048, topo_spec=(24, 37, 1
             "links": topo.E, "nodes": topo.N}
 
 
-def run_cfg5(ctx, n_topologies=8, n_tms=64, rank=0, world=1, first_seed=1000):
-    """Sweep over synthetic 100-500-link topologies x n_tms TMs, sharded by estimated cost."""
+def run_cfg5(ctx, n_topologies=8, n_tms=64, rank=0, world=1, first_seed=1000, variants_per_base=4):
+    """Link-failure sweep on synthetic data: base Zoo-shaped topologies of 50-250 undirected links
+    (100-500 directed), each with `variants_per_base` link-failure variants (1-3 links removed, connected,
+    distinct: generate_link_failure_topologies.py:123-177) that share the base topology's traffic matrices,
+    n_tms TMs per topology, sharded over the ranks by estimated cost with no collective."""
     rng = np.random.default_rng(5)
-    specs = []
-    for i in range(n_topologies):
+    specs = []                                # (n, links, caps, sigma-source seed, label)
+    n_bases = max(1, (n_topologies + variants_per_base - 1) // variants_per_base)
+    for i in range(n_bases):
         l = int(rng.integers(50, 251))
-        specs.append((max(4, int(round(l / 1.65))), l, first_seed + i))
-    costs = [ds.max_decisions(n) * min(99, n - 1) * (2 * l) * 4.0 for n, l, _ in specs]      # ~ D * K' * (P + E)
+        n = max(4, int(round(l / 1.65)))
+        links, caps = ds.zoo_like(n, l, first_seed + i)
+        fails = 1 + i % 3
+        for j, (vl, vc, _) in enumerate(ds.link_failure_variants(links, caps, n, fails, variants_per_base, 7000 + i)):
+            if len(specs) < n_topologies:
+                specs.append((n, vl, vc, first_seed + i, "syn%d_%d_%d" % (i, fails, j)))
+    costs = [ds.max_decisions(n) * min(99, n - 1) * (4 * len(vl)) * 4.0 for n, vl, _, _, _ in specs]      # ~ D * K' * (P + E)
     mine = par.shard_by_cost(costs, world)[rank]
     out = {"topologies": len(mine), "tms": 0, "decisions": 0, "ls_moves": 0, "seconds": 0.0, "build_seconds": 0.0, "links": [],
            "drl_seconds": 0.0, "ls_seconds": 0.0}
+    tmp = tempfile.mkdtemp(prefix="enero_cfg5_")
+    sigma_cache = {}
     for i in mine:
-        n, l, seed = specs[i]
+        n, vl, vc, base_seed, label = specs[i]
         t0 = time.perf_counter()
-        gf, sigma = synthetic_topology(n, l, seed)
+        p = os.path.join(tmp, label + ".graph")
+        ds.write_graph_file(p, n, vl, vc)
+        gf = ds.parse_graph_file(p)
         topo = Topology(gf, K=100)
         t1 = time.perf_counter()
-        tms = np.stack([ds.uniform_tm(n, sigma, 2000 + j) for j in range(n_tms)])
+        if base_seed not in sigma_cache:      # the variants of one base share its traffic matrices
+            sigma_cache[base_seed] = ds.sigma_for_mean_utilisation(gf)
+        tms = np.stack([ds.uniform_tm(n, sigma_cache[base_seed], 2000 + j) for j in range(n_tms)])
         res = evaluate_tms(ctx, topo, tms, batch=n_tms)
         ctx.sync()
         out["build_seconds"] += t1 - t0

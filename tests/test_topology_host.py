@@ -77,3 +77,28 @@ def test_native_demands_parser_matches_python(tmp_path):
         ds.parse_demands_files(paths + [os.path.join(str(tmp_path), "missing.demands")], n)
     with pytest.raises(_lib.EneroError):
         ds.parse_demands_files(paths[:1], 5)           # node ids out of range for a 5-node topology
+
+
+def test_link_failure_variants():
+    """generate_link_failure_topologies.py:123-177: k links removed, connected, distinct, order kept"""
+    from enero_b200 import datasets as ds
+    links, caps = ds.zoo_like(20, 31, 1001)
+    vs = ds.link_failure_variants(links, caps, 20, 2, 6, seed=3)
+    assert len(vs) == 6 and len({tuple(v[2]) for v in vs}) == 6
+    for vl, vc, removed in vs:
+        assert len(vl) == len(links) - 2 and len(vc) == len(vl) and len(removed) == 2
+        assert vl == [l for l in links if l not in removed]                      # order preserved
+        t = Topology(_gf_from(vl, vc, 20), K=100)                                # strongly connected or build fails
+        assert t.E == 2 * len(vl)
+    with pytest.raises(ValueError):
+        ds.link_failure_variants(links, caps, 20, len(links), 1, seed=0)
+
+
+def _gf_from(links, caps, n):
+    import os
+    import tempfile
+    from enero_b200 import datasets as ds
+    d = tempfile.mkdtemp()
+    p = os.path.join(d, "v.graph")
+    ds.write_graph_file(p, n, links, caps)
+    return ds.parse_graph_file(p)
