@@ -811,8 +811,23 @@ extern "C" int enero_batch_local_search(enero_batch* b, int mode, const int32_t*
               b->ls_elig_len.as<int>(), b->ls_val.as<double>(), b->ls_nmoves.as<int>(), b->ls_moves.as<int>(), b->ls_move_val.as<double>()};
     const size_t smem = ls_smem_bytes(E);
     if (smem > 200 * 1024) return fail(ENERO_ERR_INVALID, "enero_batch_local_search: topology too large for the shared-memory LS kernel");
-    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_local_search, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_local_search<<<B, LS_TPB, smem, st>>>(tv, lv); LAUNCH_CHECK(c);
+    // few episodes: split each episode's demand list over a thread-block cluster so the whole GPU works
+    int CL = 1;
+    while (CL < LS_MAX_CLUSTER && (int64_t)B * CL * 2 <= c->num_sms) CL *= 2;
+    if (CL > 1) {
+        if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_local_search<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(B * CL)); cfg.blockDim = dim3(LS_TPB); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, k_local_search<true>, tv, lv, CL));
+        c->launches++;
+    } else {
+        if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_local_search<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_local_search<false><<<B, LS_TPB, smem, st>>>(tv, lv, 1); LAUNCH_CHECK(c);
+    }
     if (final_val) CUDA_TRY(cudaMemcpyAsync(final_val, b->ls_val.p, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
     if (n_moves) CUDA_TRY(cudaMemcpyAsync(n_moves, b->ls_nmoves.p, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
     if (moves) CUDA_TRY(cudaMemcpyAsync(moves, b->ls_moves.p, (size_t)B * max_moves * 12, cudaMemcpyDeviceToHost, st));

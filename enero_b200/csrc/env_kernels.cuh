@@ -4,6 +4,7 @@
 // order-independent; every utilisation is a correctly-rounded fp64 division, i.e. the
 // very numbers the reference's Python produces.
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -269,8 +270,15 @@ __host__ __device__ inline size_t ls_smem_bytes(int E) {
     return (size_t)(3 * E + nw + LS_TOP) * 8 + (size_t)(3 * nw + LS_TOP) * 4 + (size_t)nw * E + 16;
 }
 
+// CL = CTAs per episode (thread-block cluster): with few episodes in flight the demand list of one episode
+// is split over the CTAs of a cluster; every CTA keeps its own copy of the loads, the per-CTA best moves
+// meet in CTA 0's shared memory (DSMEM), CTA 0 decides and writes the decision into every CTA's shared
+// memory, and all CTAs apply the same move -- two cluster barriers per hill-climbing iteration.
+constexpr int LS_MAX_CLUSTER = 8;
+
+template <bool CLUSTER>
 __global__ void __launch_bounds__(LS_TPB)
-k_local_search(TopoView t, LsView ls) {
+k_local_search(TopoView t, LsView ls, int CL) {
     extern __shared__ double ls_smem[];
     double* sl = ls_smem;                                // [E] loads
     double* scap = sl + t.E;                             // [E]
@@ -282,8 +290,11 @@ k_local_search(TopoView t, LsView ls) {
     int* top_e = wbest_m + 2 * (LS_TPB / 32);            // [LS_TOP] their link ids
     signed char* cnt = reinterpret_cast<signed char*>(top_e + LS_TOP);   // [nwarps][E]
     __shared__ double s_cur; __shared__ int s_stop; __shared__ int s_bd, s_ba, s_ntop;
+    __shared__ double cl_best[LS_MAX_CLUSTER]; __shared__ int cl_key[LS_MAX_CLUSTER], cl_d[LS_MAX_CLUSTER], cl_a[LS_MAX_CLUSTER];
+    namespace cg = cooperative_groups;
+    const int crank = CLUSTER ? (int)cg::this_cluster().block_rank() : 0;
 
-    const int b = blockIdx.x, NN = t.N * t.N;
+    const int b = CLUSTER ? blockIdx.x / CL : blockIdx.x, NN = t.N * t.N;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = LS_TPB / 32;
     const double* tm = ls.tm + (int64_t)b * NN;
     int* mid_cur = ls.mid_cur + (int64_t)b * NN;
@@ -323,7 +334,7 @@ k_local_search(TopoView t, LsView ls) {
         const int ntop = s_ntop;
         // ---- explore the neighbourhood
         double best = 1e300; int best_key = 0x7fffffff, best_d = -1, best_a = -1;
-        for (int di = wid; di < nd; di += nw) {
+        for (int di = crank * nw + wid; di < nd; di += nw * CL) {
             const int sdi = elig[di];
             const int s = sdi / t.N, d = sdi - s * t.N;
             const double bw = tm[sdi];
@@ -391,14 +402,30 @@ k_local_search(TopoView t, LsView ls) {
             double bb = 1e300; int bk = 0x7fffffff, bd = -1, ba = -1;
             for (int w = 0; w < nw; ++w)
                 if (wbest[w] < bb || (wbest[w] == bb && wbest_i[w] < bk)) { bb = wbest[w]; bk = wbest_i[w]; bd = wbest_m[2 * w]; ba = wbest_m[2 * w + 1]; }
+            if (CLUSTER) {
+                cg::cluster_group cl = cg::this_cluster();
+                *cl.map_shared_rank(&cl_best[crank], 0) = bb; *cl.map_shared_rank(&cl_key[crank], 0) = bk;
+                *cl.map_shared_rank(&cl_d[crank], 0) = bd; *cl.map_shared_rank(&cl_a[crank], 0) = ba;
+            } else { cl_best[0] = bb; cl_key[0] = bk; cl_d[0] = bd; cl_a[0] = ba; }
+        }
+        if (CLUSTER) cg::this_cluster().sync();
+        if (threadIdx.x == 0 && crank == 0) {
+            double bb = 1e300; int bk = 0x7fffffff, bd = -1, ba = -1;
+            for (int c = 0; c < CL; ++c)
+                if (cl_best[c] < bb || (cl_best[c] == bb && cl_key[c] < bk)) { bb = cl_best[c]; bk = cl_key[c]; bd = cl_d[c]; ba = cl_a[c]; }
             // nextVal = -bb (or -1000000 with no move), currentVal = -s_cur (script :483-486)
             const double nextVal = bd >= 0 ? -bb : -1000000.0;
             const double currentVal = -s_cur;
             const bool stop = (nextVal <= currentVal) || (fabs((-1.0) * nextVal - (-1.0) * currentVal) < 1e-4) ||
                               nmoves >= ls.max_moves;
-            s_stop = stop ? 1 : 0; s_bd = bd; s_ba = ba;
+            if (CLUSTER) {
+                cg::cluster_group cl = cg::this_cluster();
+                for (int c = 0; c < CL; ++c) {
+                    *cl.map_shared_rank(&s_stop, c) = stop ? 1 : 0; *cl.map_shared_rank(&s_bd, c) = bd; *cl.map_shared_rank(&s_ba, c) = ba;
+                }
+            } else { s_stop = stop ? 1 : 0; s_bd = bd; s_ba = ba; }
         }
-        __syncthreads();
+        if (CLUSTER) cg::this_cluster().sync(); else __syncthreads();
         if (s_stop) break;
         // ---- apply the move: de-allocate (:494-502) + step_hill_sp
         if (wid == 0) {
@@ -412,9 +439,9 @@ k_local_search(TopoView t, LsView ls) {
             double nu; int ne;
             warp_max_uti(sl, scap, t.E, lane, nu, ne);
             if (lane == 0) {
-                mid_cur[sdi] = (m1 != d) ? m1 : -1;
+                mid_cur[sdi] = (m1 != d) ? m1 : -1;      // every CTA of a cluster stores the same value (its own later reads see it)
                 s_cur = nu;
-                if (ls.moves) {
+                if (ls.moves && crank == 0) {
                     int* mv = ls.moves + ((int64_t)b * ls.max_moves + nmoves) * 3;
                     mv[0] = s_ba; mv[1] = s; mv[2] = d;
                     ls.move_val[(int64_t)b * ls.max_moves + nmoves] = nu;
@@ -424,8 +451,11 @@ k_local_search(TopoView t, LsView ls) {
         ++nmoves;
         __syncthreads();
     }
-    for (int e = threadIdx.x; e < t.E; e += LS_TPB) ls.loads[(int64_t)b * t.E + e] = sl[e];
-    if (threadIdx.x == 0) { ls.cur_val[b] = s_cur; ls.n_moves[b] = nmoves; }
+    if (crank == 0) {
+        for (int e = threadIdx.x; e < t.E; e += LS_TPB) ls.loads[(int64_t)b * t.E + e] = sl[e];
+        if (threadIdx.x == 0) { ls.cur_val[b] = s_cur; ls.n_moves[b] = nmoves; }
+    }
+    if (CLUSTER) cg::this_cluster().sync();              // no CTA leaves while its shared memory may still be written
 }
 
 }  // namespace enero
