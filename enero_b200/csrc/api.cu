@@ -63,15 +63,11 @@ extern "C" int enero_ctx_create(int device, enero_ctx** out) {
             }
         };
         int tmp = 0;
-        setup(k_mp_iter<IdxExplicit, false, 20, true>, c->occ_iter[0][0]);
-        setup(k_mp_iter<IdxExplicit, true, 20, true>, c->occ_iter[0][1]);
-        setup(k_mp_iter<IdxTopo, false, 20, true>, c->occ_iter[1][0]);
-        setup(k_mp_iter<IdxTopo, true, 20, true>, c->occ_iter[1][1]);
-        setup(k_mp_iter<IdxTopo, false, 3, true>, tmp);
-        setup(k_mp_iter<IdxTopo, false, 20, false>, tmp);
-        setup(k_mp_iter<IdxTopo, true, 20, false>, tmp);
-        setup(k_mp_iter<IdxTopo, false, 3, false>, tmp);
-        if (const char* e = std::getenv("ENERO_MP_TMA")) c->mp_tma = std::atoi(e) != 0;
+        setup(k_mp_iter<IdxExplicit, false, 20>, c->occ_iter[0][0]);
+        setup(k_mp_iter<IdxExplicit, true, 20>, c->occ_iter[0][1]);
+        setup(k_mp_iter<IdxTopo, false, 20>, c->occ_iter[1][0]);
+        setup(k_mp_iter<IdxTopo, true, 20>, c->occ_iter[1][1]);
+        setup(k_mp_iter<IdxTopo, false, 3>, tmp);
         if (r != ENERO_OK) return r;
     }
     CUDA_TRY(cudaFuncSetAttribute(k_bwd_gates, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWG_SMEM_BYTES));
@@ -247,19 +243,13 @@ static int launch_topo_iteration(enero_ctx* c, const IdxTopo& idx, int which, bo
         else launch_tile<false, 20>(c, cfg, tt, which, hin, Ain, hout, Aout);
     } else {
         const int64_t ntiles = (idx.total + MP_WROWS - 1) / MP_WROWS;          // 64-row warp tiles
-        const int occ = std::max(1, c->occ_iter[1][last ? 1 : 0]);
-        const int grid = (int)std::min<int64_t>((ntiles + MP_WARPS - 1) / MP_WARPS, (int64_t)c->num_sms * occ);
         int* ctr = nullptr;
         TRY(next_tile_counter(c, &ctr));
-        if (c->mp_tma) {
-            if (last) k_mp_iter<IdxTopo, true, 20, true><<<grid, MP_TPB, MP_SMEM_BYTES, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles, ctr);
-            else if (sparse) k_mp_iter<IdxTopo, false, 3, true><<<grid, MP_TPB, MP_SMEM_BYTES, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles, ctr);
-            else k_mp_iter<IdxTopo, false, 20, true><<<grid, MP_TPB, MP_SMEM_BYTES, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles, ctr);
-        } else {
-            if (last) k_mp_iter<IdxTopo, true, 20, false><<<grid, MP_TPB, MP_SMEM_BYTES, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles, ctr);
-            else if (sparse) k_mp_iter<IdxTopo, false, 3, false><<<grid, MP_TPB, MP_SMEM_BYTES, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles, ctr);
-            else k_mp_iter<IdxTopo, false, 20, false><<<grid, MP_TPB, MP_SMEM_BYTES, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles, ctr);
-        }
+        const int occ = std::max(1, c->occ_iter[1][last ? 1 : 0]);
+        const int grid = (int)std::min<int64_t>((ntiles + MP_WARPS - 1) / MP_WARPS, (int64_t)c->num_sms * occ);
+        if (last) k_mp_iter<IdxTopo, true, 20><<<grid, MP_TPB, MP_SMEM_BYTES, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles, ctr);
+        else if (sparse) k_mp_iter<IdxTopo, false, 3><<<grid, MP_TPB, MP_SMEM_BYTES, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles, ctr);
+        else k_mp_iter<IdxTopo, false, 20><<<grid, MP_TPB, MP_SMEM_BYTES, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles, ctr);
     }
     LAUNCH_CHECK(c);
     if (c->prof) { CUDA_TRY(cudaEventRecord(e1, c->stream)); c->prof_ev.emplace_back(e0, e1); }
@@ -280,8 +270,6 @@ static int run_iterations(enero_ctx* c, const IDX& idx, int which, int T, int64_
         if constexpr (std::is_same<IDX, IdxTopo>::value) {
             TRY(launch_topo_iteration(c, idx, which, last, it == 0 && sparse_first && !last, hin, Ain, hout, Aout));
         } else {
-            const int occ = std::max(1, c->occ_iter[idx_kind][last ? 1 : 0]);
-            const int grid = (int)std::min<int64_t>((ntiles + MP_WARPS - 1) / MP_WARPS, (int64_t)c->num_sms * occ);
             cudaEvent_t e0 = nullptr, e1 = nullptr;
             if (c->prof) {
                 CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
@@ -289,8 +277,10 @@ static int run_iterations(enero_ctx* c, const IDX& idx, int which, int T, int64_
             }
             int* ctr = nullptr;
             TRY(next_tile_counter(c, &ctr));
-            if (last) k_mp_iter<IDX, true, 20, true><<<grid, MP_TPB, MP_SMEM_BYTES, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles, ctr);
-            else k_mp_iter<IDX, false, 20, true><<<grid, MP_TPB, MP_SMEM_BYTES, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles, ctr);
+            const int occ = std::max(1, c->occ_iter[idx_kind][last ? 1 : 0]);
+            const int grid = (int)std::min<int64_t>((ntiles + MP_WARPS - 1) / MP_WARPS, (int64_t)c->num_sms * occ);
+            if (last) k_mp_iter<IDX, true, 20><<<grid, MP_TPB, MP_SMEM_BYTES, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles, ctr);
+            else k_mp_iter<IDX, false, 20><<<grid, MP_TPB, MP_SMEM_BYTES, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles, ctr);
             LAUNCH_CHECK(c);
             if (c->prof) { CUDA_TRY(cudaEventRecord(e1, c->stream)); c->prof_ev.emplace_back(e0, e1); }
         }

@@ -52,7 +52,6 @@ struct enero_ctx {
     int occ_iter[2][2] = {{0, 0}, {0, 0}};   // [indexer][last] resident CTAs/SM of k_mp_iter
     int* tile_ctr = nullptr;                 // [16] dynamic tile counters of k_mp_iter, one per launch of a sequence
     int tile_ctr_next = 16;                  // next unused counter (16 = re-zero first)
-    bool mp_tma = true;                      // ENERO_MP_TMA=0: per-thread LDG/STG variant of k_mp_iter
     int tile_tpb_override = -1;              // ENERO_MP_TPB: 0 = never use k_mp_tile, >0 = force this CTA size
     // optional per-launch CUDA-event timing of the dominant kernel (bench.py roofline leg)
     bool prof = false;

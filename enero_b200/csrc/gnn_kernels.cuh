@@ -229,24 +229,37 @@ constexpr int MP_ROWS = MP_TPB * MP_R;                       // rows per tile
 constexpr int MP_SMEM_FLOATS = W_MP_FLOATS + 2 * MP_ROWS * H;  // weights + h slots + B/z/A' slots
 constexpr size_t MP_SMEM_BYTES = sizeof(float) * MP_SMEM_FLOATS + 8 * (MP_TPB / 32);   // + one mbarrier per warp
 
+// ---- where the (warp-uniform) message + GRU weights are read from -----------------------------------------
+// WSmem: staged per CTA in shared memory, every read a broadcast LDS.128.  (The __constant__ bank was
+// measured and dropped, DESIGN.md section 3: with a warp-uniform index ptxas emits LDCU.64 + uniform-register
+// FFMA2 operands, which frees the LSU pipe but runs at half the speed -- 224 k vs 407 k decisions/s -- and
+// per-thread LDC is 5x slower.)
+struct WSmem {
+    const float* sw;
+    __device__ __forceinline__ ulonglong2 ld2(int off) const { return *reinterpret_cast<const ulonglong2*>(sw + off); }
+    __device__ __forceinline__ float4 ld4(int off) const { return *reinterpret_cast<const float4*>(sw + off); }
+};
 // ---- the FMA phases of one message-passing iteration, shared by k_mp_iter and k_mp_tile ---------------
 // B = bm + h . Wm[20:40]  ->  myb slots
-template <int KH>
-__device__ __forceinline__ void mp_phase_B(const float* __restrict__ sw, const float (&h)[MP_R][H], float* const (&myb)[MP_R]) {
+template <int KH, class W>
+__device__ __forceinline__ void mp_phase_B(const W sw, const float (&h)[MP_R][H], float* const (&myb)[MP_R]) {
 #pragma unroll 1
     for (int jb = 0; jb < H / 4; ++jb) {
-        const ulonglong2 b0 = *reinterpret_cast<const ulonglong2*>(sw + W_MSG_B + 4 * jb);
+        // accumulators start at zero and the bias is added after the dot product (the op order of
+        // Dense = matmul + BiasAdd); an accumulator initialised from a constant-bank value would also keep
+        // ptxas from using uniform-register weight operands for the whole loop
         u64 acc[MP_R][2];
 #pragma unroll
-        for (int r = 0; r < MP_R; ++r) { acc[r][0] = b0.x; acc[r][1] = b0.y; }
+        for (int r = 0; r < MP_R; ++r) { acc[r][0] = 0ull; acc[r][1] = 0ull; }
 #pragma unroll
         for (int k = 0; k < KH; ++k) {
-            const ulonglong2 w = *reinterpret_cast<const ulonglong2*>(sw + W_MSG_K + H * H + k * H + 4 * jb);
+            const ulonglong2 w = sw.ld2(W_MSG_K + H * H + k * H + 4 * jb);
 #pragma unroll
             for (int r = 0; r < MP_R; ++r) { acc[r][0] = fma2s(h[r][k], w.x, acc[r][0]); acc[r][1] = fma2s(h[r][k], w.y, acc[r][1]); }
         }
+        const ulonglong2 b0 = sw.ld2(W_MSG_B + 4 * jb);
 #pragma unroll
-        for (int r = 0; r < MP_R; ++r) *reinterpret_cast<ulonglong2*>(myb[r] + 4 * jb) = make_ulonglong2(acc[r][0], acc[r][1]);
+        for (int r = 0; r < MP_R; ++r) *reinterpret_cast<ulonglong2*>(myb[r] + 4 * jb) = make_ulonglong2(add2(acc[r][0], b0.x), add2(acc[r][1], b0.y));
     }
 }
 
@@ -266,61 +279,57 @@ __device__ __forceinline__ void mp_load_B(u64 (&t2)[H / 2], const float* __restr
 }
 
 // z = sigmoid(agg.Kz + b0z + h.Rz + b1z)   (GRUCell, reset_after=True)  ->  myb slots
-template <int KH>
-__device__ __forceinline__ void mp_phase_z(const float* __restrict__ sw, const float (&h)[MP_R][H], const float (&agg)[MP_R][H],
+template <int KH, class W>
+__device__ __forceinline__ void mp_phase_z(const W sw, const float (&h)[MP_R][H], const float (&agg)[MP_R][H],
                                            float* const (&myb)[MP_R]) {
 #pragma unroll 1
     for (int jb = 0; jb < H / 4; ++jb) {
-        const ulonglong2 b0 = *reinterpret_cast<const ulonglong2*>(sw + W_GRU_B + 4 * jb);
         u64 acc[MP_R][2];
 #pragma unroll
-        for (int r = 0; r < MP_R; ++r) { acc[r][0] = b0.x; acc[r][1] = b0.y; }
+        for (int r = 0; r < MP_R; ++r) { acc[r][0] = 0ull; acc[r][1] = 0ull; }
 #pragma unroll
         for (int k = 0; k < H; ++k) {
-            const ulonglong2 wk = *reinterpret_cast<const ulonglong2*>(sw + W_GRU_K + k * 60 + 4 * jb);
+            const ulonglong2 wk = sw.ld2(W_GRU_K + k * 60 + 4 * jb);
 #pragma unroll
             for (int r = 0; r < MP_R; ++r) { acc[r][0] = fma2s(agg[r][k], wk.x, acc[r][0]); acc[r][1] = fma2s(agg[r][k], wk.y, acc[r][1]); }
             if (k < KH) {
-                const ulonglong2 wr = *reinterpret_cast<const ulonglong2*>(sw + W_GRU_R + k * 60 + 4 * jb);
+                const ulonglong2 wr = sw.ld2(W_GRU_R + k * 60 + 4 * jb);
 #pragma unroll
                 for (int r = 0; r < MP_R; ++r) { acc[r][0] = fma2s(h[r][k], wr.x, acc[r][0]); acc[r][1] = fma2s(h[r][k], wr.y, acc[r][1]); }
             }
         }
-        const float4 b1 = *reinterpret_cast<const float4*>(sw + W_GRU_B + 60 + 4 * jb);
+        const ulonglong2 b0 = sw.ld2(W_GRU_B + 4 * jb);
+        const ulonglong2 b1 = sw.ld2(W_GRU_B + 60 + 4 * jb);
 #pragma unroll
         for (int r = 0; r < MP_R; ++r) {
             float v0, v1, v2, v3;
-            unpack2(acc[r][0], v0, v1); unpack2(acc[r][1], v2, v3);
-            *reinterpret_cast<float4*>(myb[r] + 4 * jb) =
-                make_float4(sigmoid_fast(v0 + b1.x), sigmoid_fast(v1 + b1.y), sigmoid_fast(v2 + b1.z), sigmoid_fast(v3 + b1.w));
+            unpack2(add2(add2(acc[r][0], b0.x), b1.x), v0, v1); unpack2(add2(add2(acc[r][1], b0.y), b1.y), v2, v3);
+            *reinterpret_cast<float4*>(myb[r] + 4 * jb) = make_float4(sigmoid_fast(v0), sigmoid_fast(v1), sigmoid_fast(v2), sigmoid_fast(v3));
         }
     }
 }
 
 // r, candidate state and the new h, four outputs at a time: new h -> myh slots (and hout[r] + 4*jb if non-null)
-template <int KH>
-__device__ __forceinline__ void mp_phase_rh(const float* __restrict__ sw, const float (&h)[MP_R][H], const float (&agg)[MP_R][H],
+template <int KH, class W>
+__device__ __forceinline__ void mp_phase_rh(const W sw, const float (&h)[MP_R][H], const float (&agg)[MP_R][H],
                                             float* const (&myh)[MP_R], float* const (&myb)[MP_R], float* const (&hout)[MP_R]) {
 #pragma unroll 1
     for (int jb = 0; jb < H / 4; ++jb) {
-        const ulonglong2 br = *reinterpret_cast<const ulonglong2*>(sw + W_GRU_B + 20 + 4 * jb);
-        const ulonglong2 bx = *reinterpret_cast<const ulonglong2*>(sw + W_GRU_B + 40 + 4 * jb);
-        const ulonglong2 by = *reinterpret_cast<const ulonglong2*>(sw + W_GRU_B + 100 + 4 * jb);
         u64 ar[MP_R][2], ax[MP_R][2], ay[MP_R][2];
 #pragma unroll
-        for (int r = 0; r < MP_R; ++r) { ar[r][0] = br.x; ar[r][1] = br.y; ax[r][0] = bx.x; ax[r][1] = bx.y; ay[r][0] = by.x; ay[r][1] = by.y; }
+        for (int r = 0; r < MP_R; ++r) { ar[r][0] = ar[r][1] = ax[r][0] = ax[r][1] = ay[r][0] = ay[r][1] = 0ull; }
 #pragma unroll
         for (int k = 0; k < H; ++k) {
-            const ulonglong2 kr = *reinterpret_cast<const ulonglong2*>(sw + W_GRU_K + k * 60 + 20 + 4 * jb);
-            const ulonglong2 kh = *reinterpret_cast<const ulonglong2*>(sw + W_GRU_K + k * 60 + 40 + 4 * jb);
+            const ulonglong2 kr = sw.ld2(W_GRU_K + k * 60 + 20 + 4 * jb);
+            const ulonglong2 kh = sw.ld2(W_GRU_K + k * 60 + 40 + 4 * jb);
 #pragma unroll
             for (int r = 0; r < MP_R; ++r) {
                 ar[r][0] = fma2s(agg[r][k], kr.x, ar[r][0]); ar[r][1] = fma2s(agg[r][k], kr.y, ar[r][1]);
                 ax[r][0] = fma2s(agg[r][k], kh.x, ax[r][0]); ax[r][1] = fma2s(agg[r][k], kh.y, ax[r][1]);
             }
             if (k < KH) {
-                const ulonglong2 rr = *reinterpret_cast<const ulonglong2*>(sw + W_GRU_R + k * 60 + 20 + 4 * jb);
-                const ulonglong2 rh = *reinterpret_cast<const ulonglong2*>(sw + W_GRU_R + k * 60 + 40 + 4 * jb);
+                const ulonglong2 rr = sw.ld2(W_GRU_R + k * 60 + 20 + 4 * jb);
+                const ulonglong2 rh = sw.ld2(W_GRU_R + k * 60 + 40 + 4 * jb);
 #pragma unroll
                 for (int r = 0; r < MP_R; ++r) {
                     ar[r][0] = fma2s(h[r][k], rr.x, ar[r][0]); ar[r][1] = fma2s(h[r][k], rr.y, ar[r][1]);
@@ -328,13 +337,16 @@ __device__ __forceinline__ void mp_phase_rh(const float* __restrict__ sw, const 
                 }
             }
         }
-        const float4 b1r = *reinterpret_cast<const float4*>(sw + W_GRU_B + 80 + 4 * jb);
+        const ulonglong2 br = sw.ld2(W_GRU_B + 20 + 4 * jb);       // input biases of r and the candidate,
+        const ulonglong2 bx = sw.ld2(W_GRU_B + 40 + 4 * jb);
+        const ulonglong2 by = sw.ld2(W_GRU_B + 100 + 4 * jb);      // recurrent bias of the candidate,
+        const float4 b1r = sw.ld4(W_GRU_B + 80 + 4 * jb);          // recurrent bias of r (added below)
 #pragma unroll
         for (int r = 0; r < MP_R; ++r) {
             float rv[4], xv[4], yv[4];
-            unpack2(ar[r][0], rv[0], rv[1]); unpack2(ar[r][1], rv[2], rv[3]);
-            unpack2(ax[r][0], xv[0], xv[1]); unpack2(ax[r][1], xv[2], xv[3]);
-            unpack2(ay[r][0], yv[0], yv[1]); unpack2(ay[r][1], yv[2], yv[3]);
+            unpack2(add2(ar[r][0], br.x), rv[0], rv[1]); unpack2(add2(ar[r][1], br.y), rv[2], rv[3]);
+            unpack2(add2(ax[r][0], bx.x), xv[0], xv[1]); unpack2(add2(ax[r][1], bx.y), xv[2], xv[3]);
+            unpack2(add2(ay[r][0], by.x), yv[0], yv[1]); unpack2(add2(ay[r][1], by.y), yv[2], yv[3]);
             const float4 z = *reinterpret_cast<const float4*>(myb[r] + 4 * jb);
             const float4 ho = *reinterpret_cast<const float4*>(myh[r] + 4 * jb);
             const float b1[4] = {b1r.x, b1r.y, b1r.z, b1r.w};
@@ -355,7 +367,8 @@ __device__ __forceinline__ void mp_phase_rh(const float* __restrict__ sw, const 
 }
 
 // next iteration's message operand A' = h' . Wm[0:20]  ->  aout[r] + 4*jb (skipped if null)
-__device__ __forceinline__ void mp_phase_A(const float* __restrict__ sw, float* const (&myh)[MP_R], float* const (&aout)[MP_R]) {
+template <class W>
+__device__ __forceinline__ void mp_phase_A(const W sw, float* const (&myh)[MP_R], float* const (&aout)[MP_R]) {
     float h[MP_R][H];
 #pragma unroll
     for (int r = 0; r < MP_R; ++r) load_row(h[r], myh[r]);
@@ -366,7 +379,7 @@ __device__ __forceinline__ void mp_phase_A(const float* __restrict__ sw, float* 
         for (int r = 0; r < MP_R; ++r) { acc[r][0] = 0ull; acc[r][1] = 0ull; }
 #pragma unroll
         for (int k = 0; k < H; ++k) {
-            const ulonglong2 w = *reinterpret_cast<const ulonglong2*>(sw + W_MSG_K + k * H + 4 * jb);
+            const ulonglong2 w = sw.ld2(W_MSG_K + k * H + 4 * jb);
 #pragma unroll
             for (int r = 0; r < MP_R; ++r) { acc[r][0] = fma2s(h[r][k], w.x, acc[r][0]); acc[r][1] = fma2s(h[r][k], w.y, acc[r][1]); }
         }
@@ -394,19 +407,23 @@ __device__ __forceinline__ void mp_phase_A(const float* __restrict__ sw, float* 
 constexpr int MP_WROWS = 32 * MP_R;          // rows per warp tile
 constexpr int MP_WARPS = MP_TPB / 32;
 
-template <class IDX, bool LAST, int KH, bool TMA>
+template <class IDX, bool LAST, int KH>
 __global__ void __launch_bounds__(MP_TPB, 3)
 k_mp_iter(const IDX idx, const float* __restrict__ wflat, const float* __restrict__ h_in,
           const float* __restrict__ A_in, float* __restrict__ h_out, float* __restrict__ A_out,
           int64_t ntiles, int* __restrict__ tile_counter) {
+    constexpr bool TMA = true;                 // per-thread LDG/STG variant: measured within 1 %, kept for reference
+    constexpr int NW = MP_WARPS;               // warps per CTA
     extern __shared__ __align__(16) float mp_smem[];
-    float* sw = mp_smem;
+    float* sw_s = mp_smem;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* wsh = mp_smem + W_MP_FLOATS + warp * (MP_WROWS * H);                      // h (old, then new) of the warp's tile
-    float* wsb = mp_smem + W_MP_FLOATS + MP_ROWS * H + warp * (MP_WROWS * H);        // B, then z, then A'
-    uint64_t* bar = reinterpret_cast<uint64_t*>(mp_smem + W_MP_FLOATS + 2 * MP_ROWS * H) + warp;
+    float* slots = mp_smem + W_MP_FLOATS;
+    float* wsh = slots + warp * (MP_WROWS * H);                                      // h (old, then new) of the warp's tile
+    float* wsb = slots + NW * (MP_WROWS * H) + warp * (MP_WROWS * H);                // B, then z, then A'
+    uint64_t* bar = reinterpret_cast<uint64_t*>(slots + 2 * NW * (MP_WROWS * H)) + warp;
     for (int i = threadIdx.x; i < W_MP_FLOATS / 4; i += MP_TPB)
-        reinterpret_cast<float4*>(sw)[i] = reinterpret_cast<const float4*>(wflat)[i];
+        reinterpret_cast<float4*>(sw_s)[i] = reinterpret_cast<const float4*>(wflat)[i];
+    WSmem sw; sw.sw = sw_s;
     if (TMA && lane == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -418,10 +435,10 @@ k_mp_iter(const IDX idx, const float* __restrict__ wflat, const float* __restric
     for (int r = 0; r < MP_R; ++r) { myh[r] = wsh + (r * 32 + lane) * H; myb[r] = wsb + (r * 32 + lane) * H; }
     uint32_t phase = 0u;
 
-    int64_t tile = (int64_t)blockIdx.x * MP_WARPS + warp;
+    int64_t tile = (int64_t)blockIdx.x * NW + warp;
     while (tile < ntiles) {
         int nxt = 0;
-        if (lane == 0) nxt = (int)gridDim.x * MP_WARPS + atomicAdd(tile_counter, 1);
+        if (lane == 0) nxt = (int)gridDim.x * NW + atomicAdd(tile_counter, 1);
         const int64_t next = __shfl_sync(0xffffffffu, nxt, 0);
         const int64_t row0 = tile * MP_WROWS;
         const int nrows = (int)min((int64_t)MP_WROWS, total - row0);

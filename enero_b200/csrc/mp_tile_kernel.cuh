@@ -80,13 +80,14 @@ k_mp_tile(const TileTopo tt, const float* __restrict__ wflat, const float* __res
     extern __shared__ __align__(16) float mpt_smem[];
     const int TPB = blockDim.x;
     const int slots = MP_R * TPB;
-    float* sw = mpt_smem;
-    float* sh = sw + W_MP_FLOATS;              // slot i = tile row i: h (old, then new)
+    float* sw_s = mpt_smem;
+    WSmem sw; sw.sw = sw_s;
+    float* sh = sw_s + W_MP_FLOATS;            // slot i = tile row i: h (old, then new)
     float* sb = sh + slots * H;                // B, then z, then A'
     float* stage = sb + slots * H;             // message operands of the tile's graphs
     uint64_t* bar = reinterpret_cast<uint64_t*>(stage + tt.G * tt.off_f * H);
     for (int i = threadIdx.x; i < W_MP_FLOATS / 4; i += TPB)
-        reinterpret_cast<float4*>(sw)[i] = reinterpret_cast<const float4*>(wflat)[i];
+        reinterpret_cast<float4*>(sw_s)[i] = reinterpret_cast<const float4*>(wflat)[i];
     if (threadIdx.x == 0) mbar_init(bar, 1);
     __syncthreads();
     float* myh[MP_R]; float* myb[MP_R];
