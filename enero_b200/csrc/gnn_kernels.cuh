@@ -445,7 +445,10 @@ k_mp_iter(const IDX idx, const float* __restrict__ wflat, const float* __restric
         int64_t row[MP_R]; bool ok[MP_R]; RowRef ref[MP_R];
 #pragma unroll
         for (int r = 0; r < MP_R; ++r) { row[r] = row0 + r * 32 + lane; idx.ref(row[r], ref[r]); ok[r] = ref[r].ok; }
-        if (!__any_sync(0xffffffffu, ok[0] || ok[1])) { tile = next; continue; }
+        bool any_ok = false;
+#pragma unroll
+        for (int r = 0; r < MP_R; ++r) any_ok |= ok[r];
+        if (!__any_sync(0xffffffffu, any_ok)) { tile = next; continue; }
         if (TMA && lane == 0) {
             bulk_wait_read0();                               // this lane's previous bulk store has left the slots
             mbar_expect_tx(bar, (uint32_t)nrows * H * 4);
@@ -477,7 +480,9 @@ k_mp_iter(const IDX idx, const float* __restrict__ wflat, const float* __restric
         // are in flight per step (each row still adds its pairs in ascending order); the SELU arithmetic
         // runs on packed f32x2 lanes (half the issue slots of the scalar form).
         {
-            const int steps = max(ref[0].pe - ref[0].pb, ref[1].pe - ref[1].pb);
+            int steps = 0;
+#pragma unroll
+            for (int r = 0; r < MP_R; ++r) steps = max(steps, ref[r].pe - ref[r].pb);
             u64 t2[MP_R][H / 2];
 #pragma unroll
             for (int r = 0; r < MP_R; ++r) mp_load_B(t2[r], myb[r]);
