@@ -65,13 +65,51 @@ def make_tms(gf, sigma, count, first_seed):
 # clocks sampled during the timed region
 # ------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region: NVML in a thread every 5 ms
+    (nvidia_ml_py), nvidia-smi every 100 ms as the fallback."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
 
     def __init__(self, index):
         self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # LOCAL_RANK indexes the visible devices; NVML indexes physical ones
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if index < len(ids) and ids[index].isdigit():
+                    phys = int(ids[index])
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self._nvml = pynvml
+        except Exception:
+            self._nvml = None
 
-    def _run(self):
+    def _run_nvml(self):
+        n = self._nvml
+        bits = ((getattr(n, "nvmlClocksEventReasonHwSlowdown", 0x8), "hw_slowdown"),
+                (getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", 0x40), "hw_thermal_slowdown"),
+                (getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", 0x20), "sw_thermal_slowdown"),
+                (getattr(n, "nvmlClocksEventReasonSwPowerCap", 0x4), "sw_power_cap"))
+        try:
+            mx = float(n.nvmlDeviceGetMaxClockInfo(self._h, n.NVML_CLOCK_SM))
+        except Exception:
+            mx = 0.0
+        get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self._stop.is_set():
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM))
+                mask = int(get_reasons(self._h))
+                self.rows.append([sm, mx] + ["Active" if mask & b else "Not Active" for b, _ in bits])
+            except Exception:
+                pass
+            self._stop.wait(0.005)
+
+    def _run_smi(self):
         while not self._stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
@@ -82,7 +120,7 @@ class ClockSampler:
             self._stop.wait(0.1)
 
     def __enter__(self):
-        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t = threading.Thread(target=self._run_nvml if self._nvml else self._run_smi, daemon=True)
         self._t.start()
         return self
 
@@ -92,18 +130,17 @@ class ClockSampler:
 
     def summary(self):
         sm, mx, reasons = [], 0.0, set()
-        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
         for r in self.rows:
             try:
                 sm.append(float(r[0]))
                 mx = max(mx, float(r[1]))
             except Exception:
                 continue
-            for nme, v in zip(names, r[2:6]):
-                if v.lower().startswith("active"):
+            for nme, v in zip(self.NAMES, r[2:6]):
+                if str(v).lower().startswith("active"):
                     reasons.add(nme)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvml" if self._nvml else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------
@@ -113,7 +150,7 @@ _WORKER = {}
 
 
 def _cpu_worker(args):
-    tm, n_dec, seed = args
+    tms, n_dec, seed = args
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     try:
         import threadpoolctl
@@ -126,17 +163,24 @@ def _cpu_worker(args):
         _WORKER["wd"] = load_weights()[0]
         _WORKER["topo"] = orc.Topology(make_topology()[0], K=100)
     wd, topo = _WORKER["wd"], _WORKER["topo"]
-    env = orc.Env16(topo)
-    _, s, d = env.reset(tm)
-    t0 = time.perf_counter()
-    n = 0
-    while n < n_dec:
-        probs, _, _ = orc.pred_action_distrib(wd, env, s, d)
-        _, done, _, _, s, d, _, _, _ = env.step(int(np.argmax(probs)))
-        n += 1
-        if done:
+    tms = np.asarray(tms)
+    if tms.ndim == 2:
+        tms = tms[None]
+    n, spent = 0, 0.0
+    for tm in tms:                                   # greedy episodes, one TM after the other, until the budget is used
+        env = orc.Env16(topo)
+        _, s, d = env.reset(tm)
+        t0 = time.perf_counter()
+        while n < n_dec:
+            probs, _, _ = orc.pred_action_distrib(wd, env, s, d)
+            _, done, _, _, s, d, _, _, _ = env.step(int(np.argmax(probs)))
+            n += 1
+            if done:
+                break
+        spent += time.perf_counter() - t0
+        if n >= n_dec:
             break
-    return n, time.perf_counter() - t0
+    return n, spent
 
 
 def cpu_decisions_per_sec(gf, sigma, procs, n_dec, first_seed=2000, pool=None):
@@ -144,7 +188,8 @@ def cpu_decisions_per_sec(gf, sigma, procs, n_dec, first_seed=2000, pool=None):
     tms = make_tms(gf, sigma, procs, first_seed)
     jobs = [(tms[i], n_dec, i) for i in range(procs)]
     if pool is None:
-        res = [_cpu_worker(jobs[0])]
+        n_tms = max(1, -(-n_dec // 100))             # ~131 decisions per TM on this topology
+        res = [_cpu_worker((make_tms(gf, sigma, n_tms, first_seed), n_dec, 0))]
         wall = res[0][1]
     else:
         t0 = time.perf_counter()
@@ -330,7 +375,7 @@ def run_ours(args, rank, world, local_rank):
         cores = 1
         v, total, wall = cpu_decisions_per_sec(gf, sigma, 1, args.cpu_decisions, 2000, None)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "%d greedy decisions of one TM (restated numpy actor + env step), %.1f s" % (total, wall)}
+               "sample": "%d greedy decisions over consecutive TMs (restated numpy actor + env step), %.1f s" % (total, wall)}
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -356,7 +401,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=4096, help="episodes per GPU")
     ap.add_argument("--e2e-batch", type=int, default=4096)
-    ap.add_argument("--cpu-decisions", type=int, default=300)
+    ap.add_argument("--cpu-decisions", type=int, default=1000, help="CPU-baseline sample (about 15 s on one core)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()
