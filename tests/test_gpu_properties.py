@@ -150,3 +150,52 @@ def test_rejects_bad_inputs(ctx, tmp_path):
     c2.close()
     eb2.close()
     eb.close()
+
+
+class _OracleTopoWithMids(object):
+    """oracle.Topology whose candidate-middlepoint sets are injected (the oracle's O(N^2 K E) Python
+    construction takes minutes at 150 nodes; the C++ construction it is replaced by is pinned bit for bit
+    on the golden cases and, below, on a 60-node graph)"""
+
+    def __new__(cls, gf, mids):
+        from oracle import enero_oracle as orc
+
+        class T(orc.Topology):
+            def _middlepoints(self_inner):
+                self_inner.mids = {tuple(int(v) for v in k.split(":")): list(m) for k, m in mids.items()}
+        from enero_b200 import datasets as ds
+        return T(gf, K=100, paths=ds.bfs_lexmin_paths(gf))
+
+
+@pytest.mark.parametrize("spec,full_oracle", [((60, 90, 1021), True), ((150, 230, 1011), False)])
+def test_large_topology_logits_match_oracle(ctx, weights, spec, full_oracle, tmp_path):
+    """the fused decision path against the oracle's actor on 180- and 460-link graphs (K' up to 99 candidate
+    graphs, ~45 000 link-state rows per decision): fp32 logits within 1e-5 of the output scale, candidate
+    counts exact, same greedy action"""
+    from enero_b200 import datasets as ds
+    from enero_b200.topology import Topology
+    from oracle import enero_oracle as orc
+    n, l, seed = spec
+    links, caps = ds.zoo_like(n, l, seed)
+    p = os.path.join(str(tmp_path), "big.graph")
+    ds.write_graph_file(p, n, links, caps)
+    gf = ds.parse_graph_file(p)
+    topo = Topology(gf, K=100)
+    if full_oracle:
+        ot = orc.Topology(gf, K=100, paths=ds.bfs_lexmin_paths(gf))
+        assert topo.middlepoint_dict() == {"%d:%d" % k: v for k, v in ot.mids.items()}
+    else:
+        ot = _OracleTopoWithMids(gf, topo.middlepoint_dict())
+    assert ot.first.tolist() == topo.first.tolist() and ot.second.tolist() == topo.second.tolist()
+    tm = ds.uniform_tm(n, ds.sigma_for_mean_utilisation(gf), 2000)
+    env = orc.Env16(ot)
+    _, s, d = env.reset(tm)
+    for _ in range(3):
+        probs, batch, logits = orc.pred_action_distrib(weights, env, s, d)
+        lg, pr, nK, act = ctx.decide_batch(topo, env.loads[None], np.array([[s, d]], np.int32), np.array([env.tm[s, d]]))
+        k = int(nK[0])
+        assert k == len(logits)
+        scale = max(float(np.abs(logits).max()), 1e-2)
+        assert float(np.abs(lg[0, :k] - logits).max()) <= 1e-5 * scale
+        assert int(act[0]) == int(np.argmax(probs))
+        _, done, _, _, s, d, _, _, _ = env.step(int(np.argmax(probs)))
