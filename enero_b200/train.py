@@ -242,6 +242,23 @@ class TrainingRun:
                 "actor_loss": actor_loss, "critic_loss": critic_loss, "eval_mean_reward": eval_mean,
                 "eval_max_uti": float(np.amax(max_link_uti)), "update_samples_per_s": 8 * n / (t2 - t1)}
 
+    def run(self, first_iteration, n_iterations, episodes_per_launch=20, base_lr=0.0002, base_entropy_beta=ENTROPY_BETA):
+        """the outer schedule of train_Enero_3top.py:28-34 + train script :438-444: the trainer is re-entered every
+        `episodes_per_launch` PPO episodes; at each entry the learning rate decays (x0.96^(i/60), floor 1e-4) when i is
+        a multiple of 60 and the entropy weight drops to a tenth from episode 60 on.  (The reference's restore then
+        overwrites the optimizer's learning rate with the checkpointed one; here the decayed value is
+        the one that is used, as the script's author intended.)"""
+        stats = []
+        for i in range(first_iteration, first_iteration + n_iterations):
+            if (i - first_iteration) % episodes_per_launch == 0:
+                if i % DECAY_STEPS == 0:
+                    self.lr = decayed_learning_rate(i, base_lr)
+                    self.agent.optimizer.learning_rate = np.float32(self.lr)
+                self.entropy_beta = base_entropy_beta / 10 if i >= ENTROPY_STEP else base_entropy_beta
+                self.agent.entropy_beta = float(self.entropy_beta)
+            stats.append(self.ppo_episode())
+        return stats
+
     def save_state(self, path):
         """train script :720-722"""
         with open(path, "wb") as f:

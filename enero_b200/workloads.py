@@ -114,10 +114,7 @@ def run_cfg4(ctx, ppo_episodes=1, process_group=None, specs=((20, 31, 1003), (23
     from .train import TrainingRun
     run = TrainingRun.synthetic(ctx, specs, process_group=process_group)
     run.ppo_episode()                       # warm-up: first-touch allocations of the training buffers
-    stats = []
-    for _ in range(ppo_episodes):
-        stats.append(run.ppo_episode())
-    return stats
+    return run.run(1, ppo_episodes)
 
 
 def _main():
