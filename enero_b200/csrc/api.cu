@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <type_traits>
 #include <vector>
 
@@ -526,14 +527,27 @@ extern "C" int enero_batch_reset(enero_batch* b, const double* tms) {
     CUDA_TRY(cudaMemcpyAsync(loads.data(), b->loads.p, loads.size() * 8, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     b->h_elig.assign((size_t)B * D, 0); b->h_elig_len.assign(B, 0);
-    std::vector<int> sel;
     b->max_len = 0;
+    {
+        // critical-demand selection is host work with Python-dict ordering semantics; the episodes
+        // are independent, so it runs on all host cores
+        const int nthreads = (int)std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), (unsigned)((B + 63) / 64)));
+        auto work = [&](int tid) {
+            std::vector<int> sel;
+            for (int i = tid; i < B; i += nthreads) {
+                topo_critical_demands(*t, loads.data() + (size_t)i * E, tms + (size_t)i * NN, nullptr, 0, b->pct, sel);
+                std::copy(sel.begin(), sel.end(), b->h_elig.begin() + (size_t)i * D);
+                b->h_elig_len[i] = (int)sel.size();
+            }
+        };
+        std::vector<std::thread> pool;
+        for (int tid = 1; tid < nthreads; ++tid) pool.emplace_back(work, tid);
+        work(0);
+        for (auto& th : pool) th.join();
+    }
     for (int i = 0; i < B; ++i) {
-        topo_critical_demands(*t, loads.data() + (size_t)i * E, tms + (size_t)i * NN, nullptr, 0, b->pct, sel);
-        if (sel.empty()) return fail(ENERO_ERR_INVALID, "enero_batch_reset: traffic matrix yields no eligible demand");
-        std::copy(sel.begin(), sel.end(), b->h_elig.begin() + (size_t)i * D);
-        b->h_elig_len[i] = (int)sel.size();
-        b->max_len = std::max(b->max_len, (int)sel.size());
+        if (b->h_elig_len[i] == 0) return fail(ENERO_ERR_INVALID, "enero_batch_reset: traffic matrix yields no eligible demand");
+        b->max_len = std::max(b->max_len, b->h_elig_len[i]);
     }
     CUDA_TRY(cudaMemcpyAsync(b->elig.p, b->h_elig.data(), b->h_elig.size() * 4, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(b->elig_len.p, b->h_elig_len.data(), (size_t)B * 4, cudaMemcpyHostToDevice, st));
