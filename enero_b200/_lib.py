@@ -75,6 +75,8 @@ SIGNATURES = {
     "enero_batch_get_best": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "enero_batch_local_search": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp]),
     "enero_batch_get_ls_eligible": (C.c_int, [_vp, _vp, _vp, C.c_int]),
+    "enero_batch_get_ls_state": (C.c_int, [_vp, _vp, _vp]),
+    "enero_batch_ls_route_add": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_double, _vp, _vp, _vp]),
     "enero_ppo_grad_buffer": (_vp, [_vp]),
     "enero_ppo_zero_grad": (C.c_int, [_vp]),
     "enero_ppo_accumulate": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_float, C.c_float,

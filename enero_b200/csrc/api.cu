@@ -756,7 +756,7 @@ extern "C" int enero_batch_local_search(enero_batch* b, int mode, const int32_t*
                                         int max_moves, double* start, double* final_val, int32_t* n_moves,
                                         int32_t* moves, double* move_val) {
     if (!b) return fail(ENERO_ERR_INVALID, "enero_batch_local_search: null batch");
-    if (mode < 0 || mode > 1 || max_moves < 1) return fail(ENERO_ERR_INVALID, "enero_batch_local_search: bad mode / max_moves");
+    if (mode < 0 || mode > 1 || max_moves < 0) return fail(ENERO_ERR_INVALID, "enero_batch_local_search: bad mode / max_moves");
     enero_ctx* c = b->c; enero_topo* t = b->t;
     CUDA_TRY(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
@@ -807,13 +807,17 @@ extern "C" int enero_batch_local_search(enero_batch* b, int mode, const int32_t*
         }
     }
     TRY(b->ls_elig.ensure((size_t)B * cap * 4)); TRY(b->ls_elig_len.ensure((size_t)B * 4));
-    TRY(b->ls_moves.ensure((size_t)B * max_moves * 12)); TRY(b->ls_move_val.ensure((size_t)B * max_moves * 8));
+    TRY(b->ls_moves.ensure((size_t)B * std::max(1, max_moves) * 12)); TRY(b->ls_move_val.ensure((size_t)B * std::max(1, max_moves) * 8));
     CUDA_TRY(cudaMemcpyAsync(b->ls_elig.p, b->h_ls_elig.data(), b->h_ls_elig.size() * 4, cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(b->ls_elig_len.p, b->h_ls_elig_len.data(), (size_t)B * 4, cudaMemcpyHostToDevice, st));
     if (start) CUDA_TRY(cudaMemcpyAsync(start, b->ls_val.p, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
     LsView lv{B, cap, max_moves, b->tm.as<double>(), b->ls_loads.as<double>(), b->ls_mid.as<int>(), b->ls_elig.as<int>(),
               b->ls_elig_len.as<int>(), b->ls_val.as<double>(), b->ls_nmoves.as<int>(), b->ls_moves.as<int>(), b->ls_move_val.as<double>()};
     const size_t smem = ls_smem_bytes(E);
+    if (max_moves == 0) {
+        // reset only (environment15.py:485-544): loads, start value and demand list are in place, no move is made
+        CUDA_TRY(cudaMemsetAsync(b->ls_nmoves.p, 0, (size_t)B * 4, st));
+    } else {
     if (smem > 200 * 1024) return fail(ENERO_ERR_INVALID, "enero_batch_local_search: topology too large for the shared-memory LS kernel");
     // few episodes: split each episode's demand list over a thread-block cluster so the whole GPU works
     int CL = 1;
@@ -831,6 +835,7 @@ extern "C" int enero_batch_local_search(enero_batch* b, int mode, const int32_t*
     } else {
         if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_local_search<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_local_search<false><<<B, LS_TPB, smem, st>>>(tv, lv, 1); LAUNCH_CHECK(c);
+    }
     }
     if (final_val) CUDA_TRY(cudaMemcpyAsync(final_val, b->ls_val.p, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
     if (n_moves) CUDA_TRY(cudaMemcpyAsync(n_moves, b->ls_nmoves.p, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
@@ -856,3 +861,30 @@ extern "C" int enero_batch_get_ls_eligible(enero_batch* b, int32_t* elig, int32_
 }
 
 #include "train_api.cuh"
+
+// ---- per-operation Local-Search API (callers that drive the hill climbing move by move) -------------------
+extern "C" int enero_batch_ls_route_add(enero_batch* b, int episode, int src, int dst, double value, double* loads_host,
+                                        double* max_uti, int32_t* max_edge) {
+    if (!b || episode < 0 || episode >= b->B) return fail(ENERO_ERR_INVALID, "enero_batch_ls_route_add: bad episode");
+    enero_topo* t = b->t; enero_ctx* c = b->c;
+    if (src < 0 || dst < 0 || src >= t->N || dst >= t->N || src == dst) return fail(ENERO_ERR_INVALID, "enero_batch_ls_route_add: bad path end points");
+    CUDA_TRY(cudaSetDevice(c->device));
+    double* loads = b->ls_loads.as<double>() + (size_t)episode * t->E;
+    k_ls_route_add<<<1, 32, 0, c->stream>>>(view_of(t), loads, src, dst, value, b->ls_val.as<double>() + episode, b->ls_max_edge.as<int>() + episode);
+    LAUNCH_CHECK(c);
+    if (loads_host) CUDA_TRY(cudaMemcpyAsync(loads_host, loads, (size_t)t->E * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (max_uti) CUDA_TRY(cudaMemcpyAsync(max_uti, b->ls_val.as<double>() + episode, 8, cudaMemcpyDeviceToHost, c->stream));
+    if (max_edge) CUDA_TRY(cudaMemcpyAsync(max_edge, b->ls_max_edge.as<int>() + episode, 4, cudaMemcpyDeviceToHost, c->stream));
+    if (loads_host || max_uti || max_edge) CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return ENERO_OK;
+}
+
+extern "C" int enero_batch_get_ls_state(enero_batch* b, double* loads, int32_t* max_edge) {
+    if (!b) return fail(ENERO_ERR_INVALID, "enero_batch_get_ls_state: null batch");
+    enero_ctx* c = b->c;
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (loads) CUDA_TRY(cudaMemcpyAsync(loads, b->ls_loads.p, (size_t)b->B * b->t->E * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (max_edge) CUDA_TRY(cudaMemcpyAsync(max_edge, b->ls_max_edge.p, (size_t)b->B * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return ENERO_OK;
+}

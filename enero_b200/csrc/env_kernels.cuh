@@ -246,6 +246,17 @@ k_env_step(TopoView t, EpisodeView ep, const int* __restrict__ action) {
     }
 }
 
+// one allocate_to_destination_sp / decrease_links_utilization_sp (environment15.py:546-563, 150-165) on the
+// Local-Search loads of one episode, followed by the max-utilisation scan of step_hill_sp (:389-399)
+__global__ void k_ls_route_add(TopoView t, double* __restrict__ loads, int src, int dst, double v,
+                               double* __restrict__ max_uti, int* __restrict__ max_edge) {
+    const int lane = threadIdx.x & 31;
+    warp_route_add(t, loads, src, dst, v, lane);
+    double nu; int ne;
+    warp_max_uti(loads, t.cap, t.E, lane, nu, ne);
+    if (lane == 0) { *max_uti = nu; *max_edge = ne; }
+}
+
 // ---- Local Search (kernel 7) -----------------------------------------------------------------
 // One CTA per episode runs the whole hill climbing of play_DRL_GNN_sp_hill_climbing_games
 // (script_eval_on_single_topology.py:482-509) on device: every (demand, middlepoint) move of

@@ -143,6 +143,27 @@ class EpisodeBatch:
                                                       _lib.ptr(moves), _lib.ptr(vals)))
         return {"start": start, "final": final, "n_moves": n_moves, "moves": moves, "move_val": vals}
 
+    def ls_route_add(self, episode, src, dst, value):
+        """allocate_to_destination_sp (value > 0) / decrease_links_utilization_sp (value < 0) on the Local-Search
+        loads of one episode -> (loads fp64[E], max utilisation, its edge id or -1)."""
+        loads = np.zeros(self.topo.E)
+        mx = np.zeros(1)
+        me = np.zeros(1, dtype=np.int32)
+        _lib.check(self._lib.enero_batch_ls_route_add(self._h, int(episode), int(src), int(dst), float(value),
+                                                      _lib.ptr(loads), _lib.ptr(mx), _lib.ptr(me)))
+        return loads, float(mx[0]), int(me[0])
+
+    def ls_loads(self):
+        """link loads of the Local-Search state, fp64[B,E]"""
+        out = np.zeros((self.B, self.topo.E))
+        _lib.check(self._lib.enero_batch_get_ls_state(self._h, _lib.ptr(out), None))
+        return out
+
+    def ls_max_edge(self):
+        out = np.zeros(self.B, dtype=np.int32)
+        _lib.check(self._lib.enero_batch_get_ls_state(self._h, None, _lib.ptr(out)))
+        return out
+
     def ls_eligible(self):
         cap = max(self.Dmax, self.topo.N * (self.topo.N - 1))
         elig = np.zeros((self.B, cap, 2), dtype=np.int32)

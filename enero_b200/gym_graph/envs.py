@@ -29,6 +29,14 @@ class _Graph:
     def nodes(self):
         return list(range(self._t.N))
 
+    # `for i in env.graph: for j in env.graph[i]` walks the links in edge-id order
+    # (environment16.py:557-569, script_eval_on_single_topology.py:334-339)
+    def __iter__(self):
+        return iter(self._t.graph_file.node_order)
+
+    def __getitem__(self, i):
+        return list(self._t.graph_file.adj[i])
+
 
 class _DatasetAPI:
     def __init__(self, topo, gf):
@@ -191,17 +199,15 @@ class Env15(_EnvBase):
         return out
 
     def reset_DRL_hill_sp(self, tm_id, best_routing, list_of_demands_to_change):
-        """environment15.py:485-544 -> -maxUti of the restored DRL routing.  The hill climbing
-        itself (script_eval_on_single_topology.py:482-509) runs on device: see local_search()."""
+        """environment15.py:485-544 -> -maxUti of the restored DRL routing.  The hill climbing itself
+        (script_eval_on_single_topology.py:482-509) runs on device in one launch: local_search(); callers that
+        drive it move by move use allocate_to_destination_sp / decrease_links_utilization_sp / step_hill_sp."""
         tm = self._load_tm(tm_id)
         self.sp_middlepoints = dict(best_routing) if best_routing is not None else dict()
         self.list_of_demands_to_change = list_of_demands_to_change
         self._upload_tm(tm)
         self._mode, self._routing = 0, [self._routing_list(best_routing)]
-        self._ls = self._batch.local_search(self._routing, mode=0)
-        elig, n = self._batch.ls_eligible()
-        self.list_eligible_demands = [(int(s), int(d), tm[s, d]) for s, d in elig[0, :n[0]]]
-        return -self._ls["start"][0]
+        return self._reset_only(tm, True)
 
     def reset_hill_sp(self, tm_id):
         """environment15.py:438-469 -> -maxUti on plain shortest paths; all demands eligible."""
@@ -209,9 +215,42 @@ class Env15(_EnvBase):
         self.sp_middlepoints = dict()
         self._upload_tm(tm)
         self._mode, self._routing = 1, None
-        self._ls = self._batch.local_search(None, mode=1)
-        self.list_eligible_demands = [(s, d, tm[s, d]) for s in range(self.numNodes) for d in range(self.numNodes) if s != d]
-        return -self._ls["start"][0]
+        return self._reset_only(tm, False)
+
+    def _reset_only(self, tm, critical):
+        r = self._batch.local_search(self._routing, mode=self._mode, max_moves=0, want_moves=False)
+        if critical:
+            elig, n = self._batch.ls_eligible()
+            self.list_eligible_demands = [(int(s), int(d), tm[s, d]) for s, d in elig[0, :n[0]]]
+        else:
+            self.list_eligible_demands = [(s, d, tm[s, d]) for s in range(self.numNodes) for d in range(self.numNodes) if s != d]
+        self.edge_state[:, 0] = self._batch.ls_loads()[0]
+        e = int(self._batch.ls_max_edge()[0])
+        self.edgeMaxUti = self._edge_tuple(e, r["start"][0])
+        self._ls = None
+        return -r["start"][0]
+
+    # ---- per-operation methods (environment15.py:546-563, 150-165, 378-404): each one is a device call on the
+    # episode's Local-Search loads, mirrored into edge_state[:, 0] -------------------------------------------
+    def _route_add(self, src, dst, value):
+        loads, mx, me = self._batch.ls_route_add(0, int(src), int(dst), float(value))
+        self.edge_state[:, 0] = loads
+        return mx, me
+
+    def allocate_to_destination_sp(self, src, dst, init_source, final_destination):
+        self._route_add(src, dst, self.TM[init_source][final_destination])
+
+    def decrease_links_utilization_sp(self, src, dst, init_source, final_destination):
+        self._route_add(src, dst, -self.TM[init_source][final_destination])
+
+    def step_hill_sp(self, action, source, destination):
+        mid = list(self.src_dst_k_middlepoints["%d:%d" % (source, destination)])[action]
+        mx, me = self._route_add(source, mid, self.TM[source][destination])
+        if mid != destination:
+            mx, me = self._route_add(mid, destination, self.TM[source][destination])
+            self.sp_middlepoints["%d:%d" % (source, destination)] = mid
+        self.edgeMaxUti = self._edge_tuple(int(me), mx)
+        return -self.edgeMaxUti[2]
 
     def _upload_tm(self, tm):
         # Env16-style reset puts the TM on the device; its demand list is not used by the LS
@@ -220,6 +259,8 @@ class Env15(_EnvBase):
     def local_search(self):
         """-> (final maxUti, [(action, s, d, maxUti after the move), ...]) of the hill climbing
         started by the last reset_*; updates sp_middlepoints / edgeMaxUti like the reference loop."""
+        if self._ls is None:
+            self._ls = self._batch.local_search(self._routing, mode=self._mode)
         ls = self._ls
         n = int(ls["n_moves"][0])
         moves = []

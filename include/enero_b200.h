@@ -164,11 +164,22 @@ int enero_batch_get_best(enero_batch* b, double* best, double* ospf, int32_t* ro
  * loop of play_DRL_GNN_sp_hill_climbing_games (script :473-509) to convergence on device.
  * mode 0 = critical demands of the routing (explore_neighbourhood_DRL_sp), 1 = all N(N-1)
  * demands from plain shortest paths (play_sp_hill_climbing_games, script :437-471).
+ * max_moves = 0 performs the reset only.
  * Outputs (nullable): start fp64[B] (max uti at reset), final fp64[B], n_moves int32[B],
  * moves int32[B,max_moves,3] = (action,s,d), move_val fp64[B,max_moves]. */
 int enero_batch_local_search(enero_batch* b, int mode, const int32_t* routing, const int32_t* n_routing,
                              int max_moves, double* start, double* final_val, int32_t* n_moves,
                              int32_t* moves, double* move_val);
+/* Per-operation view of the Local-Search loads of one episode, for callers that drive the hill climbing
+ * move by move through the Env15 methods (script_eval_on_single_topology.py:317-435 does): add `value`
+ * (+TM[s][d] = allocate_to_destination_sp, environment15.py:546-563; -TM[s][d] =
+ * decrease_links_utilization_sp, :150-165) on every link of the shortest path src->dst, then rescan the
+ * maximum utilisation (step_hill_sp, :389-399).  enero_batch_local_search with max_moves = 0 is the reset
+ * (reset_DRL_hill_sp / reset_hill_sp) that puts the loads in place.  Outputs nullable: loads fp64[E]. */
+int enero_batch_ls_route_add(enero_batch* b, int episode, int src, int dst, double value, double* loads_host,
+                             double* max_uti, int32_t* max_edge);
+/* Local-Search state: loads fp64[B,E] and the edge id of the maximum utilisation int32[B] (nullable) */
+int enero_batch_get_ls_state(enero_batch* b, double* loads, int32_t* max_edge);
 /* critical demands chosen by the last enero_batch_local_search reset: elig int32[B,Dcap,2] */
 int enero_batch_get_ls_eligible(enero_batch* b, int32_t* elig, int32_t* elig_len, int cap);
 

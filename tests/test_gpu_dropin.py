@@ -116,3 +116,81 @@ def test_reference_style_agent_through_myModel_call(actor, tmp_path):
         assert env.edge_state[:, 0].tolist() == stp["loads_after"]
         if done:
             break
+
+
+def _climb_move_by_move(env, current):
+    """The hill-climbing loop a caller writes against the Env15 method surface (the structure of
+    script_eval_on_single_topology.py:317-351,395-435,482-505, restated): every candidate move is evaluated by
+    de-allocating the demand, allocating it over the candidate middlepoint, scanning edge_state, and undoing it."""
+    def demand_routes(s, d):
+        key = "%d:%d" % (s, d)
+        if key in env.sp_middlepoints:
+            m = env.sp_middlepoints[key]
+            return [(s, m), (m, d)]
+        return [(s, d)]
+
+    def max_utilisation():
+        best, pos = -1000000, 0
+        for i in env.graph:
+            for j in env.graph[i]:
+                u = env.edge_state[pos][0] / env.links_bw[i][j]
+                if u > best:
+                    best = u
+                pos += 1
+        return best
+
+    moves = []
+    while True:
+        next_val, next_state = -1000000, None
+        for (s, d, _) in env.list_eligible_demands:
+            mids = env.src_dst_k_middlepoints["%d:%d" % (s, d)]
+            for action, m in enumerate(mids):
+                cur = demand_routes(s, d)
+                for a, b in cur:
+                    env.decrease_links_utilization_sp(a, b, s, d)
+                cand = [(s, m)] if m == d else [(s, m), (m, d)]
+                for a, b in cand:
+                    env.allocate_to_destination_sp(a, b, s, d)
+                value = -max_utilisation()
+                for a, b in cand:
+                    env.decrease_links_utilization_sp(a, b, s, d)
+                for a, b in cur:
+                    env.allocate_to_destination_sp(a, b, s, d)
+                if value > next_val:
+                    next_val, next_state = value, (action, s, d)
+        if next_val <= current or abs(next_val - current) < 1e-4:
+            break
+        action, s, d = next_state
+        for a, b in demand_routes(s, d):
+            env.decrease_links_utilization_sp(a, b, s, d)
+        env.sp_middlepoints.pop("%d:%d" % (s, d), None)
+        current = env.step_hill_sp(action, s, d)
+        moves.append([action, s, d, -current])
+    return -current, moves
+
+
+@pytest.mark.parametrize("name", ["tri9", "tiny12"])
+def test_env15_per_operation_api(name, tmp_path):
+    """GraphEnv-v15 driven move by move through allocate_to_destination_sp / decrease_links_utilization_sp /
+    step_hill_sp / edge_state / graph / links_bw (Env (LS) row) reproduces the move sequence and the
+    final value the reference's own loop recorded, and agrees with the one-launch device Local Search"""
+    from enero_b200 import gym_graph
+    case = load_case(name)
+    folder = str(tmp_path)
+    topo_name = _dataset(case, folder)
+    env = gym_graph.make('GraphEnv-v15')
+    env.seed(9)
+    env.generate_environment(folder, topo_name, 100, 100, 0.15)
+    for ep in case["episodes"]:
+        routing = {"%d:%d" % (s, d): m for s, d, m in ep["best_routing"]}
+        cur = env.reset_DRL_hill_sp(ep["tm_id"], dict(routing), None)
+        assert cur == ep["ls"]["reset_val"]
+        assert [[s, d, bw] for s, d, bw in env.list_eligible_demands] == ep["ls"]["elig"]
+        assert env.edge_state[:, 0].tolist() == ep["ls"]["loads0"]
+        final, moves = _climb_move_by_move(env, cur)
+        assert final == ep["ls"]["final"]
+        assert moves == ep["ls"]["moves"]
+        # the fused device Local Search from the same reset gives the same answer
+        env.reset_DRL_hill_sp(ep["tm_id"], dict(routing), None)
+        f2, m2 = env.local_search()
+        assert f2 == final and [[a, s, d, v] for a, s, d, v in m2] == moves
