@@ -343,6 +343,7 @@ def run_ours(args, rank, world, local_rank):
     # ---- end to end through the public API with host buffers: whole greedy episodes
     e2e = None
     cpu = None
+    extras = None
     if rank == 0 or world > 1:
         Be = min(B, args.e2e_batch)
         tms_e = np.ascontiguousarray(tms[:Be])
@@ -370,6 +371,16 @@ def run_ours(args, rank, world, local_rank):
                "h2d_bytes_per_step": int(tms_e.nbytes / steps_e + Be * eb2.Dmax * 4 / steps_e),
                "d2h_bytes_per_step": int((Be * E * 8 + Be * eb2.Dmax * 4 + Be * 28) / steps_e),
                "path": "EpisodeBatch.reset(host TMs) + run_greedy() + best(): %d episodes x %.0f decisions, wall clock incl. copies" % (Be, steps_e)}
+        # second stage on the same batch (Local Search reported separately): hill climbing to
+        # convergence from the DRL routing, on device; informative extras, not part of `value`
+        t0 = time.perf_counter()
+        ls = eb2.local_search(None, mode=0, want_moves=False)
+        ctx.sync()
+        t_ls = time.perf_counter() - t0
+        extras = {"local_search": {"tms_per_s": Be / t_ls, "ms": 1000.0 * t_ls, "episodes": Be, "moves_applied": int(ls["n_moves"].sum()),
+                                   "mean_max_uti_drl": float(best.mean()), "mean_max_uti_enero": float(ls["final"].mean()),
+                                   "mean_max_uti_ospf": float(ospf.mean())},
+                  "full_enero_tms_per_s": Be / (t_best + t_ls)}
         eb2.close()
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = 1
@@ -386,7 +397,7 @@ def run_ours(args, rank, world, local_rank):
                        "l2": "inputs larger than L2 (%.0f MB of link-state rows per step)" % (B * topo.Kmax * E * 320 / 1e6),
                        "parallelism": "episodes sharded x%d, no collective" % world},
             "clocks": clk.summary(), "gpu_launches": int(launches), "roofline": roofline,
-            "e2e": e2e, "cpu_baseline": cpu,
+            "e2e": e2e, "cpu_baseline": cpu, "extras": extras,
         }
         print(json.dumps(line), flush=True)
     eb.close()
