@@ -321,14 +321,14 @@ def run_ours(args, rank, world, local_rank):
     # measured DRAM traffic of one k_mp_iter launch, from the committed ncu --set full capture (taken at
     # 1024 episodes per GPU on this workload; scaled linearly with the batch)
     traffic, traffic_src = None, None
-    prof = os.path.join(ROOT, "profiles", "r01_v6_k_mp_iter_ncu_full.csv")
+    prof = os.path.join(ROOT, "profiles", "r01_v7_k_mp_iter_ncu_full.csv")
     if os.path.isfile(prof):
         import csv
         rows = {r[0]: r for r in csv.reader(open(prof)) if r}
         try:
             mb = float(rows["dram__bytes_read.sum"][2]) + float(rows["dram__bytes_write.sum"][2])
             traffic = mb * 1e6 * B / 1024.0
-            traffic_src = "profiles/r01_v6_k_mp_iter_ncu_full.csv (dram__bytes_read.sum + dram__bytes_write.sum, launch 1, x B/1024)"
+            traffic_src = "profiles/r01_v7_k_mp_iter_ncu_full.csv (dram__bytes_read.sum + dram__bytes_write.sum, launch 1, x B/1024)"
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
