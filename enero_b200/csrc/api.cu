@@ -299,6 +299,7 @@ static int ensure_rows(enero_ctx* c, int64_t rows) {
 extern "C" int enero_gnn_forward(enero_ctx* c, int which, const float* link_state, const int32_t* graph_id,
                                  const int32_t* first, const int32_t* second, int64_t n, int64_t p, int G,
                                  int T, float* out, int ptr_kind) {
+    ENERO_TRACE("enero_gnn_forward");
     if (!c || !link_state || !out || (p > 0 && (!first || !second))) return fail(ENERO_ERR_INVALID, "enero_gnn_forward: null argument");
     if (which < 0 || which > 1 || n < 1 || p < 0 || G < 1 || T < 1 || n > 0x7fffffff || p > 0x7fffffff)
         return fail(ENERO_ERR_INVALID, "enero_gnn_forward: bad sizes");
@@ -411,6 +412,7 @@ static int value_dev(enero_ctx* c, enero_topo* t, int B, const double* loads, fl
 extern "C" int enero_decide_batch(enero_ctx* c, enero_topo* t, int B, const double* loads, const int32_t* sd,
                                   const double* bw, float* logits, float* probs, int32_t* nK, int32_t* action,
                                   int ptr_kind) {
+    ENERO_TRACE("enero_decide_batch");
     if (!c || !t || !loads || !sd || !bw || B < 1) return fail(ENERO_ERR_INVALID, "enero_decide_batch: bad argument");
     if (t->dev_id != c->device) return fail(ENERO_ERR_STATE, "enero_decide_batch: topology not uploaded to this device");
     CUDA_TRY(cudaSetDevice(c->device));
@@ -439,6 +441,7 @@ extern "C" int enero_decide_batch(enero_ctx* c, enero_topo* t, int B, const doub
 }
 
 extern "C" int enero_value_batch(enero_ctx* c, enero_topo* t, int B, const double* loads, float* values, int ptr_kind) {
+    ENERO_TRACE("enero_value_batch");
     if (!c || !t || !loads || !values || B < 1) return fail(ENERO_ERR_INVALID, "enero_value_batch: bad argument");
     if (t->dev_id != c->device) return fail(ENERO_ERR_STATE, "enero_value_batch: topology not uploaded to this device");
     CUDA_TRY(cudaSetDevice(c->device));
@@ -513,6 +516,7 @@ extern "C" int enero_batch_destroy(enero_batch* b) {
 extern "C" int enero_batch_dmax(enero_batch* b) { return b ? b->Dmax : -1; }
 
 extern "C" int enero_batch_reset(enero_batch* b, const double* tms) {
+    ENERO_TRACE("enero_batch_reset");
     if (!b || !tms) return fail(ENERO_ERR_INVALID, "enero_batch_reset: null argument");
     enero_ctx* c = b->c; enero_topo* t = b->t;
     CUDA_TRY(cudaSetDevice(c->device));
@@ -591,6 +595,7 @@ extern "C" int enero_batch_restore(enero_batch* b) {
 }
 
 extern "C" int enero_batch_policy(enero_batch* b, float* probs_host, int32_t* nK_host) {
+    ENERO_TRACE("enero_batch_policy");
     if (!b) return fail(ENERO_ERR_INVALID, "enero_batch_policy: null batch");
     if (!b->reset_done) return fail(ENERO_ERR_STATE, "enero_batch_policy: reset first");
     enero_ctx* c = b->c;
@@ -624,6 +629,7 @@ static int step_dev(enero_batch* b) {
 }
 
 extern "C" int enero_batch_step(enero_batch* b, const int32_t* actions, double* reward, uint8_t* done) {
+    ENERO_TRACE("enero_batch_step");
     if (!b) return fail(ENERO_ERR_INVALID, "enero_batch_step: null batch");
     if (!b->reset_done) return fail(ENERO_ERR_STATE, "enero_batch_step: reset first");
     enero_ctx* c = b->c;
@@ -652,6 +658,7 @@ extern "C" int enero_batch_step(enero_batch* b, const int32_t* actions, double* 
 }
 
 extern "C" int enero_batch_run_greedy(enero_batch* b) {
+    ENERO_TRACE("enero_batch_run_greedy");
     if (!b) return fail(ENERO_ERR_INVALID, "enero_batch_run_greedy: null batch");
     if (!b->reset_done) return fail(ENERO_ERR_STATE, "enero_batch_run_greedy: reset first");
     enero_ctx* c = b->c;
@@ -755,6 +762,7 @@ extern "C" int enero_batch_get_best(enero_batch* b, double* best, double* ospf, 
 extern "C" int enero_batch_local_search(enero_batch* b, int mode, const int32_t* routing, const int32_t* n_routing,
                                         int max_moves, double* start, double* final_val, int32_t* n_moves,
                                         int32_t* moves, double* move_val) {
+    ENERO_TRACE("enero_batch_local_search");
     if (!b) return fail(ENERO_ERR_INVALID, "enero_batch_local_search: null batch");
     if (mode < 0 || mode > 1 || max_moves < 0) return fail(ENERO_ERR_INVALID, "enero_batch_local_search: bad mode / max_moves");
     enero_ctx* c = b->c; enero_topo* t = b->t;

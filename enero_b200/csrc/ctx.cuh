@@ -1,6 +1,7 @@
 // Shared host-side definitions of the CUDA translation units (api.cu, train.cu).
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <string>
 #include <utility>
@@ -67,6 +68,15 @@ struct enero_ctx {
     DevBuf t_agg, t_G, t_dB, t_dA, t_B, t_dagg, t_dhpart, t_dh[2], t_V, t_dlogit, t_partials;
     DevBuf t_loads, t_sd, t_bw, t_action, t_oldp, t_adv, t_ret, t_logits, t_probs, t_nK, t_loss, t_ent, t_norm;
 };
+
+// NVTX range over one C-ABI call (header-only NVTX v3: shows up in nsys / ncu timelines, free otherwise)
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
+#define ENERO_TRACE(name) NvtxRange _nvtx_range_(name)
 
 #define LAUNCH_CHECK(ctx)                                                     \
     do { (ctx)->launches++; CUDA_TRY(cudaGetLastError()); } while (0)

@@ -101,6 +101,7 @@ extern "C" int enero_ppo_accumulate(enero_ctx* c, enero_topo* t, int n, const do
                                     const double* bw, const int32_t* action, const float* old_prob,
                                     const float* advantage, const float* ret, float inv_m, float entropy_beta,
                                     float clipping_val, int ptr_kind) {
+    ENERO_TRACE("enero_ppo_accumulate");
     if (!c || !t || !loads || !sd || !bw || !action || !old_prob || !advantage || !ret || n < 1)
         return fail(ENERO_ERR_INVALID, "enero_ppo_accumulate: bad argument");
     TRY(enero_topo_upload(c, t));
@@ -180,6 +181,7 @@ extern "C" int enero_ppo_accumulate(enero_ctx* c, enero_topo* t, int n, const do
 
 extern "C" int enero_ppo_apply(enero_ctx* c, float lr, float beta1, float beta2, float eps, float clip_norm,
                                int64_t step, float* grad_norm_host) {
+    ENERO_TRACE("enero_ppo_apply");
     if (!c || step < 1 || !(clip_norm > 0)) return fail(ENERO_ERR_INVALID, "enero_ppo_apply: bad argument");
     CUDA_TRY(cudaSetDevice(c->device));
     // Keras Adam._prepare_local in fp32: lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t)
@@ -226,6 +228,7 @@ extern "C" int enero_adam_slots_download(enero_ctx* c, int which, float* m, floa
 
 extern "C" int enero_gae(enero_ctx* c, int n, const float* values, const uint8_t* masks, const double* rewards,
                          double gamma, double lmbda, double* returns, double* advantages) {
+    ENERO_TRACE("enero_gae");
     if (!c || n < 1 || !values || !masks || !rewards || !returns || !advantages) return fail(ENERO_ERR_INVALID, "enero_gae: bad argument");
     CUDA_TRY(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
