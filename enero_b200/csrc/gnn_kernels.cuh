@@ -401,7 +401,7 @@ __device__ __forceinline__ void mp_phase_A(const W sw, float* const (&myh)[MP_R]
 // TMA = true: the slot of row i of a warp's tile is wsh + 20*i, i.e. the slots ARE the tile's rows in
 // global order, so the tile's link states arrive with one bulk asynchronous copy (cp.async.bulk, 1-D TMA,
 // issued by lane 0, awaited on the warp's own mbarrier) and the new link states leave with one bulk
-// store; A' goes through the B/z slots and a warp-cooperative coalesced store.  No 80-byte-stride
+// store; A' goes through the B/z slots and leaves with a second bulk store.  No 80-byte-stride
 // LDG/STG (~20 L1 wavefronts each) except the operand gathers, whose rows were prefetched into L1.
 // TMA = false: per-thread LDG/STG for everything.
 constexpr int MP_WROWS = 32 * MP_R;          // rows per warp tile
@@ -524,11 +524,10 @@ k_mp_iter(const IDX idx, const float* __restrict__ wflat, const float* __restric
         if (TMA) {
             fence_proxy_async();                             // slot writes visible to the bulk store
             __syncwarp();
-            if (lane == 0) { bulk_s2g(h_out + row0 * H, wsh, (uint32_t)nrows * H * 4); bulk_commit(); }
-            if (!LAST) {
-                const float4* src = reinterpret_cast<const float4*>(wsb);
-                float4* dst = reinterpret_cast<float4*>(A_out + row0 * H);
-                for (int i = lane; i < nrows * (H / 4); i += 32) dst[i] = src[i];
+            if (lane == 0) {
+                bulk_s2g(h_out + row0 * H, wsh, (uint32_t)nrows * H * 4);
+                if (!LAST) bulk_s2g(A_out + row0 * H, wsb, (uint32_t)nrows * H * 4);
+                bulk_commit();
             }
             __syncwarp();
         }
