@@ -3,13 +3,14 @@
 // nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o ubench_lds ubench_lds.cu
 #include <cstdio>
 #include <cuda_runtime.h>
-template <int W, bool BCAST>
+// BCAST: 1 = one address per warp, 2 = two addresses (even / odd lanes), 0 = one address per lane
+template <int W, int BCAST>
 __global__ void __launch_bounds__(128) k(float* out, int iters, long long* cyc) {
     __shared__ __align__(16) float sm[128 * 20 + 4096];
     for (int i = threadIdx.x; i < 128 * 20 + 4096; i += 128) sm[i] = i * 1e-6f;
     __syncthreads();
     float acc = 0.f;
-    const int base = BCAST ? 0 : threadIdx.x * (W / 4);        // per-lane: consecutive W-bit words (conflict-free)
+    const int base = BCAST == 1 ? 0 : (BCAST == 2 ? (threadIdx.x & 1) * 800 : threadIdx.x * (W / 4));   // per-lane: consecutive W-bit words (conflict-free)
     const long long t0 = clock64();
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
@@ -25,7 +26,7 @@ __global__ void __launch_bounds__(128) k(float* out, int iters, long long* cyc) 
     out[blockIdx.x * 128 + threadIdx.x] = acc;
     if (threadIdx.x == 0 && blockIdx.x == 0) *cyc = t1 - t0;
 }
-template <int W, bool B> void run(const char* name, int sms, int cps) {
+template <int W, int B> void run(const char* name, int sms, int cps) {
     float* out; long long* cyc; cudaMalloc(&out, sizeof(float) * sms * cps * 128); cudaMalloc(&cyc, 8);
     const int iters = 2000;
     k<W, B><<<sms * cps, 128>>>(out, iters, cyc); cudaDeviceSynchronize();
@@ -38,12 +39,14 @@ template <int W, bool B> void run(const char* name, int sms, int cps) {
 int main() {
     cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
     for (int cps = 1; cps <= 3; cps += 2) {
-        run<4, true>("LDS.32  broadcast", p.multiProcessorCount, cps);
-        run<8, true>("LDS.64  broadcast", p.multiProcessorCount, cps);
-        run<16, true>("LDS.128 broadcast", p.multiProcessorCount, cps);
-        run<4, false>("LDS.32  per-lane", p.multiProcessorCount, cps);
-        run<8, false>("LDS.64  per-lane", p.multiProcessorCount, cps);
-        run<16, false>("LDS.128 per-lane", p.multiProcessorCount, cps);
+        run<4, 1>("LDS.32  broadcast", p.multiProcessorCount, cps);
+        run<8, 1>("LDS.64  broadcast", p.multiProcessorCount, cps);
+        run<16, 1>("LDS.128 broadcast", p.multiProcessorCount, cps);
+        run<8, 2>("LDS.64  two addresses", p.multiProcessorCount, cps);
+        run<16, 2>("LDS.128 two addresses", p.multiProcessorCount, cps);
+        run<4, 0>("LDS.32  per-lane", p.multiProcessorCount, cps);
+        run<8, 0>("LDS.64  per-lane", p.multiProcessorCount, cps);
+        run<16, 0>("LDS.128 per-lane", p.multiProcessorCount, cps);
     }
     return 0;
 }
