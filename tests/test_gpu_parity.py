@@ -307,3 +307,39 @@ def test_greedy_actions_many_tms(ctx, weights, name, n_tms, tmp_path_factory):
         ofinal, _ = orc.local_search(e15, cur)
         assert ls["final"][i] == ofinal
     eb.close()
+
+
+def test_tma_staged_tile_kernel_is_bit_identical(tmp_path):
+    """the opt-in k_mp_tile variant (ENERO_MP_TPB) shares the FMA phases with k_mp_iter:
+    same logits bit for bit, on a topology with the Q1 offset quirk (zoo30: max(second)+1 < E)"""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, json, os, tempfile; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import numpy as np\n"
+        "from conftest import case_graph_file, golden_weights, load_case\n"
+        "from enero_b200.runtime import Context\n"
+        "from enero_b200.topology import Topology\n"
+        "from enero_b200.engine import EpisodeBatch\n"
+        "from oracle import enero_oracle as orc\n"
+        "w = golden_weights(); c = Context(0); c.upload_weights(0, [w[k] for k in orc.WEIGHT_NAMES])\n"
+        "case = load_case('zoo30'); t = Topology(case_graph_file(case, tempfile.mkdtemp()), K=100)\n"
+        "tm = np.array(case['tms']['0'])\n"
+        "eb = EpisodeBatch(c, t, 3); eb.reset(np.stack([tm, tm * 2, np.floor(tm / 2)]))\n"
+        "for _ in range(4):\n"
+        "    probs, nK = eb.policy(); eb.step(None)\n"
+        "print(json.dumps({'probs': probs.view(np.uint32).tolist(), 'act': eb.history()[0][:, :4].tolist()}))\n"
+        % (root, os.path.join(root, "tests")))
+    outs = []
+    for tpb in ("", "128", "160"):
+        env = dict(os.environ)
+        env.pop("ENERO_MP_TPB", None)
+        if tpb:
+            env["ENERO_MP_TPB"] = tpb
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(json.loads(r.stdout.strip().splitlines()[-1]))
+    assert outs[0] == outs[1] == outs[2]
