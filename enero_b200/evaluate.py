@@ -143,3 +143,88 @@ def evaluate_topology(ctx: Context, dataset_folder, topology_name, tm_ids, out_f
     if out_folder is not None and mine:
         write_records(res, mine, out_folder, differentiation_str, topology_name, topo.E)
     return mine, res
+
+
+# ---------------------------------------------------------------------------------------------------
+# Driver: eval_on_single_topology.py / eval_on_zoo_topologies.py (same flags), batched on the GPU
+# ---------------------------------------------------------------------------------------------------
+def best_model_id(log_file: str) -> int:
+    """last 'MAX REWD: x REWD_ID: n,' line of the training log (eval_on_single_topology.py:59-66)"""
+    model_id = 0
+    with open(log_file) as fp:
+        for line in reversed(list(fp)):
+            parts = line.split(":")
+            if parts[0] == "MAX REWD":
+                model_id = int(parts[2].split(",")[0])
+                break
+    return model_id
+
+
+def differentiation_from_log(log_file: str) -> str:
+    """'./Logs/expSP_3top_15_B_NEWLogs.txt' -> 'SP_3top_15_B_NEW' (eval_on_single_topology.py:38-40)"""
+    return os.path.basename(log_file).split("exp", 1)[1].split("Logs")[0]
+
+
+def topologies_in_range(dataset_folder, min_nodes, max_nodes, min_edge, max_edge):
+    """.graph files whose NODES / EDGES headers are inside the limits (eval_on_single_topology.py:69-90)"""
+    out = []
+    for f in sorted(os.listdir(dataset_folder)):
+        if not f.endswith(".graph"):
+            continue
+        nodes = edges = None
+        with open(os.path.join(dataset_folder, f)) as fd:
+            for line in fd:
+                if line.startswith("NODES"):
+                    nodes = int(line.split(" ")[1])
+                elif line.startswith("EDGES"):
+                    edges = int(line.split(" ")[1])
+                    break
+        if nodes is not None and edges is not None and min_nodes <= nodes <= max_nodes and min_edge <= edges <= max_edge:
+            out.append(f.split(".")[0])
+    return out
+
+
+def main(argv=None):
+    """python -m enero_b200.evaluate -d ./Logs/exp<diff>Logs.txt -f <dataset folder> -o <result folder>
+           -max_edge 100 -min_edge 5 -max_nodes 30 -min_nodes 1 [-tms 50] [-models ./models<diff>]
+    One process per GPU under torchrun; every rank takes a contiguous shard of each topology's TM ids."""
+    import argparse
+
+    from . import checkpoint as ckpt
+    from . import parallel as par
+    ap = argparse.ArgumentParser(description="batched Enero evaluation (DRL + Local Search) of a dataset folder")
+    ap.add_argument("-d", required=True, help="training log: the model with the best evaluation reward is used")
+    ap.add_argument("-f", required=True, help="dataset folder holding <topology>.graph and TM/")
+    ap.add_argument("-o", required=True, help="result folder (records go to <o><diff>/<topology>/)")
+    ap.add_argument("-max_edge", type=int, default=100)
+    ap.add_argument("-min_edge", type=int, default=5)
+    ap.add_argument("-max_nodes", type=int, default=30)
+    ap.add_argument("-min_nodes", type=int, default=1)
+    ap.add_argument("-tms", type=int, default=50, help="traffic matrices per topology (the reference evaluates 50)")
+    ap.add_argument("-models", default=None, help="checkpoint folder (default ./models<diff>)")
+    args = ap.parse_args(argv)
+    diff = differentiation_from_log(args.d)
+    model_id = best_model_id(args.d)
+    models = args.models or "./models" + diff
+    rank, world, local = par.init_process_group()
+    ctx = Context(local)
+    ctx.upload_weights(0, ckpt.load_actor_weights(os.path.join(models, "ckpt_ACT-%d" % model_id)))
+    summary = []
+    for name in topologies_in_range(args.f, args.min_nodes, args.max_nodes, args.min_edge, args.max_edge):
+        mine, res = evaluate_topology(ctx, args.f, name, list(range(args.tms)), out_folder=args.o, differentiation_str=diff,
+                                      rank=rank, world=world)
+        if res is not None:
+            summary.append({"topology": name, "tms": len(mine), "mean_ospf": float(res["ospf"].mean()),
+                            "mean_drl": float(res["drl"].mean()), "mean_enero": float(res["enero"].mean())})
+    allsum = par.gather_records(summary)
+    if rank == 0:
+        print(json.dumps({"model_id": model_id, "differentiation_str": diff, "n_gpus": world, "topologies": allsum}))
+    ctx.close()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
