@@ -58,6 +58,7 @@ SIGNATURES = {
     "enero_parse_demands_batch": (C.c_int, [_p(C.c_char_p), C.c_int, C.c_int, _vp, C.c_int]),
     "enero_gnn_forward": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int64, C.c_int64, C.c_int, C.c_int, _vp, C.c_int]),
     "enero_decide_batch": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int]),
+    "enero_decide_value_batch": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "enero_value_batch": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, C.c_int]),
     "enero_batch_create": (C.c_int, [_vp, _vp, C.c_int, C.c_double, _p(_vp)]),
     "enero_batch_destroy": (C.c_int, [_vp]),
@@ -65,6 +66,7 @@ SIGNATURES = {
     "enero_batch_policy": (C.c_int, [_vp, _vp, _vp]),
     "enero_batch_value": (C.c_int, [_vp, _vp]),
     "enero_batch_step": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "enero_batch_step_state": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "enero_batch_run_greedy": (C.c_int, [_vp]),
     "enero_batch_snapshot": (C.c_int, [_vp]),
     "enero_batch_restore": (C.c_int, [_vp]),

@@ -440,6 +440,31 @@ extern "C" int enero_decide_batch(enero_ctx* c, enero_topo* t, int B, const doub
     return ENERO_OK;
 }
 
+extern "C" int enero_decide_value_batch(enero_ctx* c, enero_topo* t, int B, const double* loads, const int32_t* sd,
+                                        const double* bw, float* probs, int32_t* nK, float* values) {
+    ENERO_TRACE("enero_decide_value_batch");
+    if (!c || !t || !loads || !sd || !bw || !probs || !nK || !values || B < 1) return fail(ENERO_ERR_INVALID, "enero_decide_value_batch: bad argument");
+    if (t->dev_id != c->device) return fail(ENERO_ERR_STATE, "enero_decide_value_batch: topology not uploaded to this device");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const int E = t->E, Kmax = t->Kmax;
+    TRY(c->logits.ensure((size_t)B * Kmax * 4)); TRY(c->probs.ensure((size_t)B * Kmax * 4));
+    TRY(c->nK.ensure((size_t)B * 4)); TRY(c->action.ensure((size_t)B * 4)); TRY(c->x_out.ensure((size_t)B * 4));
+    TRY(c->in_loads.ensure((size_t)B * E * 8)); TRY(c->in_sd.ensure((size_t)B * 8)); TRY(c->in_bw.ensure((size_t)B * 8));
+    TRY(c->x_gid.ensure((size_t)B * 4));      // nK of the actor pass (value_dev reuses c->nK for its own prologue)
+    CUDA_TRY(cudaMemcpyAsync(c->in_loads.p, loads, (size_t)B * E * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(c->in_sd.p, sd, (size_t)B * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(c->in_bw.p, bw, (size_t)B * 8, cudaMemcpyHostToDevice, st));
+    TRY(decide_dev(c, t, B, c->in_loads.as<double>(), c->in_sd.as<int>(), c->in_bw.as<double>(), nullptr,
+                   c->logits.as<float>(), c->probs.as<float>(), c->x_gid.as<int>(), c->action.as<int>(), 5));
+    CUDA_TRY(cudaMemcpyAsync(probs, c->probs.p, (size_t)B * Kmax * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(nK, c->x_gid.p, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+    TRY(value_dev(c, t, B, c->in_loads.as<double>(), c->x_out.as<float>(), 5));
+    CUDA_TRY(cudaMemcpyAsync(values, c->x_out.p, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return ENERO_OK;
+}
+
 extern "C" int enero_value_batch(enero_ctx* c, enero_topo* t, int B, const double* loads, float* values, int ptr_kind) {
     ENERO_TRACE("enero_value_batch");
     if (!c || !t || !loads || !values || B < 1) return fail(ENERO_ERR_INVALID, "enero_value_batch: bad argument");
@@ -467,6 +492,7 @@ struct enero_batch {
         h_action, h_reward, h_max, last_reward, logits, probs, nK, action, values;
     DevBuf snap;                                    // enero_batch_snapshot image of the mutable state
     DevBuf ls_loads, ls_mid, ls_elig, ls_elig_len, ls_val, ls_nmoves, ls_moves, ls_move_val, ls_max_edge;
+    std::vector<int> h_cur; std::vector<uint8_t> h_done; bool mirror_valid = false;   // host mirror of (cur, done) for action checks
     std::vector<int> h_elig, h_elig_len;           // host mirror of list_eligible_demands
     std::vector<int> h_ls_elig, h_ls_elig_len; int ls_cap = 0;
     int max_len = 0;
@@ -557,7 +583,7 @@ extern "C" int enero_batch_reset(enero_batch* b, const double* tms) {
     CUDA_TRY(cudaMemcpyAsync(b->elig_len.p, b->h_elig_len.data(), (size_t)B * 4, cudaMemcpyHostToDevice, st));
     k_episode_begin<<<(B + 3) / 4, 128, 0, st>>>(tv, ep_view(b)); LAUNCH_CHECK(c);
     CUDA_TRY(cudaStreamSynchronize(st));
-    b->reset_done = true; b->policy_valid = false;
+    b->reset_done = true; b->policy_valid = false; b->mirror_valid = false;
     return ENERO_OK;
 }
 
@@ -590,7 +616,7 @@ extern "C" int enero_batch_restore(enero_batch* b) {
         CUDA_TRY(cudaMemcpyAsync(x.first->p, (char*)b->snap.p + o, x.second, cudaMemcpyDeviceToDevice, b->c->stream));
         o += (x.second + 255) & ~size_t(255);
     }
-    b->policy_valid = false;
+    b->policy_valid = false; b->mirror_valid = false;
     return ENERO_OK;
 }
 
@@ -620,6 +646,26 @@ extern "C" int enero_batch_value(enero_batch* b, float* values_host) {
     return ENERO_OK;
 }
 
+// host-side check of a host action vector against the candidate counts of the current demands; uses the host
+// mirror of (cur, done) when the last call left it valid, else fetches it (one extra stream round trip)
+static int check_actions(enero_batch* b, const int32_t* actions) {
+    enero_ctx* c = b->c;
+    if (!b->mirror_valid) {
+        b->h_cur.resize((size_t)b->B * 2); b->h_done.resize(b->B);
+        CUDA_TRY(cudaMemcpyAsync(b->h_cur.data(), b->cur.p, b->h_cur.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(b->h_done.data(), b->done.p, b->h_done.size(), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        b->mirror_valid = true;
+    }
+    for (int i = 0; i < b->B; ++i) {
+        if (b->h_done[i]) continue;
+        const int sdi = b->h_cur[2 * i] * b->t->N + b->h_cur[2 * i + 1];
+        const int k = b->t->mid_off[sdi + 1] - b->t->mid_off[sdi];
+        if (actions[i] < 0 || actions[i] >= k) return fail(ENERO_ERR_INVALID, "enero_batch_step: action out of range");
+    }
+    return ENERO_OK;
+}
+
 static int step_dev(enero_batch* b) {
     enero_ctx* c = b->c;
     k_env_step<<<(b->B + 3) / 4, 128, 0, c->stream>>>(view_of(b->t), ep_view(b), b->action.as<int>());
@@ -635,25 +681,43 @@ extern "C" int enero_batch_step(enero_batch* b, const int32_t* actions, double* 
     enero_ctx* c = b->c;
     CUDA_TRY(cudaSetDevice(c->device));
     if (actions) {
-        // validate against the candidate counts of the current demands (host mirror not kept: check on device data)
-        std::vector<int> cur((size_t)b->B * 2); std::vector<uint8_t> dn(b->B);
-        CUDA_TRY(cudaMemcpyAsync(cur.data(), b->cur.p, cur.size() * 4, cudaMemcpyDeviceToHost, c->stream));
-        CUDA_TRY(cudaMemcpyAsync(dn.data(), b->done.p, dn.size(), cudaMemcpyDeviceToHost, c->stream));
-        CUDA_TRY(cudaStreamSynchronize(c->stream));
-        for (int i = 0; i < b->B; ++i) {
-            if (dn[i]) continue;
-            const int sdi = cur[2 * i] * b->t->N + cur[2 * i + 1];
-            const int k = b->t->mid_off[sdi + 1] - b->t->mid_off[sdi];
-            if (actions[i] < 0 || actions[i] >= k) return fail(ENERO_ERR_INVALID, "enero_batch_step: action out of range");
-        }
+        TRY(check_actions(b, actions));
         CUDA_TRY(cudaMemcpyAsync(b->action.p, actions, (size_t)b->B * 4, cudaMemcpyHostToDevice, c->stream));
     } else if (!b->policy_valid) {
         return fail(ENERO_ERR_STATE, "enero_batch_step: greedy step needs enero_batch_policy first");
     }
     TRY(step_dev(b));
+    b->mirror_valid = false;
     if (reward) CUDA_TRY(cudaMemcpyAsync(reward, b->last_reward.p, (size_t)b->B * 8, cudaMemcpyDeviceToHost, c->stream));
     if (done) CUDA_TRY(cudaMemcpyAsync(done, b->done.p, (size_t)b->B, cudaMemcpyDeviceToHost, c->stream));
     if (reward || done || actions) CUDA_TRY(cudaStreamSynchronize(c->stream));   // otherwise asynchronous
+    return ENERO_OK;
+}
+
+extern "C" int enero_batch_step_state(enero_batch* b, const int32_t* actions, double* reward, uint8_t* done, double* loads,
+                                      int32_t* cur, double* bw, double* max_uti, int32_t* max_edge) {
+    ENERO_TRACE("enero_batch_step_state");
+    if (!b || !actions) return fail(ENERO_ERR_INVALID, "enero_batch_step_state: null argument");
+    if (!b->reset_done) return fail(ENERO_ERR_STATE, "enero_batch_step_state: reset first");
+    enero_ctx* c = b->c;
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    TRY(check_actions(b, actions));
+    const size_t B = b->B;
+    CUDA_TRY(cudaMemcpyAsync(b->action.p, actions, B * 4, cudaMemcpyHostToDevice, st));
+    TRY(step_dev(b));
+    b->h_cur.resize(B * 2); b->h_done.resize(B);
+    CUDA_TRY(cudaMemcpyAsync(b->h_cur.data(), b->cur.p, B * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(b->h_done.data(), b->done.p, B, cudaMemcpyDeviceToHost, st));
+    if (reward) CUDA_TRY(cudaMemcpyAsync(reward, b->last_reward.p, B * 8, cudaMemcpyDeviceToHost, st));
+    if (loads) CUDA_TRY(cudaMemcpyAsync(loads, b->loads.p, B * b->t->E * 8, cudaMemcpyDeviceToHost, st));
+    if (bw) CUDA_TRY(cudaMemcpyAsync(bw, b->cur_bw.p, B * 8, cudaMemcpyDeviceToHost, st));
+    if (max_uti) CUDA_TRY(cudaMemcpyAsync(max_uti, b->max_uti.p, B * 8, cudaMemcpyDeviceToHost, st));
+    if (max_edge) CUDA_TRY(cudaMemcpyAsync(max_edge, b->max_edge.p, B * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    b->mirror_valid = true;
+    if (cur) std::copy(b->h_cur.begin(), b->h_cur.end(), cur);
+    if (done) std::copy(b->h_done.begin(), b->h_done.end(), done);
     return ENERO_OK;
 }
 
@@ -668,6 +732,7 @@ extern "C" int enero_batch_run_greedy(enero_batch* b) {
                        b->logits.as<float>(), b->probs.as<float>(), b->nK.as<int>(), b->action.as<int>(), 5));
         TRY(step_dev(b));
     }
+    b->mirror_valid = false;
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return ENERO_OK;
 }

@@ -73,6 +73,22 @@ class EpisodeBatch:
         _lib.check(self._lib.enero_batch_step(self._h, _lib.ptr(a), _lib.ptr(reward), _lib.ptr(done)))
         return reward, done.astype(bool)
 
+    def step_state(self, actions):
+        """Env16.step with host actions and the post-step state in one stream round trip
+        -> (reward[B], done[B], state dict with loads, cur, bw, max_uti, max_edge)."""
+        a = np.ascontiguousarray(actions, dtype=np.int32).reshape(-1)
+        if a.size != self.B:
+            raise ValueError("need one action per episode")
+        B, E = self.B, self.topo.E
+        reward = np.zeros(B)
+        done = np.zeros(B, dtype=np.uint8)
+        st = {"loads": np.zeros((B, E)), "cur": np.zeros((B, 2), dtype=np.int32), "bw": np.zeros(B),
+              "max_uti": np.zeros(B), "max_edge": np.zeros(B, dtype=np.int32)}
+        _lib.check(self._lib.enero_batch_step_state(self._h, _lib.ptr(a), _lib.ptr(reward), _lib.ptr(done), _lib.ptr(st["loads"]),
+                                                    _lib.ptr(st["cur"]), _lib.ptr(st["bw"]), _lib.ptr(st["max_uti"]),
+                                                    _lib.ptr(st["max_edge"])))
+        return reward, done.astype(bool), st
+
     def run_greedy(self):
         _lib.check(self._lib.enero_batch_run_greedy(self._h))
 

@@ -156,12 +156,11 @@ class Env16(_EnvBase):
         mids = self.src_dst_k_middlepoints["%d:%d" % (source, destination)]
         if not 0 <= action < len(mids):
             raise IndexError("list index out of range")
-        reward, done = self._batch.step([action])
+        reward, done, st = self._batch.step_state([action])
         mid = mids[action]
         if mid != destination:
             self.sp_middlepoints["%d:%d" % (source, destination)] = mid
         self.sp_middlepoints_step = self.sp_middlepoints
-        st = self._batch.state()
         self.edgeMaxUti = self._edge_tuple(int(st["max_edge"][0]), st["max_uti"][0])
         self.currentVal = -self.edgeMaxUti[2]
         self.reward = reward[0]

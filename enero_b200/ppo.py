@@ -71,6 +71,7 @@ class PPOActorCritic:
         self._lib = _lib.load()
         self._pg = process_group
         self._grad_view = None
+        self._value_cache = None
         self.last_grad_norm = None
 
     # ---- acting ----------------------------------------------------------------------------
@@ -79,10 +80,13 @@ class PPOActorCritic:
         t = env.topology
         loads = np.array(env.edge_state[:, 0], dtype=np.float64)
         bw = float(env.TM[source][destination])
-        logits, probs, nK, _ = self.context.decide_batch(t, loads[None], np.array([[source, destination]], np.int32),
-                                                         np.array([bw]))
+        # the rollout asks for the critic's value of the same state right after (train script :495-500): both
+        # networks run in one stream round trip and the value is handed out by critic_value()
+        probs, nK, values = self.context.decide_value_batch(t, loads[None], np.array([[source, destination]], np.int32),
+                                                            np.array([bw]))
         k = int(nK[0])
-        self.listQValues = logits[:1, :k]
+        self._value_cache = (t, loads, np.float32(values[0]))
+        self.listQValues = None
         self.softMaxQValues = probs[:1, :k]
         tensor = {'topology': t, 'loads': loads, 'sd': (int(source), int(destination)), 'bw': bw, 'num_candidates': k}
         return probs[0, :k].copy(), tensor
@@ -93,6 +97,9 @@ class PPOActorCritic:
 
     def critic_value(self, features):
         """self.critic(link_state_critic, first_critic, second_critic, num_edges_critic)[0].numpy()[0]"""
+        cached = getattr(self, "_value_cache", None)
+        if cached is not None and cached[0] is features['topology'] and np.array_equal(cached[1], features['loads']):
+            return cached[2]
         return self.context.value_batch(features['topology'], features['loads'][None])[0]
 
     # ---- learning ----------------------------------------------------------------------------
@@ -158,6 +165,7 @@ class PPOActorCritic:
                                              float(self.optimizer.epsilon), max_grad_norm,
                                              int(self.optimizer.iterations), _lib.ptr(norm)))
         self.last_grad_norm = float(norm[0])
+        self._value_cache = None
         final_entropy = sums[1] / m
         actor_loss = sums[0] / m - self.entropy_beta * final_entropy
         critic_loss = sums[2] / m

@@ -140,6 +140,22 @@ class Context:
                                                 _lib.ptr(logits), _lib.ptr(probs), _lib.ptr(nK), _lib.ptr(action), _lib.HOST))
         return logits, probs, nK, action
 
+    def decide_value_batch(self, topo: Topology, loads, sd, bw):
+        """-> (probs[B,Kmax], nK[B], values[B]): actor and critic on the same states, one stream round trip."""
+        loads = np.ascontiguousarray(loads, dtype=np.float64)
+        sd = np.ascontiguousarray(sd, dtype=np.int32)
+        bw = np.ascontiguousarray(bw, dtype=np.float64).reshape(-1)
+        B = bw.size
+        if loads.shape != (B, topo.E) or sd.shape != (B, 2):
+            raise ValueError("loads must be [B,E] and sd [B,2]")
+        _lib.check(self._lib.enero_topo_upload(self._h, topo.handle))
+        probs = np.zeros((B, topo.Kmax), dtype=np.float32)
+        nK = np.zeros(B, dtype=np.int32)
+        values = np.zeros(B, dtype=np.float32)
+        _lib.check(self._lib.enero_decide_value_batch(self._h, topo.handle, B, _lib.ptr(loads), _lib.ptr(sd), _lib.ptr(bw),
+                                                      _lib.ptr(probs), _lib.ptr(nK), _lib.ptr(values)))
+        return probs, nK, values
+
     def value_batch(self, topo: Topology, loads) -> np.ndarray:
         loads = np.ascontiguousarray(loads, dtype=np.float64)
         B = loads.shape[0]

@@ -121,6 +121,10 @@ int enero_gnn_forward(enero_ctx* ctx, int which, const float* link_state, const 
 int enero_decide_batch(enero_ctx* ctx, enero_topo* topo, int B, const double* loads,
                        const int32_t* sd, const double* bw, float* logits, float* probs,
                        int32_t* nK, int32_t* action, int ptr_kind);
+/* actor probabilities AND critic value of the same B states in one stream round trip (the rollout of
+ * train_Enero_3top_script.py:495-500 asks for both at every decision).  Host pointers; probs fp32[B,Kmax]. */
+int enero_decide_value_batch(enero_ctx* ctx, enero_topo* topo, int B, const double* loads, const int32_t* sd,
+                             const double* bw, float* probs, int32_t* nK, float* values);
 /* critic value of B link-load states (critic_get_graph_features, train script :204-230) */
 int enero_value_batch(enero_ctx* ctx, enero_topo* topo, int B, const double* loads, float* values,
                       int ptr_kind);
@@ -140,6 +144,10 @@ int enero_batch_value(enero_batch* b, float* values_host);
  * enero_batch_policy.  Outputs (nullable): reward fp64[B], done u8[B].  With all three pointers NULL the
  * call only enqueues the kernel (asynchronous); otherwise it returns after the stream has drained. */
 int enero_batch_step(enero_batch* b, const int32_t* actions_host, double* reward_host, uint8_t* done_host);
+/* Env16.step with host actions plus everything the callers read afterwards (reward, done, link loads, next
+ * demand, its bandwidth, edgeMaxUti) in one stream round trip.  Outputs nullable except via `actions`. */
+int enero_batch_step_state(enero_batch* b, const int32_t* actions_host, double* reward, uint8_t* done, double* loads,
+                           int32_t* cur, double* bw, double* max_uti, int32_t* max_edge);
 /* whole greedy episodes (play_middRout_games_sp, script :162-188) without host round trips */
 int enero_batch_run_greedy(enero_batch* b);
 /* save / restore the mutable episode state on device (rollout restarts, benchmarking) */
