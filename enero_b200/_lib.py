@@ -14,6 +14,7 @@ from . import build as _build
 
 HOST, DEVICE = 0, 1
 ACTOR, CRITIC = 0, 1
+MATH_FAST, MATH_ACCURATE = 0, 1
 NPARAMS = 4201
 GRAD_STRIDE = 4204
 GRAD_FLOATS = 2 * GRAD_STRIDE + 4
@@ -42,6 +43,8 @@ SIGNATURES = {
     "enero_ctx_sync": (C.c_int, [_vp]),
     "enero_ctx_launch_count": (C.c_int64, [_vp]),
     "enero_ctx_stream": (_vp, [_vp]),
+    "enero_ctx_set_math": (C.c_int, [_vp, C.c_int]),
+    "enero_ctx_get_math": (C.c_int, [_vp]),
     "enero_ctx_profile_begin": (C.c_int, [_vp]),
     "enero_ctx_profile_end": (C.c_int, [_vp, _vp, _vp]),
     "enero_weights_upload": (C.c_int, [_vp, C.c_int, _vp]),

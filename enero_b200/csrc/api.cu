@@ -17,7 +17,6 @@
 #include "enero_internal.h"
 #include "env_kernels.cuh"
 #include "gnn_kernels.cuh"
-#include "mp_tile_kernel.cuh"
 #include "train_kernels.cuh"
 
 using namespace enero;
@@ -64,18 +63,27 @@ extern "C" int enero_ctx_create(int device, enero_ctx** out) {
             }
         };
         int tmp = 0;
-        setup(k_mp_iter<IdxExplicit, false, 20>, c->occ_iter[0][0]);
-        setup(k_mp_iter<IdxExplicit, true, 20>, c->occ_iter[0][1]);
-        setup(k_mp_iter<IdxTopo, false, 20>, c->occ_iter[1][0]);
-        setup(k_mp_iter<IdxTopo, true, 20>, c->occ_iter[1][1]);
-        setup(k_mp_iter<IdxTopo, false, 3>, tmp);
+        // [math][indexer][last]
+        setup(k_mp_iter<IdxExplicit, false, 20, false>, c->occ_iter[0][0][0]);
+        setup(k_mp_iter<IdxExplicit, true, 20, false>, c->occ_iter[0][0][1]);
+        setup(k_mp_iter<IdxTopo, false, 20, false>, c->occ_iter[0][1][0]);
+        setup(k_mp_iter<IdxTopo, true, 20, false>, c->occ_iter[0][1][1]);
+        setup(k_mp_iter<IdxTopo, false, 3, false>, tmp);
+        setup(k_mp_iter<IdxExplicit, false, 20, true>, c->occ_iter[1][0][0]);
+        setup(k_mp_iter<IdxExplicit, true, 20, true>, c->occ_iter[1][0][1]);
+        setup(k_mp_iter<IdxTopo, false, 20, true>, c->occ_iter[1][1][0]);
+        setup(k_mp_iter<IdxTopo, true, 20, true>, c->occ_iter[1][1][1]);
+        setup(k_mp_iter<IdxTopo, false, 3, true>, tmp);
         if (r != ENERO_OK) return r;
     }
-    CUDA_TRY(cudaFuncSetAttribute(k_bwd_gates, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWG_SMEM_BYTES));
-    CUDA_TRY(cudaFuncSetAttribute(k_mp_tile<false, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize, MP_TILE_SMEM_MAX));
-    CUDA_TRY(cudaFuncSetAttribute(k_mp_tile<true, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize, MP_TILE_SMEM_MAX));
-    CUDA_TRY(cudaFuncSetAttribute(k_mp_tile<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, MP_TILE_SMEM_MAX));
-    if (const char* e = std::getenv("ENERO_MP_TPB")) c->tile_tpb_override = std::atoi(e);
+    CUDA_TRY(cudaFuncSetAttribute(k_bwd_gates<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWG_SMEM_BYTES));
+    CUDA_TRY(cudaFuncSetAttribute(k_bwd_gates<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWG_SMEM_BYTES));
+    c->math_acc = ENERO_MATH_DEFAULT;
+    if (const char* e = std::getenv("ENERO_MATH")) {
+        if (!std::strcmp(e, "fast")) c->math_acc = 0;
+        else if (!std::strcmp(e, "accurate")) c->math_acc = 1;
+        else return fail(ENERO_ERR_INVALID, "ENERO_MATH must be 'fast' or 'accurate'");
+    }
     *out = c;
     return ENERO_OK;
 }
@@ -98,6 +106,13 @@ extern "C" int enero_ctx_sync(enero_ctx* c) {
 }
 extern "C" int64_t enero_ctx_launch_count(enero_ctx* c) { return c ? c->launches : -1; }
 extern "C" void* enero_ctx_stream(enero_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+extern "C" int enero_ctx_set_math(enero_ctx* c, int mode) {
+    if (!c || mode < 0 || mode > 1) return fail(ENERO_ERR_INVALID, "enero_ctx_set_math: mode must be ENERO_MATH_FAST or ENERO_MATH_ACCURATE");
+    c->math_acc = mode;
+    return ENERO_OK;
+}
+extern "C" int enero_ctx_get_math(enero_ctx* c) { return c ? c->math_acc : -1; }
 
 extern "C" int enero_ctx_profile_begin(enero_ctx* c) {
     if (!c) return fail(ENERO_ERR_INVALID, "null ctx");
@@ -182,32 +197,6 @@ static TopoView view_of(const enero_topo* t) {
 
 // ---- message passing driver ---------------------------------------------------------------
 
-// CTA size / graphs per tile of k_mp_tile for a topology, or tpb = 0 when the generic k_mp_iter should run
-// (no pairs, graphs larger than a tile, or too few candidate graphs per decision to fill the slots).
-struct TileCfg { int tpb = 0, G = 0, TPD = 0, ctas = 0; size_t smem = 0; };
-static TileCfg mp_tile_config(const enero_ctx* c, int E, int off_f, int off_s, int Kmax) {
-    TileCfg best; double best_score = 0.0;
-    // measured slower than k_mp_iter on B200: opt-in through ENERO_MP_TPB
-    if (off_f <= 0 || off_s <= 0 || Kmax < 2 || c->tile_tpb_override <= 0) return best;
-    for (int tpb = 128; tpb <= 256; tpb += 32) {
-        if (c->tile_tpb_override > 0 && tpb != c->tile_tpb_override) continue;
-        const int slots = MP_R * tpb;
-        const int G = std::min(slots / off_s, Kmax);
-        if (G < 1 || Kmax * (E - off_s) > slots) continue;
-        const size_t smem = mp_tile_smem_bytes(tpb, G * off_f);
-        if (smem > (size_t)MP_TILE_SMEM_MAX) continue;
-        const int ctas = (int)std::min<size_t>((size_t)(233472 / (smem + 1024)), (size_t)(65536 / (168 * tpb)));
-        if (ctas < 1) continue;
-        const double util = (double)G * off_s / slots;
-        const double warps = ctas * tpb / 32.0;
-        const double score = util * std::sqrt(std::min(1.0, warps / 12.0));
-        if (util >= 0.6 && score > best_score) {
-            best_score = score; best.tpb = tpb; best.G = G; best.TPD = (Kmax + G - 1) / G + 1; best.ctas = ctas; best.smem = smem;
-        }
-    }
-    return best;
-}
-
 // a zeroed tile counter for the next k_mp_iter launch (re-zeroed in batches of 16 on the stream)
 static int next_tile_counter(enero_ctx* c, int** out) {
     if (c->tile_ctr_next >= 16) {
@@ -218,73 +207,50 @@ static int next_tile_counter(enero_ctx* c, int** out) {
     return ENERO_OK;
 }
 
-template <bool LAST, int KH>
-static void launch_tile(enero_ctx* c, const TileCfg& cfg, const TileTopo& tt, int which, const float* hin, const float* Ain,
-                        float* hout, float* Aout) {
-    const int ntiles = tt.B * cfg.TPD;
-    const int grid = std::min(ntiles, c->num_sms * cfg.ctas);
-    k_mp_tile<LAST, KH><<<grid, cfg.tpb, cfg.smem, c->stream>>>(tt, c->w[which], hin, Ain, hout, Aout, ntiles);
-}
-
-// one message-passing iteration of the implicit (per-topology) row space
-static int launch_topo_iteration(enero_ctx* c, const IdxTopo& idx, int which, bool last, bool sparse, const float* hin,
-                                 const float* Ain, float* hout, float* Aout) {
-    const int Kmax = idx.RPD / idx.E;
-    const TileCfg cfg = mp_tile_config(c, idx.E, idx.off_f, idx.off_s, Kmax);
-    const int64_t B = idx.total / idx.RPD;
+// one message-passing iteration: picks the instantiation (last / 3-column first iteration / math mode),
+// sizes the persistent grid and, when profiling is on, brackets the launch with CUDA events
+template <class IDX>
+static int launch_iteration(enero_ctx* c, const IDX& idx, int idx_kind, int which, bool last, bool sparse, const float* hin,
+                            const float* Ain, float* hout, float* Aout) {
+    const int64_t ntiles = (idx.rows() + MP_WROWS - 1) / MP_WROWS;          // 64-row warp tiles
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (c->prof) {
         CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
         CUDA_TRY(cudaEventRecord(e0, c->stream));
     }
-    if (cfg.tpb > 0 && B * cfg.TPD < ((int64_t)1 << 31)) {
-        TileTopo tt{(int)B, idx.E, idx.off_f, idx.off_s, idx.RPD, cfg.G, cfg.TPD, idx.nK, idx.in_off, idx.in_first};
-        if (last) launch_tile<true, 20>(c, cfg, tt, which, hin, Ain, hout, Aout);
-        else if (sparse) launch_tile<false, 3>(c, cfg, tt, which, hin, Ain, hout, Aout);
-        else launch_tile<false, 20>(c, cfg, tt, which, hin, Ain, hout, Aout);
+    int* ctr = nullptr;
+    TRY(next_tile_counter(c, &ctr));
+    const int occ = std::max(1, c->occ_iter[c->math_acc][idx_kind][last ? 1 : 0]);
+    const int grid = (int)std::min<int64_t>((ntiles + MP_WARPS - 1) / MP_WARPS, (int64_t)c->num_sms * occ);
+    auto go = [&](auto kern) { kern<<<grid, MP_TPB, MP_SMEM_BYTES, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles, ctr); };
+    constexpr bool TOPO = std::is_same<IDX, IdxTopo>::value;     // the 3-column first iteration exists for the fused path only
+    if (c->math_acc) {
+        if (last) go(k_mp_iter<IDX, true, 20, true>);
+        else if (TOPO && sparse) go(k_mp_iter<IDX, false, TOPO ? 3 : 20, true>);
+        else go(k_mp_iter<IDX, false, 20, true>);
     } else {
-        const int64_t ntiles = (idx.total + MP_WROWS - 1) / MP_WROWS;          // 64-row warp tiles
-        int* ctr = nullptr;
-        TRY(next_tile_counter(c, &ctr));
-        const int occ = std::max(1, c->occ_iter[1][last ? 1 : 0]);
-        const int grid = (int)std::min<int64_t>((ntiles + MP_WARPS - 1) / MP_WARPS, (int64_t)c->num_sms * occ);
-        if (last) k_mp_iter<IdxTopo, true, 20><<<grid, MP_TPB, MP_SMEM_BYTES, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles, ctr);
-        else if (sparse) k_mp_iter<IdxTopo, false, 3><<<grid, MP_TPB, MP_SMEM_BYTES, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles, ctr);
-        else k_mp_iter<IdxTopo, false, 20><<<grid, MP_TPB, MP_SMEM_BYTES, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles, ctr);
+        if (last) go(k_mp_iter<IDX, true, 20, false>);
+        else if (TOPO && sparse) go(k_mp_iter<IDX, false, TOPO ? 3 : 20, false>);
+        else go(k_mp_iter<IDX, false, 20, false>);
     }
     LAUNCH_CHECK(c);
     if (c->prof) { CUDA_TRY(cudaEventRecord(e1, c->stream)); c->prof_ev.emplace_back(e0, e1); }
     return ENERO_OK;
 }
+static int launch_topo_iteration(enero_ctx* c, const IdxTopo& idx, int which, bool last, bool sparse, const float* hin,
+                                 const float* Ain, float* hout, float* Aout) {
+    return launch_iteration(c, idx, 1, which, last, sparse, hin, Ain, hout, Aout);
+}
 
 // sparse_first: the rows of iteration 0 have at most 3 non-zero leading columns (fused feature path)
 template <class IDX>
 static int run_iterations(enero_ctx* c, const IDX& idx, int which, int T, int64_t rows, int idx_kind, bool sparse_first = false) {
-    const int64_t ntiles = (rows + MP_WROWS - 1) / MP_WROWS;
     if (rows >= (int64_t)1 << 31) return fail(ENERO_ERR_INVALID, "more than 2^31 link-state rows in one launch: split the batch");
     for (int it = 0; it < T; ++it) {
         const bool last = (it == T - 1);
-        const float* hin = c->h[it & 1].as<float>();
-        const float* Ain = c->A[it & 1].as<float>();
-        float* hout = c->h[(it + 1) & 1].as<float>();
-        float* Aout = c->A[(it + 1) & 1].as<float>();
-        if constexpr (std::is_same<IDX, IdxTopo>::value) {
-            TRY(launch_topo_iteration(c, idx, which, last, it == 0 && sparse_first && !last, hin, Ain, hout, Aout));
-        } else {
-            cudaEvent_t e0 = nullptr, e1 = nullptr;
-            if (c->prof) {
-                CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
-                CUDA_TRY(cudaEventRecord(e0, c->stream));
-            }
-            int* ctr = nullptr;
-            TRY(next_tile_counter(c, &ctr));
-            const int occ = std::max(1, c->occ_iter[idx_kind][last ? 1 : 0]);
-            const int grid = (int)std::min<int64_t>((ntiles + MP_WARPS - 1) / MP_WARPS, (int64_t)c->num_sms * occ);
-            if (last) k_mp_iter<IDX, true, 20><<<grid, MP_TPB, MP_SMEM_BYTES, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles, ctr);
-            else k_mp_iter<IDX, false, 20><<<grid, MP_TPB, MP_SMEM_BYTES, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles, ctr);
-            LAUNCH_CHECK(c);
-            if (c->prof) { CUDA_TRY(cudaEventRecord(e1, c->stream)); c->prof_ev.emplace_back(e0, e1); }
-        }
+        TRY(launch_iteration(c, idx, idx_kind, which, last, it == 0 && sparse_first && !last && idx_kind == 1,
+                             c->h[it & 1].as<float>(), c->A[it & 1].as<float>(), c->h[(it + 1) & 1].as<float>(),
+                             c->A[(it + 1) & 1].as<float>()));
     }
     return ENERO_OK;
 }

@@ -50,10 +50,10 @@ struct enero_ctx {
     // scratch of the GNN engine
     DevBuf h[2], A[2], util, nK, logits, probs, action, in_loads, in_sd, in_bw, ones;
     DevBuf x_ls, x_gid, x_first, x_second, x_cnt, x_off, x_cur, x_slot, x_src, x_goff, x_err, x_out;
-    int occ_iter[2][2] = {{0, 0}, {0, 0}};   // [indexer][last] resident CTAs/SM of k_mp_iter
+    int occ_iter[2][2][2] = {};              // [math][indexer][last] resident CTAs/SM of k_mp_iter
+    int math_acc = ENERO_MATH_DEFAULT;                        // ENERO_MATH_ACCURATE / ENERO_MATH_FAST (enero_ctx_set_math, ENERO_MATH)
     int* tile_ctr = nullptr;                 // [16] dynamic tile counters of k_mp_iter, one per launch of a sequence
     int tile_ctr_next = 16;                  // next unused counter (16 = re-zero first)
-    int tile_tpb_override = -1;              // ENERO_MP_TPB: 0 = never use k_mp_tile, >0 = force this CTA size
     // optional per-launch CUDA-event timing of the dominant kernel (bench.py roofline leg)
     bool prof = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_ev;

@@ -77,7 +77,7 @@ struct IdxExplicit {
     const int* src;       // [p] source rows in CSR order
     __device__ __forceinline__ bool valid(int64_t r) const { return r < n; }
     __device__ __forceinline__ bool in_range(int64_t r) const { return r < n; }
-    __device__ __forceinline__ int64_t rows() const { return n; }
+    __host__ __device__ __forceinline__ int64_t rows() const { return n; }
     __device__ __forceinline__ bool tile_live(int64_t r0, int) const { return r0 < n; }
     __device__ __forceinline__ void seg(int64_t r, int& b, int& e, const int*& list, int64_t& add) const {
         b = seg_off[r]; e = seg_off[r + 1]; list = src; add = 0;
@@ -99,7 +99,7 @@ struct IdxTopo {
     const int* in_off;    // [E+1]
     const int* in_first;  // [P]
     __device__ __forceinline__ bool in_range(int64_t r) const { return r < total; }
-    __device__ __forceinline__ int64_t rows() const { return total; }
+    __host__ __device__ __forceinline__ int64_t rows() const { return total; }
     // does the row range [r0, r0 + n) hold a live row of any decision?
     __device__ __forceinline__ bool tile_live(int64_t r0, int n) const {
         const int64_t r1 = r0 + n;                         // exclusive
@@ -215,6 +215,37 @@ __device__ __forceinline__ u64 selu_fast2(u64 x) {
 __device__ __forceinline__ float sigmoid_fast(float x) { return rcp_approx(1.f + ex2_approx(-LOG2E * x)); }
 __device__ __forceinline__ float tanh_fast(float x) { return fmaf(-2.f, rcp_approx(1.f + ex2_approx((2.f * LOG2E) * x)), 1.f); }
 
+// ---- math policy of the message-passing kernels -----------------------------------------------------
+// ACC = false ("fast", the default): MUFU.EX2 / MUFU.RCP forms above, ~1e-6 relative error per call.
+// ACC = true  ("accurate"): libdevice expf / tanhf (<= 2 ulp) and IEEE division, the selu / sigmoid expressions
+//              written exactly as TensorFlow's functors and the oracle write them (relu_op_functor.h:
+//              scale_alpha * (exp(x) - 1); sigmoid = 1 / (1 + exp(-x))).
+// Selected per context (enero_ctx_set_math / ENERO_MATH).  Against the fp64 arbiter both modes sit at the fp32
+// rounding floor of the sums (profiles/r02_parity_sweep.json); accurate costs 46 % throughput.
+template <bool ACC> struct Mth;
+template <> struct Mth<false> {
+    static __device__ __forceinline__ float selu(float x) { return selu_fast(x); }
+    static __device__ __forceinline__ float sigmoid(float x) { return sigmoid_fast(x); }
+    static __device__ __forceinline__ float tanh_(float x) { return tanh_fast(x); }
+    static __device__ __forceinline__ float selu_grad(float u) {
+        return u < 0.f ? 1.7580993408473768599402175208123f * ex2_approx(u * LOG2E) : 1.0507009873554804934193349852946f;
+    }
+    static __device__ __forceinline__ u64 selu2(u64 x) { return selu_fast2(x); }
+};
+template <> struct Mth<true> {
+    static __device__ __forceinline__ float selu(float x) { return selu_f(x); }
+    static __device__ __forceinline__ float sigmoid(float x) { return sigmoid_f(x); }
+    static __device__ __forceinline__ float tanh_(float x) { return tanhf(x); }
+    static __device__ __forceinline__ float selu_grad(float u) {
+        return u < 0.f ? 1.7580993408473768599402175208123f * expf(u) : 1.0507009873554804934193349852946f;
+    }
+    static __device__ __forceinline__ u64 selu2(u64 x) {
+        float lo, hi;
+        unpack2(x, lo, hi);
+        return pack2(selu_f(lo), selu_f(hi));
+    }
+};
+
 // ---- one message-passing iteration ------------------------------------------------
 // Persistent CTAs of 128 threads; every thread owns MP_R = 2 link-state rows of a 256-row tile so
 // that each broadcast LDS.128 of weights feeds 8 FMAs (the shared-memory return path, not the FMA
@@ -264,10 +295,11 @@ __device__ __forceinline__ void mp_phase_B(const W sw, const float (&h)[MP_R][H]
 }
 
 // agg += selu(a + B) for one gathered operand row (packed f32x2 lanes, rounding identical to the scalar form)
+template <bool ACC>
 __device__ __forceinline__ void mp_accumulate(u64 (&agg2)[H / 2], const float (&a)[H], const u64 (&t2)[H / 2]) {
 #pragma unroll
     for (int j = 0; j < H / 2; ++j)
-        agg2[j] = add2(agg2[j], selu_fast2(add2(pack2(a[2 * j], a[2 * j + 1]), t2[j])));
+        agg2[j] = add2(agg2[j], Mth<ACC>::selu2(add2(pack2(a[2 * j], a[2 * j + 1]), t2[j])));
 }
 // the row's B vector as packed pairs, read once from its slot before the gather loop
 __device__ __forceinline__ void mp_load_B(u64 (&t2)[H / 2], const float* __restrict__ myb) {
@@ -279,7 +311,7 @@ __device__ __forceinline__ void mp_load_B(u64 (&t2)[H / 2], const float* __restr
 }
 
 // z = sigmoid(agg.Kz + b0z + h.Rz + b1z)   (GRUCell, reset_after=True)  ->  myb slots
-template <int KH, class W>
+template <int KH, bool ACC, class W>
 __device__ __forceinline__ void mp_phase_z(const W sw, const float (&h)[MP_R][H], const float (&agg)[MP_R][H],
                                            float* const (&myb)[MP_R]) {
 #pragma unroll 1
@@ -304,13 +336,13 @@ __device__ __forceinline__ void mp_phase_z(const W sw, const float (&h)[MP_R][H]
         for (int r = 0; r < MP_R; ++r) {
             float v0, v1, v2, v3;
             unpack2(add2(add2(acc[r][0], b0.x), b1.x), v0, v1); unpack2(add2(add2(acc[r][1], b0.y), b1.y), v2, v3);
-            *reinterpret_cast<float4*>(myb[r] + 4 * jb) = make_float4(sigmoid_fast(v0), sigmoid_fast(v1), sigmoid_fast(v2), sigmoid_fast(v3));
+            *reinterpret_cast<float4*>(myb[r] + 4 * jb) = make_float4(Mth<ACC>::sigmoid(v0), Mth<ACC>::sigmoid(v1), Mth<ACC>::sigmoid(v2), Mth<ACC>::sigmoid(v3));
         }
     }
 }
 
 // r, candidate state and the new h, four outputs at a time: new h -> myh slots (and hout[r] + 4*jb if non-null)
-template <int KH, class W>
+template <int KH, bool ACC, class W>
 __device__ __forceinline__ void mp_phase_rh(const W sw, const float (&h)[MP_R][H], const float (&agg)[MP_R][H],
                                             float* const (&myh)[MP_R], float* const (&myb)[MP_R], float* const (&hout)[MP_R]) {
 #pragma unroll 1
@@ -355,8 +387,8 @@ __device__ __forceinline__ void mp_phase_rh(const W sw, const float (&h)[MP_R][H
             float hn[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const float rg = sigmoid_fast(rv[i] + b1[i]);
-                const float cand = tanh_fast(xv[i] + rg * yv[i]);
+                const float rg = Mth<ACC>::sigmoid(rv[i] + b1[i]);
+                const float cand = Mth<ACC>::tanh_(xv[i] + rg * yv[i]);
                 hn[i] = zz[i] * hh0[i] + (1.f - zz[i]) * cand;
             }
             const float4 o = make_float4(hn[0], hn[1], hn[2], hn[3]);
@@ -407,7 +439,7 @@ __device__ __forceinline__ void mp_phase_A(const W sw, float* const (&myh)[MP_R]
 constexpr int MP_WROWS = 32 * MP_R;          // rows per warp tile
 constexpr int MP_WARPS = MP_TPB / 32;
 
-template <class IDX, bool LAST, int KH>
+template <class IDX, bool LAST, int KH, bool ACC>
 __global__ void __launch_bounds__(MP_TPB, 3)
 k_mp_iter(const IDX idx, const float* __restrict__ wflat, const float* __restrict__ h_in,
           const float* __restrict__ A_in, float* __restrict__ h_out, float* __restrict__ A_out,
@@ -497,7 +529,7 @@ k_mp_iter(const IDX idx, const float* __restrict__ wflat, const float* __restric
 #pragma unroll
                 for (int r = 0; r < MP_R; ++r) {
                     if (!on[r]) continue;
-                    mp_accumulate(agg2[r], a[r], t2[r]);
+                    mp_accumulate<ACC>(agg2[r], a[r], t2[r]);
                 }
             }
         }
@@ -511,7 +543,7 @@ k_mp_iter(const IDX idx, const float* __restrict__ wflat, const float* __restric
             for (int j = 0; j < H / 2; ++j) unpack2(agg2[r][j], agg[r][2 * j], agg[r][2 * j + 1]);
         }
         // ---- z = sigmoid(agg.Kz + b0z + h.Rz + b1z)   (GRUCell, reset_after=True)
-        mp_phase_z<KH>(sw, h, agg, myb);
+        mp_phase_z<KH, ACC>(sw, h, agg, myb);
         // ---- r, candidate state and the new h; then A' = h' . Wm[0:20]
         float* hout[MP_R]; float* aout[MP_R];
 #pragma unroll
@@ -519,7 +551,7 @@ k_mp_iter(const IDX idx, const float* __restrict__ wflat, const float* __restric
             hout[r] = (!TMA && ok[r]) ? h_out + row[r] * H : nullptr;
             aout[r] = TMA ? myb[r] : ((ok[r] && !LAST) ? A_out + row[r] * H : nullptr);
         }
-        mp_phase_rh<KH>(sw, h, agg, myh, myb, hout);
+        mp_phase_rh<KH, ACC>(sw, h, agg, myh, myb, hout);
         if (!LAST) mp_phase_A(sw, myh, aout);
         if (TMA) {
             fence_proxy_async();                             // slot writes visible to the bulk store
@@ -577,6 +609,26 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// Per-graph sum of the link states, rows in ASCENDING order per column -- the order of tf.math.segment_sum /
+// reduce_sum(axis=0) on the CPU (Eigen reduces the outer dimension sequentially per output packet) and of the
+// oracle's np.add.at: lane j < 20 owns column j and adds h[r][j] for r = r0, r0+1, ...; one row is one coalesced
+// 80-byte read of the warp, eight rows are in flight at a time.  Every lane gets all 20 sums.
+__device__ __forceinline__ void graph_row_sum(float (&acc)[H], const float* __restrict__ h, int64_t r0, int64_t r1, int lane) {
+    const int j = lane < H ? lane : 0;
+    float s = 0.f;
+    int64_t r = r0;
+    for (; r + 8 <= r1; r += 8) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = h[(r + i) * H + j];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += v[i];
+    }
+    for (; r < r1; ++r) s += h[r * H + j];
+#pragma unroll
+    for (int k = 0; k < H; ++k) acc[k] = __shfl_sync(0xffffffffu, s, k);
+}
+
 template <class GR>
 __global__ void __launch_bounds__(128)
 k_readout(const GR gr, const float* __restrict__ wflat, const float* __restrict__ h, float* __restrict__ out) {
@@ -588,16 +640,7 @@ k_readout(const GR gr, const float* __restrict__ wflat, const float* __restrict_
     int64_t r0, r1, o;
     if (!gr.range(g, r0, r1, o)) return;
     float acc[H];
-#pragma unroll
-    for (int j = 0; j < H; ++j) acc[j] = 0.f;
-    for (int64_t r = r0 + lane; r < r1; r += 32) {
-        float v[H];
-        load_row(v, h + r * H);
-#pragma unroll
-        for (int j = 0; j < H; ++j) acc[j] += v[j];
-    }
-#pragma unroll
-    for (int j = 0; j < H; ++j) acc[j] = warp_sum(acc[j]);
+    graph_row_sum(acc, h, r0, r1, lane);
     const float* R1 = sr; const float* B1 = sr + (W_R1_B - W_R1_K);
     const float* R2 = sr + (W_R2_K - W_R1_K); const float* B2 = sr + (W_R2_B - W_R1_K);
     const float* R3 = sr + (W_R3_K - W_R1_K); const float* B3 = sr + (W_R3_B - W_R1_K);

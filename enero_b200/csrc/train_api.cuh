@@ -60,15 +60,23 @@ int train_backward(enero_ctx* c, enero_topo* t, const TrainTopo& g, int which, i
     for (int it = T - 1; it >= 0; --it) {
         const float* ht = c->t_h[it].as<float>();
         const float* At = c->t_A[it].as<float>();
-        k_bwd_gates<<<bgrid, BW_TPB, BWG_SMEM_BYTES, st>>>(idx, w, ht, At, c->t_dh[cur].as<float>(), c->t_agg.as<float>(), c->t_G.as<float>(),
-                                              c->t_B.as<float>(), c->t_dagg.as<float>(), c->t_dhpart.as<float>());
+        auto gates = [&](auto kern) {
+            kern<<<bgrid, BW_TPB, BWG_SMEM_BYTES, st>>>(idx, w, ht, At, c->t_dh[cur].as<float>(), c->t_agg.as<float>(), c->t_G.as<float>(),
+                                                        c->t_B.as<float>(), c->t_dagg.as<float>(), c->t_dhpart.as<float>());
+        };
+        if (c->math_acc) gates(k_bwd_gates<true>); else gates(k_bwd_gates<false>);
         LAUNCH_CHECK(c);
-        if (it > 0)
-            k_bwd_msgs<true><<<bgrid, BW_TPB, 0, st>>>(idx, out, w, At, c->t_B.as<float>(), c->t_dagg.as<float>(), c->t_dhpart.as<float>(),
-                                                       c->t_dB.as<float>(), c->t_dA.as<float>(), c->t_dh[cur ^ 1].as<float>());
-        else
-            k_bwd_msgs<false><<<bgrid, BW_TPB, 0, st>>>(idx, out, w, At, c->t_B.as<float>(), c->t_dagg.as<float>(), c->t_dhpart.as<float>(),
-                                                        c->t_dB.as<float>(), c->t_dA.as<float>(), nullptr);
+        auto msgs = [&](auto kern, float* dh_prev) {
+            kern<<<bgrid, BW_TPB, 0, st>>>(idx, out, w, At, c->t_B.as<float>(), c->t_dagg.as<float>(), c->t_dhpart.as<float>(),
+                                           c->t_dB.as<float>(), c->t_dA.as<float>(), dh_prev);
+        };
+        if (it > 0) {
+            if (c->math_acc) msgs(k_bwd_msgs<true, true>, c->t_dh[cur ^ 1].as<float>());
+            else msgs(k_bwd_msgs<true, false>, c->t_dh[cur ^ 1].as<float>());
+        } else {
+            if (c->math_acc) msgs(k_bwd_msgs<false, true>, nullptr);
+            else msgs(k_bwd_msgs<false, false>, nullptr);
+        }
         LAUNCH_CHECK(c);
         WgradIter wi{ht, c->t_agg.as<float>(), c->t_G.as<float>(), c->t_dB.as<float>(), c->t_dA.as<float>()};
         k_wgrad<<<wg_grid, WG_TPB, 0, st>>>(idx, wi, (rows + WG_ROWS - 1) / WG_ROWS, c->t_partials.as<float>()); LAUNCH_CHECK(c);

@@ -26,7 +26,6 @@ namespace enero {
 constexpr int BW_TPB = 128;
 constexpr float SELU_S = 1.0507009873554804934193349852946f;
 constexpr float SELU_SA = 1.7580993408473768599402175208123f;
-__device__ __forceinline__ float selu_grad_fast(float u) { return u < 0.f ? SELU_SA * ex2_approx(u * LOG2E) : SELU_S; }
 
 // out-pairs of a row (CSR by `first`), mirroring IdxTopo::seg
 struct OutTopo {
@@ -91,6 +90,7 @@ __device__ __forceinline__ float f4_dot(const float (&d)[H], int j, const float4
     return s;
 }
 
+template <bool ACC>
 __global__ void __launch_bounds__(BW_TPB)
 k_bwd_gates(const IdxTopo idx, const float* __restrict__ wflat, const float* __restrict__ ht,
             const float* __restrict__ At, const float* __restrict__ dhn, float* __restrict__ agg_out,
@@ -128,7 +128,7 @@ k_bwd_gates(const IdxTopo idx, const float* __restrict__ wflat, const float* __r
             float a[H];
             load_row(a, At + ((int64_t)list[p] + add) * H);
 #pragma unroll
-            for (int j = 0; j < H; ++j) agg[j] += selu_fast(a[j] + t[j]);
+            for (int j = 0; j < H; ++j) agg[j] += Mth<ACC>::selu(a[j] + t[j]);
         }
     }
     store_row(agg_out + r * H, agg);
@@ -161,9 +161,9 @@ k_bwd_gates(const IdxTopo idx, const float* __restrict__ wflat, const float* __r
         float dpz[4], dpr[4], dx[4], dy[4], dhz[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const float zz = sigmoid_fast(zv[i]);
-            const float rr = sigmoid_fast(rv[i]);
-            const float cc = tanh_fast(cv[i] + rr * yv[i]);
+            const float zz = Mth<ACC>::sigmoid(zv[i]);
+            const float rr = Mth<ACC>::sigmoid(rv[i]);
+            const float cc = Mth<ACC>::tanh_(cv[i] + rr * yv[i]);
             const float dz = gv[i] * (hv[i] - cc);
             const float dpc = gv[i] * (1.f - zz) * (1.f - cc * cc);
             dx[i] = dpc;
@@ -211,7 +211,7 @@ k_bwd_gates(const IdxTopo idx, const float* __restrict__ wflat, const float* __r
 }
 
 // ---- message backward of one iteration -----------------------------------------------------------------
-template <bool NEED_DH>
+template <bool NEED_DH, bool ACC>
 __global__ void __launch_bounds__(BW_TPB)
 k_bwd_msgs(const IdxTopo idx, const OutTopo out, const float* __restrict__ wflat, const float* __restrict__ At,
            const float* __restrict__ B_in, const float* __restrict__ dagg_in, const float* __restrict__ dh_part,
@@ -234,7 +234,7 @@ k_bwd_msgs(const IdxTopo idx, const OutTopo out, const float* __restrict__ wflat
             float a[H];
             load_row(a, At + ((int64_t)list[p] + add) * H);
 #pragma unroll
-            for (int j = 0; j < H; ++j) dB[j] += dagg[j] * selu_grad_fast(a[j] + B[j]);
+            for (int j = 0; j < H; ++j) dB[j] += dagg[j] * Mth<ACC>::selu_grad(a[j] + B[j]);
         }
     }
     {
@@ -248,7 +248,7 @@ k_bwd_msgs(const IdxTopo idx, const OutTopo out, const float* __restrict__ wflat
             load_row(bs, B_in + dst * H);
             load_row(ds, dagg_in + dst * H);
 #pragma unroll
-            for (int j = 0; j < H; ++j) dA[j] += ds[j] * selu_grad_fast(Ai[j] + bs[j]);
+            for (int j = 0; j < H; ++j) dA[j] += ds[j] * Mth<ACC>::selu_grad(Ai[j] + bs[j]);
         }
     }
     store_row(dB_out + r * H, dB);
@@ -275,16 +275,7 @@ k_readout_bwd(const GraphsTopo gr, const float* __restrict__ wflat, const float*
     int64_t r0, r1, o;
     if (!gr.range(g, r0, r1, o)) return;
     float acc[H];
-#pragma unroll
-    for (int j = 0; j < H; ++j) acc[j] = 0.f;
-    for (int64_t r = r0 + lane; r < r1; r += 32) {
-        float v[H];
-        load_row(v, hT + r * H);
-#pragma unroll
-        for (int j = 0; j < H; ++j) acc[j] += v[j];
-    }
-#pragma unroll
-    for (int j = 0; j < H; ++j) acc[j] = warp_sum(acc[j]);
+    graph_row_sum(acc, hT, r0, r1, lane);
     const float* R1 = sr; const float* B1 = sr + (W_R1_B - W_R1_K);
     const float* R2 = sr + (W_R2_K - W_R1_K); const float* B2 = sr + (W_R2_B - W_R1_K);
     const float* R3 = sr + (W_R3_K - W_R1_K);

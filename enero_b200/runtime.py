@@ -86,6 +86,17 @@ class Context:
     def stream(self) -> int:
         return int(self._lib.enero_ctx_stream(self._h) or 0)
 
+    @property
+    def math(self) -> str:
+        """'fast' (MUFU ex2/rcp forms: the default) or 'accurate' (libdevice expf/tanhf, IEEE division)"""
+        return "accurate" if self._lib.enero_ctx_get_math(self._h) == _lib.MATH_ACCURATE else "fast"
+
+    @math.setter
+    def math(self, mode: str):
+        if mode not in ("fast", "accurate"):
+            raise ValueError("math mode must be 'fast' or 'accurate'")
+        _lib.check(self._lib.enero_ctx_set_math(self._h, _lib.MATH_ACCURATE if mode == "accurate" else _lib.MATH_FAST))
+
     def profile_begin(self):
         _lib.check(self._lib.enero_ctx_profile_begin(self._h))
 

@@ -35,6 +35,17 @@ extern "C" {
 #define ENERO_ACTOR 0
 #define ENERO_CRITIC 1
 
+/* transcendental arithmetic of the message-passing kernels (selu / sigmoid / tanh of actorPPOmiddR.py:45-63):
+ * FAST = MUFU.EX2 / MUFU.RCP forms (~1e-6 relative per call); ACCURATE = libdevice expf / tanhf and IEEE division,
+ * written as TensorFlow's functors write them.  Measured on 17 812 decisions against the fp64 arbiter
+ * (profiles/r02_parity_sweep.json): both modes hold every logit element-wise within
+ * 1e-5 * |x| + 1e-5 of the arbiter and of the numpy oracle, both pick the arbiter's arg-max on every decision, and
+ * neither is closer to the arbiter than the other (fp32 summation rounding dominates, not the transcendentals);
+ * ACCURATE costs 46 % of the throughput, so FAST is the default. */
+#define ENERO_MATH_FAST 0
+#define ENERO_MATH_ACCURATE 1
+#define ENERO_MATH_DEFAULT ENERO_MATH_FAST
+
 #define ENERO_H 20            /* link_state_dim  (train_Enero_3top_script.py:83) */
 #define ENERO_NPARAMS 4201    /* parameters per model, Keras variable order (:238-248) */
 #define ENERO_GRAD_STRIDE 4204  /* floats between the actor and critic halves of the gradient buffer */
@@ -57,6 +68,10 @@ int enero_ctx_sync(enero_ctx* ctx);
 int64_t enero_ctx_launch_count(enero_ctx* ctx);
 /* raw cudaStream_t the ctx launches on (for CUDA-event timing by the caller) */
 void* enero_ctx_stream(enero_ctx* ctx);
+/* math mode of every later launch on this ctx (ENERO_MATH_*); the environment variable ENERO_MATH=fast|accurate
+ * sets the mode a new ctx starts with.  get returns the mode, or -1 for a null ctx. */
+int enero_ctx_set_math(enero_ctx* ctx, int mode);
+int enero_ctx_get_math(enero_ctx* ctx);
 
 /* per-launch CUDA-event timing of the dominant kernel (k_mp_iter) between begin and end:
  * total milliseconds and number of launches (bench.py's roofline leg; off by default) */

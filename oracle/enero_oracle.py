@@ -354,6 +354,59 @@ def critic_forward(w, link_state, first, second, num_edges, T=5):
     return readout(w, g)
 
 
+# --------------------------------------------------------------------------
+# fp64 arbiter: the same formulas (actorPPOmiddR.py:45-69) evaluated in double precision on the fp32
+# inputs and fp32 weights (both exactly representable).  Its rounding error (~1e-15) is far below any
+# fp32 implementation's, so when two fp32 implementations (TensorFlow's Eigen kernels, this file's numpy
+# restatement, the CUDA kernels) disagree in the last bits, the distance to this value says which is closer
+# to what the reference's formula means.  Used by tests/ and tools/parity_report.py only.
+# --------------------------------------------------------------------------
+def _selu64(x):
+    return np.where(x < 0, (float(SELU_SCALE) * float(SELU_ALPHA)) * np.expm1(np.minimum(x, 0.0)), float(SELU_SCALE) * x)
+
+
+def message_passing64(w, link_state, first, second, num_edges, T=5):
+    h = np.asarray(link_state, dtype=np.float64)
+    wm, bm, kx, kh, b = (np.asarray(w[k], dtype=np.float64) for k in
+                         ("msg_kernel", "msg_bias", "gru_kernel", "gru_recurrent_kernel", "gru_bias"))
+    for _ in range(T):
+        m = _selu64(np.concatenate([h[first], h[second]], axis=1) @ wm + bm)
+        agg = np.zeros((num_edges, h.shape[1]))
+        np.add.at(agg, second, m)
+        x = agg @ kx + b[0]
+        y = h @ kh + b[1]
+        z = 1.0 / (1.0 + np.exp(-(x[:, :20] + y[:, :20])))
+        r = 1.0 / (1.0 + np.exp(-(x[:, 20:40] + y[:, 20:40])))
+        hh = np.tanh(x[:, 40:] + r * y[:, 40:])
+        h = z * h + (1.0 - z) * hh
+    return h
+
+
+def readout64(w, g):
+    a = _selu64(g @ np.asarray(w["r1_kernel"], np.float64) + np.asarray(w["r1_bias"], np.float64))
+    a = _selu64(a @ np.asarray(w["r2_kernel"], np.float64) + np.asarray(w["r2_bias"], np.float64))
+    return a @ np.asarray(w["r3_kernel"], np.float64) + np.asarray(w["r3_bias"], np.float64)
+
+
+def actor_forward64(w, link_state, graph_id, first, second, num_edges, T=5):
+    h = message_passing64(w, link_state, first, second, num_edges, T)
+    G = int(graph_id.max()) + 1
+    g = np.zeros((G, h.shape[1]))
+    np.add.at(g, graph_id, h)
+    return readout64(w, g)
+
+
+def critic_forward64(w, link_state, first, second, num_edges, T=5):
+    h = message_passing64(w, link_state, first, second, num_edges, T)
+    return readout64(w, h.sum(axis=0, keepdims=True))
+
+
+def softmax64(logits):
+    x = np.asarray(logits, dtype=np.float64).reshape(-1)
+    e = np.exp(x - x.max())
+    return e / e.sum()
+
+
 def softmax(logits):
     x = np.asarray(logits, dtype=np.float32).reshape(-1)
     e = np.exp(x - x.max())

@@ -34,6 +34,7 @@ CASES = [
     ("eli20", 20, 30, 1001, 2, True, False),     # cfg1: EliBackbone-sized
     ("tri9", 9, 13, 1007, 2, False, True),
     ("zoo30", 30, 50, 1000, 1, True, False),     # cfg2: 100-link
+    ("hur24", 24, 37, 1002, 1, True, False),     # cfg3: HurricaneElectric-sized (the topology of workloads.run_cfg3)
 ]
 
 

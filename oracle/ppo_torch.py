@@ -20,18 +20,21 @@ def selu(x):
     return torch.where(x < 0, SELU_SCALE_ALPHA * (torch.exp(torch.clamp(x, max=0.0)) - 1.0), SELU_SCALE * x)
 
 
-def to_params(weights):
-    """dict name -> numpy  ==>  dict name -> leaf tensors requiring grad (fp32)"""
-    return {k: torch.tensor(np.asarray(weights[k], dtype=np.float32), requires_grad=True) for k in orc.WEIGHT_NAMES}
+def to_params(weights, dtype=torch.float32):
+    """dict name -> numpy  ==>  dict name -> leaf tensors requiring grad.  dtype=torch.float64 gives the
+    fp64 ARBITER of the same formulas on the same fp32 inputs: when the CUDA kernels and this fp32
+    restatement disagree in the last bits, the distance to the fp64 result says which is closer."""
+    return {k: torch.tensor(np.asarray(weights[k], dtype=np.float32), dtype=dtype, requires_grad=True) for k in orc.WEIGHT_NAMES}
 
 
 def message_passing(w, link_state, first, second, num_edges, T=5):
     """actorPPOmiddR.py:45-63 / criticPPO.py:41-58"""
-    h = link_state
+    dt = w["msg_kernel"].dtype
+    h = link_state.to(dt)
     for _ in range(T):
         cat = torch.cat([h[first], h[second]], dim=1)
         m = selu(cat @ w["msg_kernel"] + w["msg_bias"])
-        agg = torch.zeros((num_edges, 20), dtype=torch.float32).index_add(0, second, m)
+        agg = torch.zeros((num_edges, 20), dtype=dt).index_add(0, second, m)
         x = agg @ w["gru_kernel"] + w["gru_bias"][0]
         y = h @ w["gru_recurrent_kernel"] + w["gru_bias"][1]
         z = torch.sigmoid(x[:, :20] + y[:, :20])
@@ -54,7 +57,7 @@ def actor_logits(w, batch):
     gid = torch.tensor(batch["graph_id"].astype(np.int64))
     h = message_passing(w, ls, first, second, batch["num_edges"])
     G = int(batch["graph_id"].max()) + 1
-    g = torch.zeros((G, 20), dtype=torch.float32).index_add(0, gid, h)
+    g = torch.zeros((G, 20), dtype=h.dtype).index_add(0, gid, h)
     return readout(w, g).reshape(-1)
 
 
@@ -73,9 +76,10 @@ def minibatch_loss(wa, wc, samples, entropy_beta, clipping_val=0.1):
     for s in samples:
         logits = actor_logits(wa, s)
         p = torch.softmax(logits, dim=0)
-        old_act = torch.tensor(np.asarray(s["old_act"], dtype=np.float32))
-        old_p = torch.tensor(np.asarray(s["old_policy_probs"], dtype=np.float32))
-        adv = torch.tensor(np.float32(s["advantage"]))
+        dt = logits.dtype
+        old_act = torch.tensor(np.asarray(s["old_act"], dtype=np.float32), dtype=dt)
+        old_p = torch.tensor(np.asarray(s["old_policy_probs"], dtype=np.float32), dtype=dt)
+        adv = torch.tensor(np.float32(s["advantage"]), dtype=dt)
         newp = torch.sum(old_act * p)
         ratio = torch.exp(torch.log(newp) - torch.log(torch.sum(old_act * old_p)))
         surr1 = -ratio * adv
@@ -83,15 +87,15 @@ def minibatch_loss(wa, wc, samples, entropy_beta, clipping_val=0.1):
         actor_losses.append(torch.maximum(surr1, surr2))
         entropies.append(-torch.sum(torch.log(p) * p))
         v = critic_value(wc, s["link_state_critic"], s["first_critic"], s["second_critic"], s["num_edges_critic"])
-        critic_losses.append((torch.tensor(np.float32(s["return"])) - v) ** 2)
+        critic_losses.append((torch.tensor(np.float32(s["return"]), dtype=v.dtype) - v) ** 2)
     critic_loss = torch.stack(critic_losses).mean()
     final_entropy = torch.stack(entropies).mean()
     actor_loss = torch.stack(actor_losses).mean() - entropy_beta * final_entropy
     return actor_loss + critic_loss, actor_loss, critic_loss, final_entropy
 
 
-def flat(tensors):
-    return np.concatenate([np.asarray(t, dtype=np.float32).reshape(-1) for t in tensors])
+def flat(tensors, dtype=np.float32):
+    return np.concatenate([np.asarray(t, dtype=dtype).reshape(-1) for t in tensors])
 
 
 def gradients(wa, wc, samples, entropy_beta):
@@ -101,8 +105,9 @@ def gradients(wa, wc, samples, entropy_beta):
             t.grad = None
     total, al, cl, ent = minibatch_loss(wa, wc, samples, entropy_beta)
     total.backward()
-    ga = flat([wa[k].grad.numpy() if wa[k].grad is not None else np.zeros(tuple(wa[k].shape)) for k in orc.WEIGHT_NAMES])
-    gc = flat([wc[k].grad.numpy() if wc[k].grad is not None else np.zeros(tuple(wc[k].shape)) for k in orc.WEIGHT_NAMES])
+    nd = np.float64 if wa["msg_kernel"].dtype == torch.float64 else np.float32
+    ga = flat([wa[k].grad.numpy() if wa[k].grad is not None else np.zeros(tuple(wa[k].shape)) for k in orc.WEIGHT_NAMES], nd)
+    gc = flat([wc[k].grad.numpy() if wc[k].grad is not None else np.zeros(tuple(wc[k].shape)) for k in orc.WEIGHT_NAMES], nd)
     return ga, gc, float(al.detach()), float(cl.detach()), float(ent.detach())
 
 

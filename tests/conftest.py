@@ -10,7 +10,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-CASE_NAMES = ("tri9", "tiny12", "eli20", "zoo30")
+CASE_NAMES = ("tri9", "tiny12", "eli20", "zoo30", "hur24")
 
 
 def pytest_configure(config):

@@ -2,10 +2,19 @@
 reference-recorded golden fixtures.
 
 Tolerances: integer / fp64 quantities (indices, loads, utilisations, rewards, action and
-move sequences) bit-exact; fp32 logits / probabilities / values within 1e-5 relative, as
-BASELINE.json's north_star states.  "Relative" is taken against the largest magnitude of the
-output vector (a logit is a sum of O(1) terms, so one that happens to land near zero still
-carries the fp32 rounding of those terms): |got - want| <= 1e-5 * max(|want|, 1e-2).
+move sequences) bit-exact.  fp32 logits and values ELEMENT-WISE within 1e-5 relative, as
+BASELINE.json's north_star states, with an absolute floor:
+        |got - want| <= 1e-5 * |want| + 1e-5        for every element.
+Why the floor is 1e-5: a logit is a sum over ~100 link states and 5 iterations of O(1) terms, each with its
+own fp32 rounding, so its error does not shrink when the sum happens to land near zero.  The fp64 arbiter
+(oracle.actor_forward64) measures that rounding floor on 17 812 decisions (tools/parity_sweep.py,
+profiles/r02_parity_sweep.json): the numpy fp32 oracle itself needs a floor of 1.02e-5 to stay within
+rtol 1e-5 of the arbiter, the CUDA path 8.3e-6 (fast math) / 6.6e-6 (accurate math) -- no two fp32
+implementations of this network (TensorFlow's included) can be pinned to each other more tightly.  It is also
+torch.testing's default absolute tolerance for fp32.
+Probabilities are soft-max outputs: an absolute logit error d becomes a relative probability error
+of up to 2d, so they are held, purely relatively, to the propagated bound 2 * (1e-5 * max|logit| + ATOL)
+(north_star lists logits, values, utilisations and rewards, not probabilities, under the 1e-5 rule).
 """
 import numpy as np
 import pytest
@@ -16,17 +25,19 @@ from oracle import enero_oracle as orc
 pytestmark = pytest.mark.gpu
 
 RTOL = 1e-5
+ATOL = 1e-5
 
 
-def assert_close(got, want, amplification=1.0):
-    """amplification: soft-max turns an absolute logit error d into a relative probability error d,
-    so probabilities are compared with the 1e-5 scaled by max(1, max|logit|)."""
+def assert_close(got, want, rtol=RTOL, atol=ATOL):
     got = np.asarray(got, dtype=np.float64).reshape(-1)
     want = np.asarray(want, dtype=np.float64).reshape(-1)
     assert got.shape == want.shape
-    scale = max(float(np.abs(want).max()), 1e-2) * max(1.0, amplification)
-    err = float(np.abs(got - want).max())
-    assert err <= RTOL * scale, "max |diff| %.3e > %.1e * %.3e" % (err, RTOL, scale)
+    np.testing.assert_allclose(got, want, rtol=rtol, atol=atol)
+
+
+def assert_probs_close(got, want, logits):
+    """soft-max propagation of the logit tolerance: |dp/p| <= 2 max|dlogit|, purely relative"""
+    assert_close(got, want, rtol=2 * (RTOL * float(np.abs(logits).max()) + ATOL), atol=1e-9)
 
 
 @pytest.fixture(scope="module")
@@ -126,7 +137,7 @@ def test_decide_batch_matches_oracle_and_golden(ctx, trio, weights):
             k = len(dc["logits"])
             assert nK[b] == k
             assert_close(logits[b, :k], dc["logits"])
-            assert_close(probs[b, :k], dc["probs"], amplification=np.abs(dc["logits"]).max())
+            assert_probs_close(probs[b, :k], dc["probs"], dc["logits"])
             assert not logits[b, k:].any() and not probs[b, k:].any()
             assert action[b] == ep["steps"][b]["action"]
 
@@ -203,7 +214,7 @@ def test_stepwise_env_matches_trace(ctx, trio):
     eb.reset(np.array([case["tms"][str(ep["tm_id"])]]))
     for k, (stp, dc) in enumerate(zip(ep["steps"][:6], ep["decisions"][:6])):
         probs, nK = eb.policy()
-        assert_close(probs[0, :nK[0]], dc["probs"], amplification=np.abs(dc["logits"]).max())
+        assert_probs_close(probs[0, :nK[0]], dc["probs"], dc["logits"])
         reward, done = eb.step([stp["action"]])
         assert reward[0] == stp["reward"] and bool(done[0]) == stp["done"]
         st = eb.state()
@@ -309,37 +320,52 @@ def test_greedy_actions_many_tms(ctx, weights, name, n_tms, tmp_path_factory):
     eb.close()
 
 
-def test_tma_staged_tile_kernel_is_bit_identical(tmp_path):
-    """the opt-in k_mp_tile variant (ENERO_MP_TPB) shares the FMA phases with k_mp_iter:
-    same logits bit for bit, on a topology with the Q1 offset quirk (zoo30: max(second)+1 < E)"""
-    import json
-    import os
-    import subprocess
-    import sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    code = (
-        "import sys, json, os, tempfile; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
-        "import numpy as np\n"
-        "from conftest import case_graph_file, golden_weights, load_case\n"
-        "from enero_b200.runtime import Context\n"
-        "from enero_b200.topology import Topology\n"
-        "from enero_b200.engine import EpisodeBatch\n"
-        "from oracle import enero_oracle as orc\n"
-        "w = golden_weights(); c = Context(0); c.upload_weights(0, [w[k] for k in orc.WEIGHT_NAMES])\n"
-        "case = load_case('zoo30'); t = Topology(case_graph_file(case, tempfile.mkdtemp()), K=100)\n"
-        "tm = np.array(case['tms']['0'])\n"
-        "eb = EpisodeBatch(c, t, 3); eb.reset(np.stack([tm, tm * 2, np.floor(tm / 2)]))\n"
-        "for _ in range(4):\n"
-        "    probs, nK = eb.policy(); eb.step(None)\n"
-        "print(json.dumps({'probs': probs.view(np.uint32).tolist(), 'act': eb.history()[0][:, :4].tolist()}))\n"
-        % (root, os.path.join(root, "tests")))
-    outs = []
-    for tpb in ("", "128", "160"):
-        env = dict(os.environ)
-        env.pop("ENERO_MP_TPB", None)
-        if tpb:
-            env["ENERO_MP_TPB"] = tpb
-        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
-        assert r.returncode == 0, r.stderr[-2000:]
-        outs.append(json.loads(r.stdout.strip().splitlines()[-1]))
-    assert outs[0] == outs[1] == outs[2]
+def test_math_modes_against_fp64_arbiter(ctx, trio, weights):
+    """Both math modes (fast = default, accurate = opt-in) against the fp64 arbiter (oracle.actor_forward64) on the
+    same states, at the same element-wise tolerance as against the fp32 oracle; both must pick the arbiter's
+    arg-max.  tools/parity_sweep.py runs this comparison over 692 episodes (profiles/r02_parity_sweep.json)."""
+    case, topo, ot = trio
+    ep = case["episodes"][0]
+    tm = np.array(case["tms"][str(ep["tm_id"])])
+    decs = ep["decisions"][:12]
+    loads = np.array([dc["loads_before"] for dc in decs])
+    sd = np.array([[dc["s"], dc["d"]] for dc in decs], dtype=np.int32)
+    bw = np.array([tm[dc["s"], dc["d"]] for dc in decs])
+    truth = []
+    env = orc.Env16(ot)
+    env.tm = tm
+    for b, dc in enumerate(decs):
+        env.loads = loads[b].copy()
+        bt = orc.batch_candidates(env.candidate_features(dc["s"], dc["d"]), ot.first, ot.second)
+        truth.append(orc.actor_forward64(weights, bt["link_state"], bt["graph_id"], bt["first"], bt["second"], bt["num_edges"]).reshape(-1))
+    before = ctx.math
+    try:
+        for mode in ("accurate", "fast"):
+            ctx.math = mode
+            logits, _, nK, action = ctx.decide_batch(topo, loads, sd, bw)
+            for b, t in enumerate(truth):
+                np.testing.assert_allclose(logits[b, :nK[b]], t, rtol=RTOL, atol=ATOL)
+                top2 = np.sort(t)[-2:]
+                if top2[1] - top2[0] > 4 * ATOL:           # the arbiter's arg-max, unless its two best are within the floor
+                    assert action[b] == int(np.argmax(t))
+    finally:
+        ctx.math = before
+
+
+def test_accurate_math_greedy_episode_identical(ctx, weights, tmp_path_factory):
+    """the opt-in accurate math mode reproduces the oracle's greedy action sequences too (eli20-sized graph)"""
+    from enero_b200.engine import EpisodeBatch
+    case, topo, ot = _topos("tiny12", tmp_path_factory)
+    tms = np.array([case["tms"][str(ep["tm_id"])] for ep in case["episodes"]])
+    before = ctx.math
+    try:
+        ctx.math = "accurate"
+        eb = EpisodeBatch(ctx, topo, len(tms))
+        eb.reset(tms)
+        eb.run_greedy()
+        act, _, _ = eb.history()
+        for b, ep in enumerate(case["episodes"]):
+            assert act[b, :len(ep["steps"])].tolist() == [s["action"] for s in ep["steps"]]
+        eb.close()
+    finally:
+        ctx.math = before

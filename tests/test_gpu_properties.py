@@ -170,7 +170,7 @@ class _OracleTopoWithMids(object):
 @pytest.mark.parametrize("spec,full_oracle", [((60, 90, 1021), True), ((150, 230, 1011), False)])
 def test_large_topology_logits_match_oracle(ctx, weights, spec, full_oracle, tmp_path):
     """the fused decision path against the oracle's actor on 180- and 460-link graphs (K' up to 99 candidate
-    graphs, ~45 000 link-state rows per decision): fp32 logits within 1e-5 of the output scale, candidate
+    graphs, ~45 000 link-state rows per decision): fp32 logits element-wise within 1e-5 (floor 1e-5), candidate
     counts exact, same greedy action"""
     from enero_b200 import datasets as ds
     from enero_b200.topology import Topology
@@ -195,7 +195,6 @@ def test_large_topology_logits_match_oracle(ctx, weights, spec, full_oracle, tmp
         lg, pr, nK, act = ctx.decide_batch(topo, env.loads[None], np.array([[s, d]], np.int32), np.array([env.tm[s, d]]))
         k = int(nK[0])
         assert k == len(logits)
-        scale = max(float(np.abs(logits).max()), 1e-2)
-        assert float(np.abs(lg[0, :k] - logits).max()) <= 1e-5 * scale
+        np.testing.assert_allclose(lg[0, :k], logits, rtol=1e-5, atol=1e-5)
         assert int(act[0]) == int(np.argmax(probs))
         _, done, _, _, s, d, _, _, _ = env.step(int(np.argmax(probs)))
