@@ -82,6 +82,10 @@ SIGNATURES = {
     "enero_batch_get_ls_eligible": (C.c_int, [_vp, _vp, _vp, C.c_int]),
     "enero_batch_get_ls_state": (C.c_int, [_vp, _vp, _vp]),
     "enero_batch_ls_route_add": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_double, _vp, _vp, _vp]),
+    "enero_topo_build_ksp": (C.c_int, [_vp, C.c_int]),
+    "enero_topo_ksp_sizes": (C.c_int, [_vp, _vp]),
+    "enero_topo_get_ksp": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "enero_batch_sap": (C.c_int, [_vp, _vp, C.c_int, C.c_uint32, _vp, _vp]),
     "enero_ppo_grad_buffer": (_vp, [_vp]),
     "enero_ppo_zero_grad": (C.c_int, [_vp]),
     "enero_ppo_accumulate": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_float, C.c_float,

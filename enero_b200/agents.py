@@ -4,6 +4,7 @@
     play_middRout_games_sp                           script :162-188
     play_DRL_GNN_sp_hill_climbing_games              script :473-509  -> k_local_search
     play_sp_hill_climbing_games                      script :437-471  -> k_local_search (mode 1)
+    SAPAgent / play_sap_games                        script :511-557  -> k_sap_order + k_sap_run
 """
 from __future__ import annotations
 
@@ -93,4 +94,24 @@ def play_sp_hill_climbing_games(tm_id, dataset_folder, topology_name, percentage
     start = tt.time()
     env.reset_hill_sp(tm_id)
     final, _ = env.local_search()
+    return final, tt.time() - start
+
+
+class SAPAgent:
+    """script :511-541.  The per-demand ``act`` lives inside k_sap_run (one device loop per traffic matrix)."""
+
+    def __init__(self, env):
+        self.K = env.K
+
+
+def play_sap_games(tm_id, dataset_folder, topology_name, env=None):
+    """script :543-557 -> (final maxLinkUti[2], seconds)."""
+    if env is None:
+        env = gym_graph.make('GraphEnv-v20')
+        env.seed(SEED)
+        env.generate_environment(dataset_folder, topology_name, 100, 100)
+    env.reset(tm_id)
+    SAPAgent(env)
+    start = tt.time()
+    final, _ = env.run_sap()
     return final, tt.time() - start

@@ -17,6 +17,7 @@
 #include "enero_internal.h"
 #include "env_kernels.cuh"
 #include "gnn_kernels.cuh"
+#include "sap_kernels.cuh"
 #include "train_kernels.cuh"
 
 using namespace enero;
@@ -167,6 +168,9 @@ static void topo_free_dev(enero_topo* t) {
     cudaFree(d.cap); cudaFree(d.capf); cudaFree(d.in_off); cudaFree(d.in_first);
     cudaFree(d.sp_off); cudaFree(d.sp_edge); cudaFree(d.mid_off); cudaFree(d.mids); cudaFree(d.out_off); cudaFree(d.out_second);
     d = TopoDev();
+    cudaFree(t->d_ksp_pair_off); cudaFree(t->d_ksp_edge_off); cudaFree(t->d_ksp_edge);
+    t->d_ksp_pair_off = t->d_ksp_edge_off = t->d_ksp_edge = nullptr;
+    t->ksp_dev_stale = true;
     t->dev_id = -1;
 }
 extern "C" int enero_topo_destroy(enero_topo* t) {
@@ -457,6 +461,7 @@ struct enero_batch {
     DevBuf tm, loads, mid_cur, elig, elig_len, it, cur, cur_bw, done, steps, max_uti, max_edge, best, best_step, ospf,
         h_action, h_reward, h_max, last_reward, logits, probs, nK, action, values;
     DevBuf snap;                                    // enero_batch_snapshot image of the mutable state
+    DevBuf sap_order, sap_loads, sap_mt, sap_idx, sap_max, sap_act;   // SAP baseline scratch
     DevBuf ls_loads, ls_mid, ls_elig, ls_elig_len, ls_val, ls_nmoves, ls_moves, ls_move_val, ls_max_edge;
     std::vector<int> h_cur; std::vector<uint8_t> h_done; bool mirror_valid = false;   // host mirror of (cur, done) for action checks
     std::vector<int> h_elig, h_elig_len;           // host mirror of list_eligible_demands
@@ -896,6 +901,42 @@ extern "C" int enero_batch_get_ls_eligible(enero_batch* b, int32_t* elig, int32_
             elig[((size_t)i * cap + k) * 2 + 1] = sdi % N;
         }
     }
+    return ENERO_OK;
+}
+
+// ---- SAP baseline --------------------------------------------------------------------------------------------
+extern "C" int enero_batch_sap(enero_batch* b, const double* tms, int K, uint32_t seed, double* max_uti, int32_t* actions) {
+    ENERO_TRACE("enero_batch_sap");
+    if (!b || K < 1) return fail(ENERO_ERR_INVALID, "enero_batch_sap: bad argument");
+    if (!tms && !b->reset_done) return fail(ENERO_ERR_STATE, "enero_batch_sap: no traffic matrices (pass tms or reset the batch first)");
+    enero_ctx* c = b->c; enero_topo* t = b->t;
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    TRY(enero_topo_build_ksp(t, K));
+    if (t->ksp_dev_stale) {
+        cudaFree(t->d_ksp_pair_off); cudaFree(t->d_ksp_edge_off); cudaFree(t->d_ksp_edge);
+        TRY(upload_vec(&t->d_ksp_pair_off, t->ksp_pair_off)); TRY(upload_vec(&t->d_ksp_edge_off, t->ksp_edge_off));
+        TRY(upload_vec(&t->d_ksp_edge, t->ksp_edge));
+        t->ksp_dev_stale = false;
+    }
+    const int B = b->B, N = t->N, NN = b->NN, D = NN - N, E = t->E;
+    for (int sdi = 0; sdi < NN; ++sdi)
+        if (sdi / N != sdi % N && t->ksp_pair_off[sdi + 1] == t->ksp_pair_off[sdi])
+            return fail(ENERO_ERR_INVALID, "enero_batch_sap: a node pair has no path");
+    if (tms) CUDA_TRY(cudaMemcpyAsync(b->tm.p, tms, (size_t)B * NN * 8, cudaMemcpyHostToDevice, st));
+    TRY(b->sap_order.ensure((size_t)B * D * 4)); TRY(b->sap_loads.ensure((size_t)B * E * 8));
+    TRY(b->sap_mt.ensure((size_t)B * 624 * 4)); TRY(b->sap_idx.ensure((size_t)B * 4)); TRY(b->sap_max.ensure((size_t)B * 8));
+    if (actions) TRY(b->sap_act.ensure((size_t)B * D * 4));
+    k_sap_order<<<dim3((NN + 255) / 256, B), 256, 0, st>>>(N, b->tm.as<double>(), b->sap_order.as<int>()); LAUNCH_CHECK(c);
+    KspView ks{t->d_ksp_pair_off, t->d_ksp_edge_off, t->d_ksp_edge};
+    k_sap_run<<<(B + 3) / 4, 128, 0, st>>>(view_of(t), ks, B, K, seed, b->tm.as<double>(), b->sap_order.as<int>(), b->sap_loads.as<double>(),
+                                           b->sap_mt.as<uint32_t>(), b->sap_idx.as<int>(), b->sap_max.as<double>(),
+                                           actions ? b->sap_act.as<int>() : nullptr);
+    LAUNCH_CHECK(c);
+    if (max_uti) CUDA_TRY(cudaMemcpyAsync(max_uti, b->sap_max.p, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
+    if (actions) CUDA_TRY(cudaMemcpyAsync(actions, b->sap_act.p, (size_t)B * D * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (tms) { b->reset_done = false; b->policy_valid = false; }     // the resident TMs no longer belong to the last reset
     return ENERO_OK;
 }
 

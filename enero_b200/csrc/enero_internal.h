@@ -49,6 +49,13 @@ struct enero_topo {
     std::vector<int> sp_node_off, sp_node;      // SP as node lists
     std::vector<int> mid_off, mids;
     std::vector<int> cross_off, cross_sd;       // per link: (s*N+d) of direct SPs crossing it, row-major
+    // SAP baseline (Env20): K shortest simple paths per pair, built on demand (ksp.cpp)
+    int ksp_K = 0;
+    std::vector<int> ksp_pair_off;              // [N*N+1] -> path index
+    std::vector<int> ksp_path_off, ksp_node;    // node lists (for allPaths)
+    std::vector<int> ksp_edge_off, ksp_edge;    // edge-id lists (for the kernel)
+    bool ksp_dev_stale = true;
+    int* d_ksp_pair_off = nullptr; int* d_ksp_edge_off = nullptr; int* d_ksp_edge = nullptr;
     TopoDev dev;
     int dev_id = -1;                            // device the mirrors live on (-1 = none)
 };

@@ -159,6 +159,21 @@ class EpisodeBatch:
                                                       _lib.ptr(moves), _lib.ptr(vals)))
         return {"start": start, "final": final, "n_moves": n_moves, "moves": moves, "move_val": vals}
 
+    # ---- Env20 + SAPAgent ----------------------------------------------------------------------
+    def sap(self, tms=None, K: int = 5, seed: int = 9, want_actions: bool = False):
+        """play_sap_games (script_eval_on_single_topology.py:511-557) for every traffic matrix of the batch
+        (tms fp64 [B,N,N], or None for the matrices of the last reset) -> final max link utilisation [B]
+        (and, with want_actions, what SAPAgent.act returned per demand, int32 [B, N(N-1)], -1 = no path had room)."""
+        if tms is not None:
+            tms = np.ascontiguousarray(tms, dtype=np.float64)
+            if tms.shape != (self.B, self.topo.N, self.topo.N):
+                raise ValueError("tms must be [B,N,N]")
+        out = np.zeros(self.B)
+        n = self.topo.N
+        acts = np.zeros((self.B, n * (n - 1)), dtype=np.int32) if want_actions else None
+        _lib.check(self._lib.enero_batch_sap(self._h, _lib.ptr(tms), int(K), int(seed), _lib.ptr(out), _lib.ptr(acts)))
+        return (out, acts) if want_actions else out
+
     def ls_route_add(self, episode, src, dst, value):
         """allocate_to_destination_sp (value > 0) / decrease_links_utilization_sp (value < 0) on the Local-Search
         loads of one episode -> (loads fp64[E], max utilisation, its edge id or -1)."""

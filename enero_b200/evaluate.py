@@ -8,8 +8,9 @@ figure_9.py:110-125) read them unchanged:
     <out>/<diff>/<topo>/<topo>.<tm_id>.pckl        pickle of results = np.zeros(17):
         [3] Enero (DRL + LS) max utilisation   [6] number of links   [7] plain hill climbing
         [9] DRL only   [11] OSPF (initial)     [14] DRL cost (s)     [15] plain HC cost (s)
-        [16] DRL + LS cost (s)                 [4] = [8] = [12] = [13] = 1 (SA / SAP are disabled or out
-        of scope here, exactly the constants the reference stores at script :615,619)
+        [16] DRL + LS cost (s)                 [8] SAP baseline, [13] its cost (with sap=True, as
+        script_eval_on_zoo_topologies.py:622,633 and the link-failure script store them; 1 otherwise, the constant
+        script_eval_on_single_topology.py:619 stores)     [4] = [12] = 1 (simulated annealing is disabled upstream)
     <out>/<diff>/<topo>/<topo>.<tm_id>.timesteps   JSON list of (t, maxUti, time_start_DRL, DRL maxUti)
 
 Costs are wall-clock seconds of the batch divided by its size (one number for all TMs of a batch):
@@ -34,13 +35,14 @@ LS_MAX_MOVES = 1024          # recorded moves per TM (the reference's LS on <=50
 
 
 def evaluate_tms(ctx: Context, topo: Topology, tms, percentage_demands: float = 0.15, plain_hill_climbing: bool = False,
-                 batch: int = 1024):
+                 batch: int = 1024, sap: bool = False):
     """Full Enero inference for traffic matrices `tms` fp64[n,N,N] -> dict of per-TM arrays:
     ospf, drl, enero, (plain_hc), decisions, ls_moves, drl_history (list of improvement steps),
     and amortised per-TM costs cost_drl, cost_ls, cost_hc in seconds."""
     tms = np.ascontiguousarray(tms, dtype=np.float64)
     n = tms.shape[0]
     out = {k: np.zeros(n) for k in ("ospf", "drl", "enero", "plain_hc", "cost_drl", "cost_ls", "cost_hc")}
+    out["sap"], out["cost_sap"] = np.ones(n), np.ones(n)
     out["decisions"] = np.zeros(n, dtype=np.int64)
     out["ls_moves"] = np.zeros(n, dtype=np.int64)
     out["drl_steps"] = [None] * n
@@ -74,6 +76,10 @@ def evaluate_tms(ctx: Context, topo: Topology, tms, percentage_demands: float = 
                 hc = eb.local_search(None, mode=1, want_moves=False)
                 out["plain_hc"][sl] = hc["final"]
                 out["cost_hc"][sl] = (tt.perf_counter() - t3) / B
+            if sap:
+                t4 = tt.perf_counter()
+                out["sap"][sl] = eb.sap(None)
+                out["cost_sap"][sl] = (tt.perf_counter() - t4) / B
         finally:
             eb.close()
     return out
@@ -86,11 +92,11 @@ def result_record(res, i, num_links):
     r[4] = 1
     r[6] = num_links
     r[7] = res["plain_hc"][i]
-    r[8] = 1
+    r[8] = res["sap"][i]
     r[9] = res["drl"][i]
     r[11] = res["ospf"][i]
     r[12] = 1
-    r[13] = 1
+    r[13] = res["cost_sap"][i]
     r[14] = res["cost_drl"][i]
     r[15] = res["cost_hc"][i]
     r[16] = res["cost_drl"][i] + res["cost_ls"][i]
@@ -130,7 +136,7 @@ def write_records(res, tm_ids, out_folder, differentiation_str, topology_name, n
 
 
 def evaluate_topology(ctx: Context, dataset_folder, topology_name, tm_ids, out_folder=None, differentiation_str="",
-                      percentage_demands=0.15, K=100, plain_hill_climbing=True, rank=0, world=1, batch=1024):
+                      percentage_demands=0.15, K=100, plain_hill_climbing=True, rank=0, world=1, batch=1024, sap=False):
     """One topology of eval_on_single_topology.py / eval_on_zoo_topologies.py: this rank's share of
     `tm_ids` (contiguous shard, no collective) through DRL + LS (+ plain hill climbing), records written
     under out_folder if given.  -> (tm ids of this rank, result dict)."""
@@ -139,92 +145,7 @@ def evaluate_topology(ctx: Context, dataset_folder, topology_name, tm_ids, out_f
     b, e = shard_range(len(tm_ids), rank, world)
     mine = list(tm_ids[b:e])
     tms = ds.parse_demands_files([os.path.join(dataset_folder, "TM", "%s.%s.demands" % (topology_name, t)) for t in mine], topo.N)
-    res = evaluate_tms(ctx, topo, tms, percentage_demands, plain_hill_climbing, batch) if mine else None
+    res = evaluate_tms(ctx, topo, tms, percentage_demands, plain_hill_climbing, batch, sap) if mine else None
     if out_folder is not None and mine:
         write_records(res, mine, out_folder, differentiation_str, topology_name, topo.E)
     return mine, res
-
-
-# ---------------------------------------------------------------------------------------------------
-# Driver: eval_on_single_topology.py / eval_on_zoo_topologies.py (same flags), batched on the GPU
-# ---------------------------------------------------------------------------------------------------
-def best_model_id(log_file: str) -> int:
-    """last 'MAX REWD: x REWD_ID: n,' line of the training log (eval_on_single_topology.py:59-66)"""
-    model_id = 0
-    with open(log_file) as fp:
-        for line in reversed(list(fp)):
-            parts = line.split(":")
-            if parts[0] == "MAX REWD":
-                model_id = int(parts[2].split(",")[0])
-                break
-    return model_id
-
-
-def differentiation_from_log(log_file: str) -> str:
-    """'./Logs/expSP_3top_15_B_NEWLogs.txt' -> 'SP_3top_15_B_NEW' (eval_on_single_topology.py:38-40)"""
-    return os.path.basename(log_file).split("exp", 1)[1].split("Logs")[0]
-
-
-def topologies_in_range(dataset_folder, min_nodes, max_nodes, min_edge, max_edge):
-    """.graph files whose NODES / EDGES headers are inside the limits (eval_on_single_topology.py:69-90)"""
-    out = []
-    for f in sorted(os.listdir(dataset_folder)):
-        if not f.endswith(".graph"):
-            continue
-        nodes = edges = None
-        with open(os.path.join(dataset_folder, f)) as fd:
-            for line in fd:
-                if line.startswith("NODES"):
-                    nodes = int(line.split(" ")[1])
-                elif line.startswith("EDGES"):
-                    edges = int(line.split(" ")[1])
-                    break
-        if nodes is not None and edges is not None and min_nodes <= nodes <= max_nodes and min_edge <= edges <= max_edge:
-            out.append(f.split(".")[0])
-    return out
-
-
-def main(argv=None):
-    """python -m enero_b200.evaluate -d ./Logs/exp<diff>Logs.txt -f <dataset folder> -o <result folder>
-           -max_edge 100 -min_edge 5 -max_nodes 30 -min_nodes 1 [-tms 50] [-models ./models<diff>]
-    One process per GPU under torchrun; every rank takes a contiguous shard of each topology's TM ids."""
-    import argparse
-
-    from . import checkpoint as ckpt
-    from . import parallel as par
-    ap = argparse.ArgumentParser(description="batched Enero evaluation (DRL + Local Search) of a dataset folder")
-    ap.add_argument("-d", required=True, help="training log: the model with the best evaluation reward is used")
-    ap.add_argument("-f", required=True, help="dataset folder holding <topology>.graph and TM/")
-    ap.add_argument("-o", required=True, help="result folder (records go to <o><diff>/<topology>/)")
-    ap.add_argument("-max_edge", type=int, default=100)
-    ap.add_argument("-min_edge", type=int, default=5)
-    ap.add_argument("-max_nodes", type=int, default=30)
-    ap.add_argument("-min_nodes", type=int, default=1)
-    ap.add_argument("-tms", type=int, default=50, help="traffic matrices per topology (the reference evaluates 50)")
-    ap.add_argument("-models", default=None, help="checkpoint folder (default ./models<diff>)")
-    args = ap.parse_args(argv)
-    diff = differentiation_from_log(args.d)
-    model_id = best_model_id(args.d)
-    models = args.models or "./models" + diff
-    rank, world, local = par.init_process_group()
-    ctx = Context(local)
-    ctx.upload_weights(0, ckpt.load_actor_weights(os.path.join(models, "ckpt_ACT-%d" % model_id)))
-    summary = []
-    for name in topologies_in_range(args.f, args.min_nodes, args.max_nodes, args.min_edge, args.max_edge):
-        mine, res = evaluate_topology(ctx, args.f, name, list(range(args.tms)), out_folder=args.o, differentiation_str=diff,
-                                      rank=rank, world=world)
-        if res is not None:
-            summary.append({"topology": name, "tms": len(mine), "mean_ospf": float(res["ospf"].mean()),
-                            "mean_drl": float(res["drl"].mean()), "mean_enero": float(res["enero"].mean())})
-    allsum = par.gather_records(summary)
-    if rank == 0:
-        print(json.dumps({"model_id": model_id, "differentiation_str": diff, "n_gpus": world, "topologies": allsum}))
-    ctx.close()
-    if world > 1:
-        import torch.distributed as dist
-        dist.barrier()
-        dist.destroy_process_group()
-
-
-if __name__ == "__main__":
-    main()

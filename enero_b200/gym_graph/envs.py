@@ -271,3 +271,40 @@ class Env15(_EnvBase):
                 self.sp_middlepoints["%d:%d" % (s, d)] = mid
             moves.append((a, s, d, float(ls["move_val"][0, k])))
         return float(ls["final"][0]), moves
+
+
+class Env20(_EnvBase):
+    """GraphEnv-v20 (environment20.py:14-316): the environment of the SAP baseline.  K is fixed to 5 shortest simple
+    paths per pair (environment20.py:221); ``allPaths`` is the reference's table.  The episode itself is one kernel
+    over the whole sorted demand list (``run_sap``): SAPAgent.act + step for all N(N-1) demands, the per-step Python
+    round trip of play_sap_games (script :543-557) folded into the device loop."""
+
+    def generate_environment(self, dataset_folder_name, graph_topology_name, EPISODE_LENGTH, K):
+        self._generate(dataset_folder_name, graph_topology_name, EPISODE_LENGTH, K, 0.15, 3)
+        self.K = 5
+        self.allPaths = self.topology.k_shortest_paths(self.K)
+        self._seed = 9
+
+    def seed(self, seed):
+        super().seed(seed)
+        self._seed = int(seed)
+
+    def reset(self, tm_id):
+        """environment20.py:300-316 -> (TM[s][d], s, d) of the largest demand."""
+        tm = self._load_tm(tm_id)
+        n = self.numNodes
+        self.list_eligible_demands = sorted(((s, d, tm[s, d]) for s in range(n) for d in range(n) if s != d),
+                                            key=lambda tup: tup[2], reverse=True)
+        self.iter_list_elig_demn = 1
+        s, d, bw = self.list_eligible_demands[0]
+        self.patMaxBandwth = (s, d, int(bw))
+        return tm[s, d], s, d
+
+    def run_sap(self):
+        """The whole play_sap_games loop for the traffic matrix of the last reset -> (maxLinkUti[2], actions)."""
+        mx, acts = self._batch.sap(self.TM[None], K=self.K, seed=self._seed, want_actions=True)
+        return float(mx[0]), acts[0]
+
+    def step(self, action, demand, source, destination):
+        raise NotImplementedError("Env20 runs whole SAP episodes on the device: use run_sap() "
+                                  "(agents.play_sap_games does) instead of act()/step() one demand at a time")

@@ -104,5 +104,25 @@ class Topology:
         return {"%d:%d" % (s, d): self.path_nodes(s, d)
                 for s in range(self.N) for d in range(self.N) if s != d}
 
+    def k_shortest_paths(self, K: int = 5) -> dict:
+        """``Env20.allPaths`` keyed ``"s:d"`` (environment20.py:165-196): the K simple paths with the fewest hops among
+        those of at most 2*diameter links, ties in lexicographic node order; built by csrc/ksp.cpp."""
+        lib = _lib.load()
+        _lib.check(lib.enero_topo_build_ksp(self._h, int(K)))
+        sz = np.zeros(2, dtype=np.int64)
+        _lib.check(lib.enero_topo_ksp_sizes(self._h, _lib.ptr(sz)))
+        pair_off = np.zeros(self.N * self.N + 1, dtype=np.int32)
+        path_off = np.zeros(int(sz[0]) + 1, dtype=np.int32)
+        nodes = np.zeros(max(1, int(sz[1])), dtype=np.int32)
+        _lib.check(lib.enero_topo_get_ksp(self._h, _lib.ptr(pair_off), _lib.ptr(path_off), _lib.ptr(nodes)))
+        out = {}
+        for s in range(self.N):
+            for d in range(self.N):
+                if s != d:
+                    i = s * self.N + d
+                    out["%d:%d" % (s, d)] = [[int(v) for v in nodes[path_off[p]:path_off[p + 1]]]
+                                             for p in range(pair_off[i], pair_off[i + 1])]
+        return out
+
     def max_decisions(self, percentage: float = 0.15) -> int:
         return ds.max_decisions(self.N, percentage)

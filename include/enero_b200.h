@@ -206,6 +206,22 @@ int enero_batch_get_ls_state(enero_batch* b, double* loads, int32_t* max_edge);
 /* critical demands chosen by the last enero_batch_local_search reset: elig int32[B,Dcap,2] */
 int enero_batch_get_ls_eligible(enero_batch* b, int32_t* elig, int32_t* elig_len, int cap);
 
+/* ---- SAP baseline (GraphEnv-v20 + SAPAgent, results[8] of the evaluation records) -----------------------
+ * enero_topo_build_ksp: Env20.compute_SPs (environment20.py:165-196): per node pair the K simple paths with the
+ * fewest hops among those of at most 2*diameter links, ties in lexicographic node order (host precompute, idempotent).
+ * enero_topo_get_ksp: pair_off int32[N*N+1] -> path index, path_off int32[n_paths+1] -> nodes; sizes out[0]=n_paths,
+ * out[1]=total nodes. */
+int enero_topo_build_ksp(enero_topo* topo, int K);
+int enero_topo_ksp_sizes(const enero_topo* topo, int64_t out[2]);
+int enero_topo_get_ksp(const enero_topo* topo, int32_t* pair_off, int32_t* path_off, int32_t* nodes);
+/* play_sap_games (script_eval_on_single_topology.py:511-557) for the B traffic matrices tms_host fp64[B,N,N]
+ * (NULL = the matrices of the last enero_batch_reset): every demand in descending bandwidth order
+ * (environment20.py:124-163) goes to the first of its K shortest paths on which no link would exceed its capacity
+ * (SAPAgent.act), else to random.randint(0, len(paths)-1) of Python's Mersenne Twister seeded with `seed`
+ * (env.seed(SEED), environment20.py:98-100, 251-254).  Outputs (nullable): max_uti fp64[B] = maxLinkUti[2] of the
+ * last step; actions int32[B, N(N-1)] = what SAPAgent.act returned per demand (-1 = no path had room). */
+int enero_batch_sap(enero_batch* b, const double* tms_host, int K, uint32_t seed, double* max_uti, int32_t* actions);
+
 /* ---- PPO update (train_Enero_3top_script.py:264-377) ---------------------------------------
  * The gradient buffer is one device array fp32[ENERO_GRAD_FLOATS]:
  *   [0, 4201)                       d total_loss / d actor weights   (Keras variable order)

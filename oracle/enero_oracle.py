@@ -548,6 +548,64 @@ def local_search(env: Env15, current):
 
 
 # ==========================================================================
+# SAP baseline (environment20.py:124-196, 240-316; script_eval_on_single_topology.py:511-557)
+# ==========================================================================
+def k_shortest_simple_paths(topo: Topology, K=5, exhaustive=True):
+    """Env20.compute_SPs, environment20.py:165-196 -> {"s:d": [node lists]}.  exhaustive=True restates the
+    reference literally (every simple path of <= 2*diameter links, sorted by (len, nodes), first K: exponential, small
+    graphs only); exhaustive=False reaches the same list through networkx's Yen generator (paths by length; every
+    path as short as the K-th is collected before sorting)."""
+    import itertools
+    import networkx as nx
+    G = nx.DiGraph()
+    G.add_nodes_from(range(topo.N))
+    G.add_edges_from(topo.edges)
+    cutoff = 2 * nx.diameter(G)
+    out = {}
+    for n1 in range(topo.N):
+        for n2 in range(topo.N):
+            if n1 == n2:
+                continue
+            if exhaustive:
+                paths = [p for p in nx.all_simple_paths(G, source=n1, target=n2, cutoff=cutoff)]
+            else:
+                paths, gen = [], nx.shortest_simple_paths(G, n1, n2)
+                for p in gen:
+                    if len(p) - 1 > cutoff or (len(paths) >= K and len(p) > len(paths[K - 1])):
+                        break
+                    paths.append(p)
+                    paths.sort(key=lambda item: (len(item), item))
+            out["%d:%d" % (n1, n2)] = sorted(paths, key=lambda item: (len(item), item))[:K]
+    return out
+
+
+def play_sap(topo: Topology, all_paths, tm, K=5, seed=9):
+    """play_sap_games (script :543-557) with SAPAgent.act (:515-541) on Env20.reset / step (environment20.py:300-316,
+    240-291) -> (final max link utilisation, list of the agent's actions, -1 = no path had room)."""
+    import random
+    rnd = random.Random(seed)                      # env.seed(SEED): random.seed(9), environment20.py:98-100
+    tm = np.asarray(tm, dtype=np.float64)
+    demands = [(s, d, tm[s, d]) for s in range(topo.N) for d in range(topo.N) if s != d]
+    demands = sorted(demands, key=lambda tup: tup[2], reverse=True)            # :149
+    loads = np.zeros(topo.E)
+    actions = []
+    for (s, d, bw) in demands:
+        path_list = all_paths["%d:%d" % (s, d)]
+        action = -1
+        for pi, path in enumerate(path_list[:K]):
+            if all(not ((loads[topo.eid[(a, b)]] + bw) / topo.cap[topo.eid[(a, b)]] > 1) for a, b in zip(path[:-1], path[1:])):
+                action = pi
+                break
+        actions.append(action)
+        if action == -1:
+            action = rnd.randint(0, len(path_list) - 1)                          # :253
+        path = path_list[action]
+        for a, b in zip(path[:-1], path[1:]):
+            loads[topo.eid[(a, b)]] += bw
+    return _scan_max(loads, topo.cap, topo.edges)[2], actions
+
+
+# ==========================================================================
 # PPO pieces (train_Enero_3top_script.py:264-377)
 # ==========================================================================
 def get_advantages(values, masks, rewards, gamma=0.99, lmbda=0.95):

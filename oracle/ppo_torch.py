@@ -111,22 +111,22 @@ def gradients(wa, wc, samples, entropy_beta):
     return ga, gc, float(al.detach()), float(cl.detach()), float(ent.detach())
 
 
-def clip_by_global_norm(grads, clip_norm):
+def clip_by_global_norm(grads, clip_norm, dtype=np.float32):
     """tf.clip_by_global_norm over the concatenation of all gradient tensors (train script :319)"""
-    g = np.concatenate(grads).astype(np.float32)
-    norm = np.sqrt(np.sum(g.astype(np.float32) ** 2, dtype=np.float32))
-    scale = np.float32(clip_norm) / max(norm, np.float32(clip_norm))
-    return [np.float32(scale) * x for x in grads], norm
+    g = np.concatenate(grads).astype(dtype)
+    norm = np.sqrt(np.sum(g ** 2, dtype=dtype))
+    scale = dtype(clip_norm) / max(norm, dtype(clip_norm))
+    return [dtype(scale) * x.astype(dtype) for x in grads], norm
 
 
-def adam_step(theta, m, v, g, lr, step, beta1=0.9, beta2=0.999, eps=1e-5):
+def adam_step(theta, m, v, g, lr, step, beta1=0.9, beta2=0.999, eps=1e-5, dtype=np.float32):
     """Keras OptimizerV2 Adam dense update as TF's ApplyAdam CPU kernel evaluates it (fp32):
     alpha = lr * sqrt(1 - b2^t) / (1 - b1^t);  m += (g - m) * (1 - b1);  v += (g*g - v) * (1 - b2);
-    theta -= (m * alpha) / (sqrt(v) + eps);  t = optimizer.iterations + 1."""
-    f = np.float32
+    theta -= (m * alpha) / (sqrt(v) + eps);  t = optimizer.iterations + 1.  dtype=np.float64: the arbiter."""
+    f = dtype
     t = f(step)
     alpha = f(lr) * np.sqrt(f(1) - np.power(f(beta2), t)) / (f(1) - np.power(f(beta1), t))
-    m = (m + (g - m) * (f(1) - f(beta1))).astype(np.float32)
-    v = (v + (g * g - v) * (f(1) - f(beta2))).astype(np.float32)
-    theta = (theta - (m * f(alpha)) / (np.sqrt(v) + f(eps))).astype(np.float32)
+    m = (m + (g - m) * (f(1) - f(beta1))).astype(dtype)
+    v = (v + (g * g - v) * (f(1) - f(beta2))).astype(dtype)
+    theta = (theta - (m * f(alpha)) / (np.sqrt(v) + f(eps))).astype(dtype)
     return theta, m, v

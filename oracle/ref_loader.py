@@ -21,7 +21,8 @@ REFERENCE_ROOT = os.environ.get("ENERO_REFERENCE_ROOT", "/root/reference")
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
 _LIFTED = ("HILL_CLIMBING", "play_middRout_games_sp",
-           "play_DRL_GNN_sp_hill_climbing_games", "play_sp_hill_climbing_games")
+           "play_DRL_GNN_sp_hill_climbing_games", "play_sp_hill_climbing_games",
+           "SAPAgent", "play_sap_games")
 
 
 def available() -> bool:
@@ -59,7 +60,7 @@ def load_eval_functions(dataset_folder, topology_name, percentage_demands=0.15):
     mod = ast.Module(body=body, type_ignores=[])
     glb = {
         "gym": gym, "np": np, "tt": tt,
-        "ENV_SIMM_ANEAL_AGENT": "GraphEnv-v15", "SEED": 9,
+        "ENV_SIMM_ANEAL_AGENT": "GraphEnv-v15", "ENV_SAP_AGENT": "GraphEnv-v20", "SEED": 9,
         "general_dataset_folder": dataset_folder,
         "graph_topology_name": topology_name,
         "EPISODE_LENGTH_MIDDROUT": 100, "NUM_ACTIONS": 100,

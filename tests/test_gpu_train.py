@@ -1,11 +1,15 @@
 """GPU parity of the PPO update (kernel family 5: backward kernels, PPO loss head, global-norm
 clip + Adam, GAE) against the torch-CPU restatement in oracle/ppo_torch.py.
 
-Tolerances (fp32, written here as north_star asks): a gradient tensor entry is a sum of many
-products of O(1) activations, so errors are measured against the largest magnitude of the flat
-gradient: |got - want| <= GRAD_RTOL * max|want|.  The forward/backward kernels use MUFU
-ex2/rcp approximations (about 1e-6 relative per transcendental), hence 1e-4 rather than 1e-5 for
-gradients; losses, the clip scale and the Adam update are compared at 1e-5.
+Tolerances (fp32, written here as north_star asks).  A gradient entry is a sum over thousands of link-state
+rows of products of O(1) activations with cancellation, so a per-element relative error is meaningless for the
+entries that cancel to ~0; errors are measured against the largest magnitude of the flat gradient:
+        |got - want| <= tol * max|want|.
+The fp64 arbiter (the same torch graph in float64, oracle/ppo_torch.to_params(dtype=float64)) shows where fp32
+itself stands: torch's own fp32 gradients are up to 1.3e-5 * max|g| away from the fp64 ones
+(tools/train_parity.py, profiles/r02_train_parity.json), the CUDA path 1.4e-6 ... 1.45e-5 in either math mode.
+So the test holds the CUDA gradients to the arbiter at  max(1e-5, 2 x torch-fp32's own distance to it)
+and to the fp32 restatement at 2e-5 (two fp32 roundings apart); losses and the clip scale at 1e-5.
 """
 import numpy as np
 import pytest
@@ -16,7 +20,8 @@ from oracle import ppo_torch as ppo_o
 
 pytestmark = pytest.mark.gpu
 
-GRAD_RTOL = 1e-4
+GRAD_TOL_ARBITER = 1e-5     # vs fp64, unless torch fp32 itself is further away (then 2x its distance)
+GRAD_TOL_FP32 = 2e-5        # vs the fp32 restatement
 RTOL = 1e-5
 BETA = 0.01
 
@@ -79,10 +84,15 @@ def agent(weights):
     ctx.close()
 
 
-def _assert_grad(got, want, what):
-    scale = float(np.abs(want).max())
-    err = float(np.abs(got.astype(np.float64) - want.astype(np.float64)).max())
-    assert err <= GRAD_RTOL * scale, "%s: max |diff| %.3e > %.1e * %.3e" % (what, err, GRAD_RTOL, scale)
+def _dist(a, b):
+    return float(np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64)).max())
+
+
+def _assert_grad(got, fp32, fp64, what):
+    scale = float(np.abs(fp64).max())
+    tol = max(GRAD_TOL_ARBITER, 2.0 * _dist(fp32, fp64) / scale)
+    assert _dist(got, fp64) <= tol * scale, "%s vs fp64 arbiter: %.3e > %.2e * %.3e" % (what, _dist(got, fp64), tol, scale)
+    assert _dist(got, fp32) <= GRAD_TOL_FP32 * scale, "%s vs torch fp32: %.3e > %.1e * %.3e" % (what, _dist(got, fp32), GRAD_TOL_FP32, scale)
 
 
 @pytest.mark.parametrize("names,n", [(("tri9",), 6), (("tiny12",), 9), (("eli20", "zoo30"), 7)])
@@ -95,66 +105,96 @@ def test_minibatch_gradients(agent, weights, names, n, tmp_path_factory):
         _, o, g = _rollout(name, weights, n, 11 + i, tmp_path_factory.mktemp("r" + name))
         o_all += o
         g_all += g
+    import torch
     ag.memory = g_all
-    ga, gc, sums = ag.gradients(np.arange(len(g_all)))
     wa, wc = ppo_o.to_params(weights), ppo_o.to_params(cw)
     oa, oc, al, cl, ent = ppo_o.gradients(wa, wc, o_all, BETA)
+    ta, tc, *_ = ppo_o.gradients(ppo_o.to_params(weights, torch.float64), ppo_o.to_params(cw, torch.float64), o_all, BETA)
     m = len(g_all)
-    np.testing.assert_allclose(sums[1] / m, ent, rtol=RTOL)
-    np.testing.assert_allclose(sums[0] / m - BETA * sums[1] / m, al, rtol=RTOL, atol=1e-6)
-    np.testing.assert_allclose(sums[2] / m, cl, rtol=RTOL)
-    _assert_grad(ga, oa, "actor gradient")
-    _assert_grad(gc, oc, "critic gradient")
-    # per-tensor check so that a small tensor cannot hide behind a large one
-    o = 0
-    for k in orc.WEIGHT_NAMES:
-        sz = weights[k].size
-        if np.abs(oa[o:o + sz]).max() > 1e-3 * np.abs(oa).max():
-            _assert_grad(ga[o:o + sz], oa[o:o + sz], "actor " + k)
-        if np.abs(oc[o:o + sz]).max() > 1e-3 * np.abs(oc).max():
-            _assert_grad(gc[o:o + sz], oc[o:o + sz], "critic " + k)
-        o += sz
+    before = ag.context.math
+    try:
+        for mode in ("fast", "accurate"):
+            ag.context.math = mode
+            ga, gc, sums = ag.gradients(np.arange(len(g_all)))
+            np.testing.assert_allclose(sums[1] / m, ent, rtol=RTOL)
+            np.testing.assert_allclose(sums[0] / m - BETA * sums[1] / m, al, rtol=RTOL, atol=1e-6)
+            np.testing.assert_allclose(sums[2] / m, cl, rtol=RTOL)
+            _assert_grad(ga, oa, ta, mode + " actor gradient")
+            _assert_grad(gc, oc, tc, mode + " critic gradient")
+            # per-tensor check so that a small tensor cannot hide behind a large one
+            o = 0
+            for k in orc.WEIGHT_NAMES:
+                sz = weights[k].size
+                if np.abs(ta[o:o + sz]).max() > 1e-2 * np.abs(ta).max():
+                    _assert_grad(ga[o:o + sz], oa[o:o + sz], ta[o:o + sz], mode + " actor " + k)
+                if np.abs(tc[o:o + sz]).max() > 1e-2 * np.abs(tc).max():
+                    _assert_grad(gc[o:o + sz], oc[o:o + sz], tc[o:o + sz], mode + " critic " + k)
+                o += sz
+    finally:
+        ag.context.math = before
     ag.memory = []
 
 
-def test_train_steps_match_oracle(agent, weights, tmp_path_factory):
-    """three consecutive _train_step_combined calls (gradient, clip_by_global_norm(0.5), Adam) leave the
-    same weights and slots as the oracle's restatement of Keras Adam."""
-    ag, cw = agent
-    _, o, g = _rollout("eli20", weights, 12, 5, tmp_path_factory.mktemp("steps"))
-    ag.memory = g
-    wa, wc = ppo_o.to_params(weights), ppo_o.to_params(cw)
-    fa = ppo_o.flat([weights[k] for k in orc.WEIGHT_NAMES])
-    fc = ppo_o.flat([cw[k] for k in orc.WEIGHT_NAMES])
-    slots = [np.zeros_like(fa) for _ in range(4)]       # ma, va, mc, vc
-    lr = float(ag.optimizer.learning_rate)
+def _oracle_steps(weights, cw, o, batches, lr, tdtype, ndtype):
+    """three _train_step_combined calls restated: torch gradients in `tdtype`, clip + Keras Adam in `ndtype`"""
     import torch
-    for step, inds in enumerate(([0, 1, 2, 3], [4, 5, 6, 7, 8], [9, 10, 11, 0]), start=1):
-        got = ag._train_step_combined(np.array(inds))
+    wa, wc = ppo_o.to_params(weights, tdtype), ppo_o.to_params(cw, tdtype)
+    fa = ppo_o.flat([weights[k] for k in orc.WEIGHT_NAMES], ndtype)
+    fc = ppo_o.flat([cw[k] for k in orc.WEIGHT_NAMES], ndtype)
+    slots = [np.zeros_like(fa) for _ in range(4)]       # ma, va, mc, vc
+    outs = []
+    for step, inds in enumerate(batches, start=1):
         oa, oc, al, cl, ent = ppo_o.gradients(wa, wc, [o[i] for i in inds], BETA)
-        (ca, cc), norm = ppo_o.clip_by_global_norm([oa, oc], 0.5)
-        np.testing.assert_allclose(ag.last_grad_norm, norm, rtol=1e-4)
-        np.testing.assert_allclose(got, (al, cl, ent), rtol=1e-4, atol=1e-6)
-        fa, slots[0], slots[1] = ppo_o.adam_step(fa, slots[0], slots[1], ca, lr, step)
-        fc, slots[2], slots[3] = ppo_o.adam_step(fc, slots[2], slots[3], cc, lr, step)
+        (ca, cc), norm = ppo_o.clip_by_global_norm([oa, oc], 0.5, ndtype)
+        outs.append((al, cl, ent, float(norm)))
+        fa, slots[0], slots[1] = ppo_o.adam_step(fa, slots[0], slots[1], ca, lr, step, dtype=ndtype)
+        fc, slots[2], slots[3] = ppo_o.adam_step(fc, slots[2], slots[3], cc, lr, step, dtype=ndtype)
         with torch.no_grad():
             for w, f in ((wa, fa), (wc, fc)):
                 off = 0
                 for k in orc.WEIGHT_NAMES:
                     sz = w[k].numel()
-                    w[k].copy_(torch.tensor(f[off:off + sz]).reshape(w[k].shape))
+                    w[k].copy_(torch.tensor(f[off:off + sz], dtype=tdtype).reshape(w[k].shape))
                     off += sz
+    return fa, fc, slots, outs
+
+
+def test_train_steps_match_oracle(agent, weights, tmp_path_factory):
+    """Three consecutive _train_step_combined calls (gradient, clip_by_global_norm(0.5), Keras Adam) against the
+    same three steps restated in fp32 and, as the arbiter, in fp64.  An Adam update is lr_t * m / (sqrt(v) + eps):
+    for entries whose gradient is far above eps it is ~lr * sign(g) and insensitive to rounding; for entries with
+    |g| ~ eps = 1e-5 it is g / eps, i.e. it amplifies the 1e-5-of-max|g| gradient rounding by max|g| / eps ~ 1e3.
+    Tolerances therefore: first moments (linear in g) 2e-5 of their largest entry against the fp32 restatement; the
+    weight UPDATES within max(1e-5, 2 x the fp32 restatement's own distance to the fp64 arbiter) of the arbiter,
+    measured against the largest update."""
+    import torch
+    ag, cw = agent
+    _, o, g = _rollout("eli20", weights, 12, 5, tmp_path_factory.mktemp("steps"))
+    ag.memory = g
+    lr = float(ag.optimizer.learning_rate)
+    batches = ([0, 1, 2, 3], [4, 5, 6, 7, 8], [9, 10, 11, 0])
+    fa, fc, slots, outs = _oracle_steps(weights, cw, o, batches, lr, torch.float32, np.float32)
+    ta, tc, tslots, _ = _oracle_steps(weights, cw, o, batches, lr, torch.float64, np.float64)
+    for inds, (al, cl, ent, norm) in zip(batches, outs):
+        got = ag._train_step_combined(np.array(inds))
+        np.testing.assert_allclose(ag.last_grad_norm, norm, rtol=2e-5)
+        np.testing.assert_allclose(got, (al, cl, ent), rtol=2e-5, atol=1e-6)
     ga = np.concatenate([w.reshape(-1) for w in ag.context.download_weights(0)])
     gc = np.concatenate([w.reshape(-1) for w in ag.context.download_weights(1)])
-    # three Adam steps of at most lr each: compare the *updates*, not just the weights
-    fa0 = ppo_o.flat([weights[k] for k in orc.WEIGHT_NAMES])
-    fc0 = ppo_o.flat([cw[k] for k in orc.WEIGHT_NAMES])
-    assert np.abs((ga - fa0) - (fa - fa0)).max() <= 2e-2 * np.abs(fa - fa0).max()
-    assert np.abs((gc - fc0) - (fc - fc0)).max() <= 2e-2 * np.abs(fc - fc0).max()
-    np.testing.assert_allclose(ga, fa, rtol=0, atol=3 * lr * 2e-2)
+    fa0 = ppo_o.flat([weights[k] for k in orc.WEIGHT_NAMES], np.float64)
+    fc0 = ppo_o.flat([cw[k] for k in orc.WEIGHT_NAMES], np.float64)
+    for got_w, f32, f64, w0, what in ((ga, fa, ta, fa0, "actor"), (gc, fc, tc, fc0, "critic")):
+        upd = float(np.abs(f64 - w0).max())
+        assert upd > 0.5 * lr
+        tol = max(1e-5, 2.0 * _dist(f32, f64) / upd)
+        # the weights themselves carry an fp32 representation error of 6e-8 * |w| on top of the update error
+        floor = float(np.abs(w0).max()) * 1.2e-7
+        assert _dist(got_w, f64) <= tol * upd + floor, "%s updates: %.3e > %.2e * %.3e" % (what, _dist(got_w, f64), tol, upd)
     m, v = ag.download_slots(0)
     gm = np.concatenate([x.reshape(-1) for x in m])
-    assert np.abs(gm - slots[0]).max() <= 1e-3 * np.abs(slots[0]).max()
+    gv = np.concatenate([x.reshape(-1) for x in v])
+    assert _dist(gm, slots[0]) <= 3e-5 * np.abs(slots[0]).max()
+    assert _dist(gv, slots[1]) <= 1e-4 * np.abs(slots[1]).max()
     # restore the module-scoped agent for other tests
     ag.actor.set_weights([weights[k] for k in orc.WEIGHT_NAMES])
     ag.critic.set_weights([cw[k] for k in orc.WEIGHT_NAMES])

@@ -7,7 +7,7 @@ import pickle
 import numpy as np
 import pytest
 
-from conftest import CASE_NAMES, load_case
+from conftest import GOLDEN, CASE_NAMES, load_case
 
 pytestmark = pytest.mark.gpu
 
@@ -42,8 +42,10 @@ def test_eval_worker_records(name, ctx, tmp_path):
     folder = _dataset(case, tmp_path)
     tm_ids = [ep["tm_id"] for ep in case["episodes"]]
     want_hc = all(ep.get("plain_hill_final") is not None for ep in case["episodes"])
+    sap_gold = os.path.join(GOLDEN, "sap_%s.json" % name)
+    want_sap = os.path.isfile(sap_gold)        # the reference's own Env20 ran on these cases (oracle/gen_sap_golden.py)
     mine, res = evaluate_topology(ctx, folder, name, tm_ids, out_folder=str(tmp_path) + "/out", differentiation_str="X",
-                                  plain_hill_climbing=want_hc)
+                                  plain_hill_climbing=want_hc, sap=want_sap)
     assert mine == tm_ids
     for i, ep in enumerate(case["episodes"]):
         base = os.path.join(str(tmp_path) + "/outX", name, "%s.%s" % (name, ep["tm_id"]))
@@ -54,7 +56,11 @@ def test_eval_worker_records(name, ctx, tmp_path):
         assert r[6] == len(case["topo"]["edges"])
         if want_hc:
             assert r[7] == ep["plain_hill_final"]
-        assert r[4] == r[8] == r[12] == r[13] == 1
+        assert r[4] == r[12] == 1
+        if want_sap:                               # results[8] (script_eval_on_zoo_topologies.py:622,633); TM i <-> gold episode 3*i (scale 1.0)
+            assert r[8] == json.load(open(sap_gold))["episodes"][3 * i]["max_uti"] and r[13] > 0
+        else:
+            assert r[8] == r[13] == 1
         ts = json.load(open(base + ".timesteps"))
         assert ts[0][1] == ep["ospf"] and all(row[3] == ep["best"] for row in ts)
         vals = [row[1] for row in ts]
@@ -110,30 +116,3 @@ def test_training_loop_runs_and_checkpoints(ctx, tmp_path):
                                   np.concatenate([x.reshape(-1) for x in b.adam_slots("m")]))
     st2 = run2.ppo_episode()
     assert os.path.isfile(os.path.join(cdir, "ckpt_ACT-2.index")) and np.isfinite(st2["actor_loss"])
-
-
-def test_eval_driver_cli(tmp_path):
-    """python -m enero_b200.evaluate: picks the model from the log like eval_on_single_topology.py:59-66, walks
-    the dataset folder, writes the per-TM records"""
-    import shutil
-    from conftest import GOLDEN
-    from enero_b200 import evaluate as ev
-    case = load_case("tiny12")
-    folder = _dataset(case, tmp_path)
-    logs = os.path.join(str(tmp_path), "Logs")
-    os.makedirs(logs)
-    log = os.path.join(logs, "expSP_test_15Logs.txt")
-    with open(log, "w") as fp:
-        fp.write("REW,1.0,\nMAX REWD: 1.0 REWD_ID: 7,\nREW,2.0,\nMAX REWD: 2.0 REWD_ID: 1835,\nlr,0.0001,\n")
-    assert ev.best_model_id(log) == 1835 and ev.differentiation_from_log(log) == "SP_test_15"
-    models = os.path.join(str(tmp_path), "modelsSP_test_15")
-    os.makedirs(models)
-    for ext in (".index", ".data-00000-of-00001"):
-        shutil.copy(os.path.join(GOLDEN, "ckpt_ACT-1835" + ext), os.path.join(models, "ckpt_ACT-1835" + ext))
-    assert ev.topologies_in_range(folder, 1, 30, 5, 100) == ["tiny12"]
-    assert ev.topologies_in_range(folder, 1, 5, 5, 100) == []
-    out = os.path.join(str(tmp_path), "res")
-    ev.main(["-d", log, "-f", folder, "-o", out, "-tms", str(len(case["episodes"])), "-models", models])
-    for ep in case["episodes"]:
-        r = pickle.load(open(os.path.join(out + "SP_test_15", "tiny12", "tiny12.%s.pckl" % ep["tm_id"]), "rb"))
-        assert r[3] == ep["ls"]["final"] and r[9] == ep["best"] and r[11] == ep["ospf"]
