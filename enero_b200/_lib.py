@@ -47,6 +47,7 @@ SIGNATURES = {
     "enero_ctx_get_math": (C.c_int, [_vp]),
     "enero_ctx_profile_begin": (C.c_int, [_vp]),
     "enero_ctx_profile_end": (C.c_int, [_vp, _vp, _vp]),
+    "enero_ctx_fp32_peak": (C.c_int, [_vp, _vp]),
     "enero_weights_upload": (C.c_int, [_vp, C.c_int, _vp]),
     "enero_weights_download": (C.c_int, [_vp, C.c_int, _vp]),
     "enero_topo_build": (C.c_int, [C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp, _vp, _p(_vp)]),

@@ -37,6 +37,7 @@ class PPOMIDDROUTING_SP:
         loads = np.ascontiguousarray(env.edge_state[:, 0][None])
         sd = np.array([[source, destination]], dtype=np.int32)
         bw = np.array([env.TM[source][destination]], dtype=np.float64)
+        self.actor.bind()
         logits, probs, nK, action = self.actor.context.decide_batch(t, loads, sd, bw)
         k = int(nK[0])
         self.listQValues = logits[:1, :k]
@@ -45,25 +46,43 @@ class PPOMIDDROUTING_SP:
 
 
 def play_middRout_games_sp(tm_id, env_middRout_sp, agent, timesteps):
-    """script_eval_on_single_topology.py:162-188, same return tuple."""
-    demand, source, destination = env_middRout_sp.reset(tm_id)
-    initMaxUti = env_middRout_sp.edgeMaxUti[2]
+    """script_eval_on_single_topology.py:162-188, same return tuple
+    (best maxUti, seconds, OSPF maxUti, best_routing, list_of_demands_to_change, time_start_DRL).
+
+    With this package's agent and environment the decision loop of :169-186 (actor over every candidate, arg-max,
+    env.step, best-routing bookkeeping) runs on the device without a host round trip per decision
+    (enero_batch_run_greedy: one CUDA-graph replay per decision); `timesteps` gets one row per strict improvement,
+    spaced by the amortised per-decision time.  Any other agent / environment pair goes through the reference's
+    per-decision protocol (pred_action_node_distrib_sp -> np.argmax -> env.step)."""
+    env = env_middRout_sp
+    demand, source, destination = env.reset(tm_id)
+    initMaxUti = env.edgeMaxUti[2]
     OSPF_init = initMaxUti
-    best_routing = env_middRout_sp.sp_middlepoints_step.copy()
-    list_of_demands_to_change = env_middRout_sp.list_eligible_demands
+    list_of_demands_to_change = env.list_eligible_demands
     timesteps.append((0, initMaxUti))
     start = tt.time()
     time_start_DRL = start
-    while 1:
-        action_dist, _ = agent.pred_action_node_distrib_sp(env_middRout_sp, source, destination)
+    if (isinstance(agent, PPOMIDDROUTING_SP) and hasattr(env, "run_greedy_episode")
+            and agent.actor.context is env.context):
+        agent.actor.bind()
+        ep = env.run_greedy_episode()
+        end = tt.time()
+        dt = (end - start) / max(1, len(ep["max_uti"]))
+        for k, v in enumerate(ep["max_uti"]):
+            if v < initMaxUti:
+                initMaxUti = float(v)
+                timesteps.append(((k + 1) * dt, initMaxUti))
+        return initMaxUti, end - start, OSPF_init, ep["best_routing"], list_of_demands_to_change, time_start_DRL
+    best_routing = env.sp_middlepoints_step.copy()
+    done = False
+    while not done:
+        action_dist, _ = agent.pred_action_node_distrib_sp(env, source, destination)
         action = np.argmax(action_dist)
-        reward, done, _, demand, source, destination, maxLinkUti, _, _ = env_middRout_sp.step(action, demand, source, destination)
+        _, done, _, demand, source, destination, maxLinkUti, _, _ = env.step(action, demand, source, destination)
         if maxLinkUti[2] < initMaxUti:
             initMaxUti = maxLinkUti[2]
-            best_routing = env_middRout_sp.sp_middlepoints_step.copy()
+            best_routing = env.sp_middlepoints_step.copy()
             timesteps.append((tt.time() - time_start_DRL, initMaxUti))
-        if done:
-            break
     end = tt.time()
     return initMaxUti, end - start, OSPF_init, best_routing, list_of_demands_to_change, time_start_DRL
 

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libenero_b200.so")
 SOURCES = ("topology.cpp", "ksp.cpp", "ingest.cpp", "api.cu")
-HEADERS = ("enero_internal.h", "ctx.cuh", "gnn_kernels.cuh", "env_kernels.cuh", "train_kernels.cuh", "train_api.cuh",
+HEADERS = ("enero_internal.h", "ctx.cuh", "gnn_kernels.cuh", "env_kernels.cuh", "train_kernels.cuh", "train_api.cuh", "sap_kernels.cuh", "ubench.cuh",
            os.path.join("..", "..", "include", "enero_b200.h"))
 
 NVCC_FLAGS = [

@@ -19,6 +19,7 @@
 #include "gnn_kernels.cuh"
 #include "sap_kernels.cuh"
 #include "train_kernels.cuh"
+#include "ubench.cuh"
 
 using namespace enero;
 
@@ -79,6 +80,7 @@ extern "C" int enero_ctx_create(int device, enero_ctx** out) {
     }
     CUDA_TRY(cudaFuncSetAttribute(k_bwd_gates<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWG_SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(k_bwd_gates<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWG_SMEM_BYTES));
+    if (const char* e = std::getenv("ENERO_NO_GRAPHS")) c->no_graphs = std::atoi(e) != 0;
     c->math_acc = ENERO_MATH_DEFAULT;
     if (const char* e = std::getenv("ENERO_MATH")) {
         if (!std::strcmp(e, "fast")) c->math_acc = 0;
@@ -136,6 +138,30 @@ extern "C" int enero_ctx_profile_end(enero_ctx* c, double* mp_iter_ms, int64_t* 
     if (mp_iter_launches) *mp_iter_launches = (int64_t)c->prof_ev.size();
     c->prof_ev.clear();
     c->prof = false;
+    return ENERO_OK;
+}
+
+extern "C" int enero_ctx_fp32_peak(enero_ctx* c, double* tflops) {
+    if (!c || !tflops) return fail(ENERO_ERR_INVALID, "enero_ctx_fp32_peak: null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    const int blocks = c->num_sms * 8, tpb = 256;
+    DevBuf out;
+    TRY(out.ensure((size_t)blocks * tpb * 4));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {                       // first repetition warms up; best of the rest
+        CUDA_TRY(cudaEventRecord(e0, c->stream));
+        k_ubench_ffma2<<<blocks, tpb, 0, c->stream>>>(out.as<float>(), 1.0001f, 0.5f);
+        LAUNCH_CHECK(c);
+        CUDA_TRY(cudaEventRecord(e1, c->stream));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep) best = std::min(best, ms);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *tflops = 2.0 * 16 * UB_ITERS * (double)blocks * tpb / (best * 1e-3) / 1e12;
     return ENERO_OK;
 }
 
@@ -454,8 +480,17 @@ extern "C" int enero_value_batch(enero_ctx* c, enero_topo* t, int B, const doubl
 }
 
 // ---- device-resident episode batch ---------------------------------------------------------------
+// captured greedy decision step (enero_batch_run_greedy): executable graph + what its nodes baked in
+struct GreedyGraph {
+    cudaGraphExec_t exec = nullptr;
+    const void* key[8] = {};
+    int kernels = 0;
+    void release() { if (exec) cudaGraphExecDestroy(exec); exec = nullptr; }
+};
+
 struct enero_batch {
     enero_ctx* c = nullptr; enero_topo* t = nullptr;
+    GreedyGraph graph;
     int B = 0, Dmax = 0, NN = 0; double pct = 0.15;
     bool reset_done = false, policy_valid = false;
     DevBuf tm, loads, mid_cur, elig, elig_len, it, cur, cur_bw, done, steps, max_uti, max_edge, best, best_step, ospf,
@@ -506,6 +541,7 @@ extern "C" int enero_batch_destroy(enero_batch* b) {
     if (!b) return ENERO_OK;
     cudaSetDevice(b->c->device);
     cudaStreamSynchronize(b->c->stream);
+    b->graph.release();
     delete b;
     return ENERO_OK;
 }
@@ -692,16 +728,57 @@ extern "C" int enero_batch_step_state(enero_batch* b, const int32_t* actions, do
     return ENERO_OK;
 }
 
+// One greedy decision step (decide_dev + step_dev) captured as a CUDA graph and replayed max_len times: at small
+// batch sizes the episode is bound by launch latency (10 launches per decision), and a graph replay hands the whole
+// step to the GPU in one submission.  The graph is keyed on everything its nodes baked in (buffer addresses, math
+// mode) and re-captured when any of it changes.
+static int greedy_step_graph(enero_batch* b) {
+    enero_ctx* c = b->c; const TopoDev& d = b->t->dev;
+    const int64_t rows = (int64_t)b->B * d.Kmax * d.E;
+    TRY(ensure_rows(c, rows));                                   // no allocation may happen while capturing
+    TRY(c->util.ensure((size_t)b->B * d.E * 4));
+    const void* key[8] = {c->h[0].p, c->h[1].p, c->A[0].p, c->A[1].p, c->util.p, b->loads.p,
+                          (const void*)(intptr_t)(c->math_acc + 1), (const void*)b->t->dev.in_first};
+    GreedyGraph& g = b->graph;
+    if (g.exec && !std::memcmp(key, g.key, sizeof(key))) return ENERO_OK;
+    g.release();
+    c->tile_ctr_next = 16;                                       // the captured step starts by zeroing its own tile counters
+    const int64_t l0 = c->launches;
+    CUDA_TRY(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    int r = decide_dev(c, b->t, b->B, b->loads.as<double>(), b->cur.as<int>(), b->cur_bw.as<double>(), b->done.as<uint8_t>(),
+                       b->logits.as<float>(), b->probs.as<float>(), b->nK.as<int>(), b->action.as<int>(), 5);
+    if (r == ENERO_OK) r = step_dev(b);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+    g.kernels = (int)(c->launches - l0);
+    c->launches = l0;                                            // nothing ran yet: replays are counted when launched
+    c->tile_ctr_next = 16;
+    if (r != ENERO_OK) { if (graph) cudaGraphDestroy(graph); return r; }
+    if (e != cudaSuccess) { enero_set_error(std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e)); return ENERO_ERR_CUDA; }
+    const cudaError_t e2 = cudaGraphInstantiate(&g.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e2 != cudaSuccess) { g.exec = nullptr; enero_set_error(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e2)); return ENERO_ERR_CUDA; }
+    std::memcpy(g.key, key, sizeof(key));
+    return ENERO_OK;
+}
+
 extern "C" int enero_batch_run_greedy(enero_batch* b) {
     ENERO_TRACE("enero_batch_run_greedy");
     if (!b) return fail(ENERO_ERR_INVALID, "enero_batch_run_greedy: null batch");
     if (!b->reset_done) return fail(ENERO_ERR_STATE, "enero_batch_run_greedy: reset first");
     enero_ctx* c = b->c;
     CUDA_TRY(cudaSetDevice(c->device));
-    for (int s = 0; s < b->max_len; ++s) {
-        TRY(decide_dev(c, b->t, b->B, b->loads.as<double>(), b->cur.as<int>(), b->cur_bw.as<double>(), b->done.as<uint8_t>(),
-                       b->logits.as<float>(), b->probs.as<float>(), b->nK.as<int>(), b->action.as<int>(), 5));
-        TRY(step_dev(b));
+    if (c->prof || c->no_graphs) {                               // per-launch event timing needs individual launches
+        for (int s = 0; s < b->max_len; ++s) {
+            TRY(decide_dev(c, b->t, b->B, b->loads.as<double>(), b->cur.as<int>(), b->cur_bw.as<double>(), b->done.as<uint8_t>(),
+                           b->logits.as<float>(), b->probs.as<float>(), b->nK.as<int>(), b->action.as<int>(), 5));
+            TRY(step_dev(b));
+        }
+    } else {
+        TRY(greedy_step_graph(b));
+        for (int s = 0; s < b->max_len; ++s) CUDA_TRY(cudaGraphLaunch(b->graph.exec, c->stream));
+        c->launches += (int64_t)b->graph.kernels * b->max_len;
+        b->policy_valid = false;
     }
     b->mirror_valid = false;
     CUDA_TRY(cudaStreamSynchronize(c->stream));

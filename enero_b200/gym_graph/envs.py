@@ -175,6 +175,38 @@ class Env16(_EnvBase):
         return (self.reward, self.episode_over, 0.0, self.TM[ns][nd], ns, nd, self.edgeMaxUti, 0.0,
                 np.std(self.edge_state[:, 0]))
 
+    def run_greedy_episode(self):
+        """The whole greedy loop of play_middRout_games_sp (script_eval_on_single_topology.py:169-186) for the
+        traffic matrix of the last reset(), device resident: one CUDA-graph replay per decision, no host round
+        trip until the episode is over.  The actor weights are whatever the context holds (the agent binds its
+        model first).  -> dict(actions, rewards, max_uti per step, best, best_routing {"s:d": mid})."""
+        eb = self._batch
+        eb.run_greedy()
+        st = eb.state()
+        n = int(st["steps"][0])
+        act, rew, mx = eb.history()
+        best, ospf, routing = eb.best()
+        # leave the attributes the way the reference's loop leaves them after the last step()
+        self.sp_middlepoints = {}
+        for k in range(n):
+            s, d, _ = self.list_eligible_demands[k]
+            mid = self.src_dst_k_middlepoints["%d:%d" % (s, d)][int(act[0, k])]
+            nxt = self.list_eligible_demands[k + 1][:2] if k + 1 < n else (1, 2)
+            if mid != d:
+                self.sp_middlepoints["%d:%d" % (s, d)] = mid
+            self.sp_middlepoints.pop("%d:%d" % nxt, None)
+        self.sp_middlepoints_step = self.sp_middlepoints
+        self.edgeMaxUti = self._edge_tuple(int(st["max_edge"][0]), st["max_uti"][0])
+        self.currentVal = -self.edgeMaxUti[2]
+        self.iter_list_elig_demn = n
+        self.episode_over = True
+        self.patMaxBandwth = (1, 2, int(self.TM[1][2]))
+        self.edge_state[:, 0] = st["loads"][0]
+        self.edge_state[:, 2] = 0
+        return {"actions": act[0, :n].copy(), "rewards": rew[0, :n].copy(), "max_uti": mx[0, :n].copy(),
+                "best": float(best[0]), "ospf": float(ospf[0]),
+                "best_routing": {"%d:%d" % (s, d): int(m) for s, d, m in routing[0]}}
+
     def mark_action_sp(self, src, dst, init_source, final_destination):
         """environment16.py:711-725 -- host-side mirror for agents that still build their own
         features; the fused GPU path (enero_decide_batch) marks candidates on device."""

@@ -23,10 +23,10 @@ class Variable:
         self.name = VARIABLE_NAMES[index]
 
     def numpy(self):
-        return self._owner._weights[self._index]
+        return self._owner.get_weights()[self._index]
 
     def assign(self, value):
-        w = list(self._owner._weights)
+        w = self._owner.get_weights()
         w[self._index] = np.asarray(value, dtype=np.float32).reshape(WEIGHT_SHAPES[self._index])
         self._owner.set_weights(w)
         return self
@@ -69,6 +69,8 @@ class _GNNModel:
         self._kernel_gain = getattr(kernel_init, "gain", None)
         self._ctx = context
         self._weights = None
+        self._device_dirty = False
+        self._version = 0            # bumped whenever the weights change (value caches key on it)
         self.built = False
 
     # ---- Keras-shaped surface ------------------------------------------------------------
@@ -90,19 +92,57 @@ class _GNNModel:
             self._ctx = default_context()
         return self._ctx
 
+    # ---- device residency ------------------------------------------------------------------
+    # A context holds ONE actor and ONE critic weight buffer (plus their Adam slots).  Several model objects may
+    # share a context (an eval agent next to a training agent, two TrainingRuns in one process): the context records
+    # which object's weights each buffer currently holds, and bind() -- called by everything that is about to launch
+    # with this model -- swaps the buffer over, first pulling a trained-on-device owner's weights back into its host
+    # mirror so that nothing is lost or silently overwritten.
+    def bind(self):
+        ctx = self.context
+        owners = ctx.__dict__.setdefault("_weight_owner", {})
+        cur = owners.get(self.WHICH)
+        if cur is self:
+            return
+        if self._weights is None:
+            raise RuntimeError("model has no weights yet: call build() or set_weights() first")
+        if cur is not None and cur._device_dirty:
+            cur.sync_from_device()
+        self._upload()
+
+    def _upload(self):
+        self.context.upload_weights(self.WHICH, self._weights)          # (clears the slot's owner)
+        self.context.__dict__.setdefault("_weight_owner", {})[self.WHICH] = self
+
+    def _owns_device(self):
+        return self.context.__dict__.get("_weight_owner", {}).get(self.WHICH) is self
+
+    def mark_device_dirty(self):
+        """the device copy was updated by a GPU optimiser step: the host mirror is stale until the next read"""
+        self._device_dirty = True
+        self._version += 1
+
     def set_weights(self, tensors):
         w = [np.array(t, dtype=np.float32).reshape(s) for t, s in zip(tensors, WEIGHT_SHAPES)]
         if len(w) != 11:
             raise ValueError("expected 11 tensors in Keras variable order")
+        owned = self._owns_device()
         self._weights = w
-        self.context.upload_weights(self.WHICH, w)
+        self._device_dirty = False
+        self._version += 1
+        if owned:
+            self._upload()
 
     def get_weights(self):
+        if self._device_dirty and self._owns_device():
+            self.sync_from_device()
         return [w.copy() for w in self._weights]
 
     def sync_from_device(self):
         """after a GPU optimiser step: refresh the host mirror"""
-        self._weights = self.context.download_weights(self.WHICH)
+        if self._owns_device():
+            self._weights = self.context.download_weights(self.WHICH)
+        self._device_dirty = False
 
     @property
     def variables(self):
@@ -124,6 +164,7 @@ class ActorModel(_GNNModel):
         if ls.shape[0] != n:
             raise ValueError("num_edges (%d) must equal the number of link_state rows (%d)" % (n, ls.shape[0]))
         G = int(gid.max()) + 1 if gid.size else 0
+        self.bind()
         out = self.context.gnn_forward(self.WHICH, ls, gid, states_first, states_second, G, T=int(self.hparams["T"]))
         return out.reshape(G, 1)
 
@@ -140,6 +181,7 @@ class CriticModel(_GNNModel):
         n = int(np.asarray(num_edges_critic))
         if ls.shape[0] != n:
             raise ValueError("num_edges (%d) must equal the number of link_state rows (%d)" % (n, ls.shape[0]))
+        self.bind()
         out = self.context.gnn_forward(self.WHICH, ls, None, first_critic, second_critic, 1, T=int(self.hparams["T"]))
         return out.reshape(1, 1)
 

@@ -26,7 +26,7 @@ from .parallel import shard_indices
 # train_Enero_3top_script.py:28-87
 MINI_BATCH_SIZE = 55
 PPO_EPOCHS = 8
-hparams = {'l2': 0.005, 'dropout_rate': 0.1, 'link_state_dim': 20, 'readout_units': 20, 'learning_rate': 0.0002, 'T': 5}
+hparams = {'l2': 0.0001, 'link_state_dim': 20, 'readout_units': 20, 'learning_rate': 0.0002, 'T': 5}   # :81-87
 gamma = 0.99
 lmbda = 0.95
 clipping_val = 0.1
@@ -74,6 +74,19 @@ class PPOActorCritic:
         self._value_cache = None
         self.last_grad_norm = None
 
+    def _bind(self, optimizer=False):
+        """this agent's weights (and, for an update, its Adam slots) are what the context's device buffers hold"""
+        self.actor.bind()
+        self.critic.bind()
+        if optimizer:
+            owners = self.context.__dict__.setdefault("_optimizer_owner", {})
+            cur = owners.get("adam")
+            if cur is not self:
+                if cur is not None:
+                    cur.store_optimizer_state()
+                self.load_optimizer_state()
+                owners["adam"] = self
+
     # ---- acting ----------------------------------------------------------------------------
     def pred_action_distrib_sp(self, env, source, destination):
         """train script :125-171 -> (probabilities over the K' middlepoints, sample record)."""
@@ -82,10 +95,11 @@ class PPOActorCritic:
         bw = float(env.TM[source][destination])
         # the rollout asks for the critic's value of the same state right after (train script :495-500): both
         # networks run in one stream round trip and the value is handed out by critic_value()
+        self._bind()
         probs, nK, values = self.context.decide_value_batch(t, loads[None], np.array([[source, destination]], np.int32),
                                                             np.array([bw]))
         k = int(nK[0])
-        self._value_cache = (t, loads, np.float32(values[0]))
+        self._value_cache = (t, loads, np.float32(values[0]), self.critic._version)
         self.listQValues = None
         self.softMaxQValues = probs[:1, :k]
         tensor = {'topology': t, 'loads': loads, 'sd': (int(source), int(destination)), 'bw': bw, 'num_candidates': k}
@@ -98,8 +112,10 @@ class PPOActorCritic:
     def critic_value(self, features):
         """self.critic(link_state_critic, first_critic, second_critic, num_edges_critic)[0].numpy()[0]"""
         cached = getattr(self, "_value_cache", None)
-        if cached is not None and cached[0] is features['topology'] and np.array_equal(cached[1], features['loads']):
+        if (cached is not None and cached[0] is features['topology'] and cached[3] == self.critic._version
+                and np.array_equal(cached[1], features['loads'])):
             return cached[2]
+        self.critic.bind()
         return self.context.value_batch(features['topology'], features['loads'][None])[0]
 
     # ---- learning ----------------------------------------------------------------------------
@@ -137,6 +153,7 @@ class PPOActorCritic:
 
     def gradients(self, inds):
         """accumulate the minibatch gradient without applying it -> (actor[4201], critic[4201], sums[3])"""
+        self._bind()
         _lib.check(self._lib.enero_ppo_zero_grad(self.context.handle))
         self._accumulate(self._group_by_topology(inds), 1.0 / len(inds))
         ga, gc_, sums = np.zeros(_lib.NPARAMS, np.float32), np.zeros(_lib.NPARAMS, np.float32), np.zeros(3, np.float32)
@@ -151,6 +168,7 @@ class PPOActorCritic:
             import torch.distributed as dist
             rank, world = dist.get_rank(self._pg), dist.get_world_size(self._pg)
             mine = shard_indices(inds, rank, world)
+        self._bind(optimizer=True)
         _lib.check(self._lib.enero_ppo_zero_grad(self.context.handle))
         if len(mine):
             self._accumulate(self._group_by_topology(mine), 1.0 / m)
@@ -165,6 +183,8 @@ class PPOActorCritic:
                                              float(self.optimizer.epsilon), max_grad_norm,
                                              int(self.optimizer.iterations), _lib.ptr(norm)))
         self.last_grad_norm = float(norm[0])
+        self.actor.mark_device_dirty()
+        self.critic.mark_device_dirty()
         self._value_cache = None
         final_entropy = sums[1] / m
         actor_loss = sums[0] / m - self.entropy_beta * final_entropy
@@ -207,9 +227,12 @@ class PPOActorCritic:
         for which, model in ((_lib.ACTOR, self.actor), (_lib.CRITIC, self.critic)):
             m, v = self.optimizer.get_slots(model)
             self.upload_slots(which, m, v)
+        self.context.__dict__.setdefault("_optimizer_owner", {})["adam"] = self
 
     def store_optimizer_state(self):
         """before Checkpoint.save: pull weights and Adam slots of both models back to the host objects"""
+        if self.context.__dict__.get("_optimizer_owner", {}).get("adam") is not self:
+            return                              # the device holds another agent's slots; ours are already on the host
         for which, model in ((_lib.ACTOR, self.actor), (_lib.CRITIC, self.critic)):
             model.sync_from_device()
             m, v = self.download_slots(which)

@@ -97,6 +97,12 @@ class Context:
             raise ValueError("math mode must be 'fast' or 'accurate'")
         _lib.check(self._lib.enero_ctx_set_math(self._h, _lib.MATH_ACCURATE if mode == "accurate" else _lib.MATH_FAST))
 
+    def fp32_peak_tflops(self) -> float:
+        """FP32 FMA peak of this device, measured live (FFMA2 register loop)"""
+        v = C.c_double(0)
+        _lib.check(self._lib.enero_ctx_fp32_peak(self._h, C.byref(v)))
+        return v.value
+
     def profile_begin(self):
         _lib.check(self._lib.enero_ctx_profile_begin(self._h))
 
@@ -108,6 +114,12 @@ class Context:
 
     # ---- weights -------------------------------------------------------------------------
     def upload_weights(self, which: int, tensors):
+        """raw upload into the context's actor / critic buffer; a model object that owned the buffer (models.bind)
+        loses it, so its next use re-uploads its own weights instead of computing with these"""
+        prev = self.__dict__.setdefault("_weight_owner", {}).get(which)
+        if prev is not None and prev._device_dirty:
+            prev.sync_from_device()                  # keep what a GPU optimiser step left there
+        self._weight_owner.pop(which, None)
         flat = flatten_weights(tensors)
         _lib.check(self._lib.enero_weights_upload(self._h, which, _lib.ptr(flat)))
 

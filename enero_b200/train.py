@@ -169,6 +169,7 @@ class TrainingRun:
     # ---- greedy evaluation (train script :633-693), batched --------------------------------------------
     def evaluate(self):
         rewards, max_uti, uti_std = [], [], []
+        self.agent._bind()                       # the batches below run with whatever weights the context holds
         for env in self.eval_envs:
             tms = np.stack([ds.parse_demands_file(os.path.join(env.dataset_folder_name, "TM", "%s.%d.demands"
                                                                % (env.graph_topology_name, t)), env.numNodes)

@@ -78,6 +78,10 @@ int enero_ctx_get_math(enero_ctx* ctx);
 int enero_ctx_profile_begin(enero_ctx* ctx);
 int enero_ctx_profile_end(enero_ctx* ctx, double* mp_iter_ms, int64_t* mp_iter_launches);
 
+/* FP32 FMA peak of the ctx's device measured live with a packed-FFMA2 register loop (no memory traffic): the
+ * denominator of bench.py's FP32 roofline fraction (MEASURED_PEAKS.json holds HBM and bf16 tensor peaks only). */
+int enero_ctx_fp32_peak(enero_ctx* ctx, double* tflops);
+
 /* ---- weights ---------------------------------------------------------------
  * Flat fp32[4201] in Keras variable order: FirstLayer/kernel[40,20], bias[20],
  * gru/kernel[20,60], recurrent_kernel[20,60], bias[2,60], Readout1/kernel[20,20],

@@ -70,6 +70,56 @@ def test_eval_script_flow(name, actor, tmp_path):
             assert fin_h == ep["plain_hill_final"]
 
 
+def test_greedy_driver_device_loop_equals_per_decision_protocol(actor, tmp_path):
+    """play_middRout_games_sp runs the decision loop on the device (CUDA-graph replays) for this package's agent;
+    a foreign agent object goes through pred_action_node_distrib_sp / np.argmax / env.step one decision at a time.
+    Both must return the same tuple and leave the environment in the same state."""
+    from enero_b200 import agents, gym_graph
+    case = load_case("tiny12")
+    folder = str(tmp_path)
+    topo_name = _dataset(case, folder)
+
+    class Foreign:                                   # same policy, not an instance of PPOMIDDROUTING_SP
+        def __init__(self, inner):
+            self.inner = inner
+
+        def pred_action_node_distrib_sp(self, env, s, d):
+            return self.inner.pred_action_node_distrib_sp(env, s, d)
+
+    outs = []
+    for wrap in (False, True):
+        env = gym_graph.make('GraphEnv-v16')
+        env.seed(9)
+        env.generate_environment(folder, topo_name, 100, 100, 0.15)
+        env.top_K_critical_demands = True
+        agent = agents.PPOMIDDROUTING_SP(env, actor)
+        ts = []
+        r = agents.play_middRout_games_sp(case["episodes"][0]["tm_id"], env, Foreign(agent) if wrap else agent, ts)
+        outs.append((r[0], r[2], dict(r[3]), list(r[4]), [v for _, v in ts], env.edge_state[:, 0].tolist(),
+                     tuple(env.edgeMaxUti), dict(env.sp_middlepoints), env.episode_over))
+    assert outs[0] == outs[1]
+    assert outs[0][0] == case["episodes"][0]["best"]
+
+
+def test_two_models_share_a_context_without_clobbering(actor):
+    """a second model built on the same context must not silently replace the first one's weights"""
+    import enero_b200.actorPPOmiddR as actor_mod
+    ls = np.random.default_rng(0).normal(0, 0.3, (12, 20)).astype(np.float32)
+    first = np.array([0, 1, 2, 3, 4, 5], np.int32)
+    second = np.array([1, 2, 3, 4, 5, 0], np.int32)
+    gid = np.zeros(12, np.int32)
+    want = actor(ls, gid, first, second, 12)
+    other = actor_mod.myModel(hparams, None, None)
+    other.build()                                    # random initialisation: different weights, same context
+    got_other = other(ls, gid, first, second, 12)
+    assert not np.array_equal(got_other, want)
+    assert np.array_equal(actor(ls, gid, first, second, 12), want)          # the first model still computes with ITS weights
+    assert np.array_equal(other(ls, gid, first, second, 12), got_other)
+    for a, b in zip(actor.get_weights(), other.get_weights()):
+        if a.size > 1 and np.abs(a).max() > 0:
+            assert not np.array_equal(a, b)
+
+
 def test_reference_style_agent_through_myModel_call(actor, tmp_path):
     """The reference agent's own feature plumbing (mark_action_sp, old_cummax offsets, concat;
     script :83-129) feeding actor(link_state, graph_id, first, second, num_edges): logits within
