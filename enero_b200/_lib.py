@@ -18,6 +18,7 @@ MATH_FAST, MATH_ACCURATE = 0, 1
 NPARAMS = 4201
 GRAD_STRIDE = 4204
 GRAD_FLOATS = 2 * GRAD_STRIDE + 4
+PPO_HISTORY = 4096
 
 _lib = None
 
@@ -91,7 +92,10 @@ SIGNATURES = {
     "enero_ppo_zero_grad": (C.c_int, [_vp]),
     "enero_ppo_accumulate": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_float, C.c_float,
                                        C.c_float, C.c_int]),
-    "enero_ppo_apply": (C.c_int, [_vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64, _vp]),
+    "enero_ppo_store": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "enero_ppo_accumulate_stored": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_float, C.c_float, C.c_float]),
+    "enero_ppo_apply": (C.c_int, [_vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64, _vp, C.c_int]),
+    "enero_ppo_history": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "enero_ppo_grad_download": (C.c_int, [_vp, _vp, _vp, _vp]),
     "enero_adam_slots_upload": (C.c_int, [_vp, C.c_int, _vp, _vp]),
     "enero_adam_slots_download": (C.c_int, [_vp, C.c_int, _vp, _vp]),

@@ -25,6 +25,8 @@ using namespace enero;
 
 #include "ctx.cuh"
 
+void train_release_stores(enero_ctx* c);
+
 // ---------------------------------------------------------------------------------------
 extern "C" int enero_device_count(void) {
     int n = 0;
@@ -97,6 +99,7 @@ extern "C" int enero_ctx_destroy(enero_ctx* c) {
     cudaStreamSynchronize(c->stream);
     for (int i = 0; i < 2; ++i) { cudaFree(c->w[i]); cudaFree(c->adam_m[i]); cudaFree(c->adam_v[i]); }
     cudaFree(c->gradbuf); cudaFree(c->tile_ctr);
+    train_release_stores(c);
     cudaStreamDestroy(c->stream);
     delete c;
     return ENERO_OK;

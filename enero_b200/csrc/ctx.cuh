@@ -67,7 +67,8 @@ struct enero_ctx {
     float* adam_v[2] = {nullptr, nullptr};
     DevBuf t_h[8], t_A[8];   // h_0..h_T, A_0..A_{T-1} of a training forward
     DevBuf t_agg, t_G, t_dB, t_dA, t_B, t_dagg, t_dhpart, t_dh[2], t_V, t_dlogit, t_partials;
-    DevBuf t_loads, t_sd, t_bw, t_action, t_oldp, t_adv, t_ret, t_logits, t_probs, t_nK, t_loss, t_ent, t_norm;
+    DevBuf t_loads, t_sd, t_bw, t_action, t_oldp, t_adv, t_ret, t_logits, t_probs, t_nK, t_loss, t_ent, t_norm, t_hist;
+    void* sample_stores = nullptr;            // topology -> device-resident PPO samples (train_api.cuh)
 };
 
 // NVTX range over one C-ABI call (header-only NVTX v3: shows up in nsys / ncu timelines, free otherwise)

@@ -4,6 +4,8 @@
 // Reference: train_Enero_3top_script.py:264-324 (_critic_step, _actor_step, _train_step_combined),
 // :326-365 (ppo_update), :367-377 (get_advantages).
 #pragma once
+#include <unordered_map>
+
 #include "train_kernels.cuh"
 
 namespace {
@@ -105,6 +107,21 @@ extern "C" int enero_ppo_zero_grad(enero_ctx* c) {
     return ENERO_OK;
 }
 
+// validate what a kernel could not report (host copies of the demands / actions)
+static int validate_samples(const enero_topo* t, int n, const int32_t* sd, const int32_t* action, const char* who) {
+    for (int i = 0; i < n; ++i) {
+        const int s = sd[2 * i], dd = sd[2 * i + 1];
+        if (s < 0 || dd < 0 || s >= t->N || dd >= t->N || s == dd) return fail(ENERO_ERR_INVALID, std::string(who) + ": bad demand");
+        const int k = t->mid_off[s * t->N + dd + 1] - t->mid_off[s * t->N + dd];
+        if (action[i] < 0 || action[i] >= k) return fail(ENERO_ERR_INVALID, std::string(who) + ": action out of range");
+    }
+    return ENERO_OK;
+}
+
+static int accumulate_dev(enero_ctx* c, enero_topo* t, int n, const double* loads, const int32_t* sd, const double* bw,
+                          const int32_t* action, const float* old_prob, const float* advantage, const float* ret,
+                          float inv_m, float entropy_beta, float clipping_val);
+
 extern "C" int enero_ppo_accumulate(enero_ctx* c, enero_topo* t, int n, const double* loads, const int32_t* sd,
                                     const double* bw, const int32_t* action, const float* old_prob,
                                     const float* advantage, const float* ret, float inv_m, float entropy_beta,
@@ -115,16 +132,9 @@ extern "C" int enero_ppo_accumulate(enero_ctx* c, enero_topo* t, int n, const do
     TRY(enero_topo_upload(c, t));
     CUDA_TRY(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
-    const TopoDev& d = t->dev;
-    const int E = d.E, Kmax = d.Kmax, T = 5;
+    const int E = t->dev.E;
     if (ptr_kind == ENERO_HOST) {
-        // validate what a kernel could not report
-        for (int i = 0; i < n; ++i) {
-            const int s = sd[2 * i], dd = sd[2 * i + 1];
-            if (s < 0 || dd < 0 || s >= t->N || dd >= t->N || s == dd) return fail(ENERO_ERR_INVALID, "enero_ppo_accumulate: bad demand");
-            const int k = t->mid_off[s * t->N + dd + 1] - t->mid_off[s * t->N + dd];
-            if (action[i] < 0 || action[i] >= k) return fail(ENERO_ERR_INVALID, "enero_ppo_accumulate: action out of range");
-        }
+        TRY(validate_samples(t, n, sd, action, "enero_ppo_accumulate"));
         TRY(c->t_loads.ensure((size_t)n * E * 8)); TRY(c->t_sd.ensure((size_t)n * 8)); TRY(c->t_bw.ensure((size_t)n * 8));
         TRY(c->t_action.ensure((size_t)n * 4)); TRY(c->t_oldp.ensure((size_t)n * 4)); TRY(c->t_adv.ensure((size_t)n * 4));
         TRY(c->t_ret.ensure((size_t)n * 4));
@@ -138,6 +148,103 @@ extern "C" int enero_ppo_accumulate(enero_ctx* c, enero_topo* t, int n, const do
         loads = c->t_loads.as<double>(); sd = c->t_sd.as<int>(); bw = c->t_bw.as<double>();
         action = c->t_action.as<int>(); old_prob = c->t_oldp.as<float>(); advantage = c->t_adv.as<float>(); ret = c->t_ret.as<float>();
     }
+    return accumulate_dev(c, t, n, loads, sd, bw, action, old_prob, advantage, ret, inv_m, entropy_beta, clipping_val);
+}
+
+// ---- device-resident sample store ----------------------------------------------------------------------------------
+// ppo_update (train script :326-365) walks the same 835-sample buffer 8 times in minibatches of 55: the samples of
+// one topology are uploaded ONCE per update (enero_ppo_store) and every minibatch passes only the indices it drew
+// (enero_ppo_accumulate_stored: one small H2D copy + a gather kernel) instead of seven host arrays per call.
+struct SampleStore {
+    int n = 0;
+    DevBuf loads, sd, bw, action, oldp, adv, ret, idx;
+};
+static std::unordered_map<const enero_topo*, SampleStore*>& stores_of(enero_ctx* c) {
+    if (!c->sample_stores) c->sample_stores = new std::unordered_map<const enero_topo*, SampleStore*>();
+    return *static_cast<std::unordered_map<const enero_topo*, SampleStore*>*>(c->sample_stores);
+}
+void train_release_stores(enero_ctx* c) {
+    if (!c->sample_stores) return;
+    auto* m = static_cast<std::unordered_map<const enero_topo*, SampleStore*>*>(c->sample_stores);
+    for (auto& kv : *m) delete kv.second;
+    delete m;
+    c->sample_stores = nullptr;
+}
+
+__global__ void k_gather_samples(int n, int E, const int* __restrict__ idx, const double* __restrict__ loads, const int* __restrict__ sd,
+                                 const double* __restrict__ bw, const int* __restrict__ action, const float* __restrict__ oldp,
+                                 const float* __restrict__ adv, const float* __restrict__ ret, double* __restrict__ o_loads,
+                                 int* __restrict__ o_sd, double* __restrict__ o_bw, int* __restrict__ o_action,
+                                 float* __restrict__ o_oldp, float* __restrict__ o_adv, float* __restrict__ o_ret) {
+    const int i = blockIdx.x;
+    const int j = idx[i];
+    for (int e = threadIdx.x; e < E; e += blockDim.x) o_loads[(int64_t)i * E + e] = loads[(int64_t)j * E + e];
+    if (threadIdx.x == 0) {
+        o_sd[2 * i] = sd[2 * j]; o_sd[2 * i + 1] = sd[2 * j + 1]; o_bw[i] = bw[j]; o_action[i] = action[j];
+        o_oldp[i] = oldp[j]; o_adv[i] = adv[j]; o_ret[i] = ret[j];
+    }
+}
+
+extern "C" int enero_ppo_store(enero_ctx* c, enero_topo* t, int n, const double* loads, const int32_t* sd, const double* bw,
+                               const int32_t* action, const float* old_prob, const float* advantage, const float* ret) {
+    ENERO_TRACE("enero_ppo_store");
+    if (!c || !t || n < 0 || (n > 0 && (!loads || !sd || !bw || !action || !old_prob || !advantage || !ret)))
+        return fail(ENERO_ERR_INVALID, "enero_ppo_store: bad argument");
+    TRY(enero_topo_upload(c, t));
+    CUDA_TRY(cudaSetDevice(c->device));
+    TRY(validate_samples(t, n, sd, action, "enero_ppo_store"));
+    auto& m = stores_of(c);
+    if (!m.count(t)) m[t] = new SampleStore();
+    SampleStore& s = *m[t];
+    const size_t N = std::max(1, n), E = t->dev.E;
+    TRY(s.loads.ensure(N * E * 8)); TRY(s.sd.ensure(N * 8)); TRY(s.bw.ensure(N * 8)); TRY(s.action.ensure(N * 4));
+    TRY(s.oldp.ensure(N * 4)); TRY(s.adv.ensure(N * 4)); TRY(s.ret.ensure(N * 4)); TRY(s.idx.ensure(N * 4));
+    cudaStream_t st = c->stream;
+    if (n) {
+        CUDA_TRY(cudaMemcpyAsync(s.loads.p, loads, (size_t)n * E * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(s.sd.p, sd, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(s.bw.p, bw, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(s.action.p, action, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(s.oldp.p, old_prob, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(s.adv.p, advantage, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(s.ret.p, ret, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    }
+    s.n = n;
+    return ENERO_OK;
+}
+
+extern "C" int enero_ppo_accumulate_stored(enero_ctx* c, enero_topo* t, int n, const int32_t* idx, float inv_m,
+                                           float entropy_beta, float clipping_val) {
+    ENERO_TRACE("enero_ppo_accumulate_stored");
+    if (!c || !t || !idx || n < 1) return fail(ENERO_ERR_INVALID, "enero_ppo_accumulate_stored: bad argument");
+    auto& m = stores_of(c);
+    if (!m.count(t)) return fail(ENERO_ERR_STATE, "enero_ppo_accumulate_stored: no samples stored for this topology (enero_ppo_store)");
+    SampleStore& s = *m[t];
+    for (int i = 0; i < n; ++i)
+        if (idx[i] < 0 || idx[i] >= s.n) return fail(ENERO_ERR_INVALID, "enero_ppo_accumulate_stored: sample index out of range");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const int E = t->dev.E;
+    TRY(c->t_loads.ensure((size_t)n * E * 8)); TRY(c->t_sd.ensure((size_t)n * 8)); TRY(c->t_bw.ensure((size_t)n * 8));
+    TRY(c->t_action.ensure((size_t)n * 4)); TRY(c->t_oldp.ensure((size_t)n * 4)); TRY(c->t_adv.ensure((size_t)n * 4));
+    TRY(c->t_ret.ensure((size_t)n * 4));
+    if (s.idx.cap < (size_t)n * 4) TRY(s.idx.ensure((size_t)n * 4));
+    CUDA_TRY(cudaMemcpyAsync(s.idx.p, idx, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    k_gather_samples<<<n, 64, 0, st>>>(n, E, s.idx.as<int>(), s.loads.as<double>(), s.sd.as<int>(), s.bw.as<double>(), s.action.as<int>(),
+                                       s.oldp.as<float>(), s.adv.as<float>(), s.ret.as<float>(), c->t_loads.as<double>(), c->t_sd.as<int>(),
+                                       c->t_bw.as<double>(), c->t_action.as<int>(), c->t_oldp.as<float>(), c->t_adv.as<float>(),
+                                       c->t_ret.as<float>());
+    LAUNCH_CHECK(c);
+    return accumulate_dev(c, t, n, c->t_loads.as<double>(), c->t_sd.as<int>(), c->t_bw.as<double>(), c->t_action.as<int>(),
+                          c->t_oldp.as<float>(), c->t_adv.as<float>(), c->t_ret.as<float>(), inv_m, entropy_beta, clipping_val);
+}
+
+static int accumulate_dev(enero_ctx* c, enero_topo* t, int n, const double* loads, const int32_t* sd, const double* bw,
+                          const int32_t* action, const float* old_prob, const float* advantage, const float* ret,
+                          float inv_m, float entropy_beta, float clipping_val) {
+    cudaStream_t st = c->stream;
+    const TopoDev& d = t->dev;
+    const int E = d.E, Kmax = d.Kmax, T = 5;
     TopoView tv = view_of(t);
     TRY(c->util.ensure((size_t)n * E * 4)); TRY(c->t_nK.ensure((size_t)n * 4));
     TRY(c->t_logits.ensure((size_t)n * Kmax * 4)); TRY(c->t_dlogit.ensure((size_t)n * Kmax * 4));
@@ -188,22 +295,34 @@ extern "C" int enero_ppo_accumulate(enero_ctx* c, enero_topo* t, int n, const do
 }
 
 extern "C" int enero_ppo_apply(enero_ctx* c, float lr, float beta1, float beta2, float eps, float clip_norm,
-                               int64_t step, float* grad_norm_host) {
+                               int64_t step, float* grad_norm_host, int hist_slot) {
     ENERO_TRACE("enero_ppo_apply");
-    if (!c || step < 1 || !(clip_norm > 0)) return fail(ENERO_ERR_INVALID, "enero_ppo_apply: bad argument");
+    if (!c || step < 1 || !(clip_norm > 0) || hist_slot >= ENERO_PPO_HISTORY)
+        return fail(ENERO_ERR_INVALID, "enero_ppo_apply: bad argument");
     CUDA_TRY(cudaSetDevice(c->device));
     // Keras Adam._prepare_local in fp32: lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t)
     const float t = (float)step;
     const float alpha = lr * std::sqrt(1.0f - std::pow(beta2, t)) / (1.0f - std::pow(beta1, t));
     TRY(c->t_norm.ensure(16));
+    TRY(c->t_hist.ensure((size_t)ENERO_PPO_HISTORY * 16));
     k_clip_adam<<<1, 1024, 0, c->stream>>>(c->w[0], c->w[1], c->grad[0], c->grad[1], c->adam_m[0], c->adam_v[0], c->adam_m[1],
-                                           c->adam_v[1], alpha, beta1, beta2, eps, clip_norm, c->t_norm.as<float>());
+                                           c->adam_v[1], alpha, beta1, beta2, eps, clip_norm, c->t_norm.as<float>(),
+                                           c->gradbuf + 2 * ENERO_GRAD_STRIDE, hist_slot >= 0 ? c->t_hist.as<float>() + 4 * hist_slot : nullptr);
     LAUNCH_CHECK(c);
     CUDA_TRY(cudaMemsetAsync(c->gradbuf + 2 * ENERO_GRAD_STRIDE, 0, 16, c->stream));
     if (grad_norm_host) {
         CUDA_TRY(cudaMemcpyAsync(grad_norm_host, c->t_norm.p, 4, cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
     }
+    return ENERO_OK;
+}
+
+extern "C" int enero_ppo_history(enero_ctx* c, int first_slot, int n, float* out) {
+    if (!c || !out || first_slot < 0 || n < 1 || first_slot + n > ENERO_PPO_HISTORY) return fail(ENERO_ERR_INVALID, "enero_ppo_history: bad argument");
+    if (!c->t_hist.p) return fail(ENERO_ERR_STATE, "enero_ppo_history: no step recorded yet");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaMemcpyAsync(out, c->t_hist.as<float>() + 4 * first_slot, (size_t)n * 16, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
     return ENERO_OK;
 }
 

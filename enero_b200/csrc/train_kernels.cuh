@@ -520,7 +520,8 @@ __global__ void k_sum_into(int n, const float* __restrict__ x, float* __restrict
 __global__ void __launch_bounds__(1024)
 k_clip_adam(float* __restrict__ wa, float* __restrict__ wc, float* __restrict__ ga, float* __restrict__ gc,
             float* __restrict__ ma, float* __restrict__ va, float* __restrict__ mc, float* __restrict__ vc,
-            float alpha, float beta1, float beta2, float eps, float clip_norm, float* __restrict__ norm_out) {
+            float alpha, float beta1, float beta2, float eps, float clip_norm, float* __restrict__ norm_out,
+            const float* __restrict__ sums, float* __restrict__ hist) {
     __shared__ float red[32];
     __shared__ float s_scale;
     float s = 0.f;
@@ -535,6 +536,8 @@ k_clip_adam(float* __restrict__ wa, float* __restrict__ wc, float* __restrict__ 
             const float norm = sqrtf(v);
             s_scale = clip_norm * fminf(1.f / norm, 1.f / clip_norm);
             if (norm_out) *norm_out = norm;
+            // per-step record read back once per ppo_update: global norm before clipping and the three loss sums
+            if (hist) { hist[0] = norm; hist[1] = sums[0]; hist[2] = sums[1]; hist[3] = sums[2]; }
         }
     }
     __syncthreads();

@@ -141,15 +141,23 @@ class PPOActorCritic:
                                                       float(inv_m), self.entropy_beta, clipping_val, _lib.HOST))
 
     def _allreduce(self):
-        """sum the flat gradient buffer over the ranks of the process group (the path's only collective)"""
+        """sum the flat gradient buffer over the ranks of the process group (the path's only collective).  The
+        collective is enqueued from the library's own stream (torch sees it as an ExternalStream): c10d orders NCCL
+        after the kernels already on that stream and the following clip + Adam kernel after NCCL, all on the device --
+        no host synchronisation on either side."""
         import torch
         import torch.distributed as dist
         if self._grad_view is None:
             self._grad_view = _device_view(self._lib.enero_ppo_grad_buffer(self.context.handle), _lib.GRAD_FLOATS,
                                            self.context.device)
-        self.context.sync()                       # the library launches on its own stream
-        dist.all_reduce(self._grad_view, op=dist.ReduceOp.SUM, group=self._pg)
-        torch.cuda.current_stream(self.context.device).synchronize()
+            self._ext_stream = torch.cuda.ExternalStream(self.context.stream, device=torch.device("cuda", self.context.device))
+        if dist.get_backend(self._pg) == "nccl":
+            with torch.cuda.stream(self._ext_stream):
+                dist.all_reduce(self._grad_view, op=dist.ReduceOp.SUM, group=self._pg)
+        else:                                     # gloo (CPU tests of the N > 1 logic): staged through the host
+            self.context.sync()
+            dist.all_reduce(self._grad_view, op=dist.ReduceOp.SUM, group=self._pg)
+            torch.cuda.current_stream(self.context.device).synchronize()
 
     def gradients(self, inds):
         """accumulate the minibatch gradient without applying it -> (actor[4201], critic[4201], sums[3])"""
@@ -160,8 +168,42 @@ class PPOActorCritic:
         _lib.check(self._lib.enero_ppo_grad_download(self.context.handle, _lib.ptr(ga), _lib.ptr(gc_), _lib.ptr(sums)))
         return ga, gc_, sums
 
-    def _train_step_combined(self, inds):
-        """train script :293-324 -> (actor_loss, critic_loss, final_entropy) of the minibatch."""
+    # ---- device-resident buffer of one ppo_update -------------------------------------------------------
+    def _store_memory(self):
+        """upload self.memory once, grouped by topology -> per-sample (topology, index inside its store)"""
+        groups = {}
+        where = []
+        for smp in self.memory:
+            t = smp['topology']
+            g = groups.setdefault(id(t), (t, []))
+            where.append((id(t), len(g[1])))
+            g[1].append(smp)
+        for t, group in groups.values():
+            loads = np.ascontiguousarray(np.stack([s['loads'] for s in group]), dtype=np.float64)
+            sd = np.ascontiguousarray([s['sd'] for s in group], dtype=np.int32)
+            bw = np.ascontiguousarray([s['bw'] for s in group], dtype=np.float64)
+            act = np.ascontiguousarray([s['action'] for s in group], dtype=np.int32)
+            oldp = np.ascontiguousarray([s['old_prob'] for s in group], dtype=np.float32)
+            adv = np.ascontiguousarray([s['advantage'] for s in group], dtype=np.float32)
+            ret = np.ascontiguousarray([s['return'] for s in group], dtype=np.float32)
+            _lib.check(self._lib.enero_ppo_store(self.context.handle, t.handle, len(group), _lib.ptr(loads), _lib.ptr(sd),
+                                                 _lib.ptr(bw), _lib.ptr(act), _lib.ptr(oldp), _lib.ptr(adv), _lib.ptr(ret)))
+        self._store = ({k: g[0] for k, g in groups.items()}, where)
+
+    def _accumulate_stored(self, inds, inv_m):
+        topos, where = self._store
+        per = {}
+        for i in inds:
+            k, j = where[int(i)]
+            per.setdefault(k, []).append(j)
+        for k, idx in per.items():
+            idx = np.ascontiguousarray(idx, dtype=np.int32)
+            _lib.check(self._lib.enero_ppo_accumulate_stored(self.context.handle, topos[k].handle, idx.size, _lib.ptr(idx),
+                                                             float(inv_m), self.entropy_beta, clipping_val))
+
+    def _train_step_combined(self, inds, hist_slot=None):
+        """train script :293-324 -> (actor_loss, critic_loss, final_entropy) of the minibatch.  With hist_slot the
+        step is only enqueued (its losses and gradient norm go to the device history, ppo_update reads them once)."""
         m = len(inds)
         mine = inds
         if self._pg is not None:
@@ -171,28 +213,37 @@ class PPOActorCritic:
         self._bind(optimizer=True)
         _lib.check(self._lib.enero_ppo_zero_grad(self.context.handle))
         if len(mine):
-            self._accumulate(self._group_by_topology(mine), 1.0 / m)
+            if getattr(self, "_store", None) is not None:
+                self._accumulate_stored(mine, 1.0 / m)
+            else:
+                self._accumulate(self._group_by_topology(mine), 1.0 / m)
         if self._pg is not None:
             self._allreduce()
-        sums = np.zeros(3, np.float32)
-        _lib.check(self._lib.enero_ppo_grad_download(self.context.handle, None, None, _lib.ptr(sums)))
         self.optimizer.iterations += 1
-        norm = np.zeros(1, np.float32)
-        _lib.check(self._lib.enero_ppo_apply(self.context.handle, float(self.optimizer.learning_rate),
-                                             float(self.optimizer.beta_1), float(self.optimizer.beta_2),
-                                             float(self.optimizer.epsilon), max_grad_norm,
-                                             int(self.optimizer.iterations), _lib.ptr(norm)))
-        self.last_grad_norm = float(norm[0])
         self.actor.mark_device_dirty()
         self.critic.mark_device_dirty()
         self._value_cache = None
-        final_entropy = sums[1] / m
-        actor_loss = sums[0] / m - self.entropy_beta * final_entropy
-        critic_loss = sums[2] / m
+        args = (self.context.handle, float(self.optimizer.learning_rate), float(self.optimizer.beta_1),
+                float(self.optimizer.beta_2), float(self.optimizer.epsilon), max_grad_norm, int(self.optimizer.iterations))
+        if hist_slot is not None:
+            _lib.check(self._lib.enero_ppo_apply(*args, None, int(hist_slot)))
+            return None
+        _lib.check(self._lib.enero_ppo_apply(*args, None, 0))
+        return self._step_record(0, m)
+
+    def _step_record(self, slot, m):
+        rec = np.zeros(4, np.float32)
+        _lib.check(self._lib.enero_ppo_history(self.context.handle, int(slot), 1, _lib.ptr(rec)))
+        self.last_grad_norm = float(rec[0])
+        final_entropy = rec[2] / m
+        actor_loss = rec[1] / m - self.entropy_beta * final_entropy
+        critic_loss = rec[3] / m
         return float(actor_loss), float(critic_loss), float(final_entropy)
 
     def ppo_update(self, actions, actions_probs, tensors, critic_features, returns, advantages, shuffle=np.random.shuffle):
-        """train script :326-365.  ``actions`` are the one-hot vectors the reference stores."""
+        """train script :326-365.  ``actions`` are the one-hot vectors the reference stores.  The buffer goes to the
+        device once; the 8 x ceil(n / 55) Adam steps are enqueued without a host synchronisation and the losses of the
+        last minibatch (what the reference returns and logs) are read back at the end."""
         n = len(tensors)
         if self.inds is None or len(self.inds) != n:
             self.inds = np.arange(n)
@@ -205,11 +256,20 @@ class PPOActorCritic:
             sample.update(action=act, old_prob=np.float32(probs[act]), advantage=np.float32(advantages[pos]),
                           **{'return': np.float32(returns[pos])})
             self.memory.append(sample)
-        actor_loss = critic_loss = None
-        for _ in range(PPO_EPOCHS):
-            shuffle(self.inds)
-            for start in range(0, n, MINI_BATCH_SIZE):
-                actor_loss, critic_loss, _ = self._train_step_combined(self.inds[start:start + MINI_BATCH_SIZE])
+        self._bind(optimizer=True)
+        self._store_memory()
+        slot, last_m = 0, 1
+        try:
+            for _ in range(PPO_EPOCHS):
+                shuffle(self.inds)
+                for start in range(0, n, MINI_BATCH_SIZE):
+                    mb = self.inds[start:start + MINI_BATCH_SIZE]
+                    slot = (slot + 1) % _lib.PPO_HISTORY
+                    last_m = len(mb)
+                    self._train_step_combined(mb, hist_slot=slot)
+        finally:
+            self._store = None
+        actor_loss, critic_loss, _ = self._step_record(slot, last_m)
         self.memory.clear()
         self.actor.sync_from_device()
         self.critic.sync_from_device()

@@ -50,6 +50,7 @@ extern "C" {
 #define ENERO_NPARAMS 4201    /* parameters per model, Keras variable order (:238-248) */
 #define ENERO_GRAD_STRIDE 4204  /* floats between the actor and critic halves of the gradient buffer */
 #define ENERO_GRAD_FLOATS (2 * ENERO_GRAD_STRIDE + 4)
+#define ENERO_PPO_HISTORY 4096  /* per-step records kept on the device by enero_ppo_apply */
 
 typedef struct enero_ctx enero_ctx;
 typedef struct enero_topo enero_topo;
@@ -246,11 +247,22 @@ int enero_ppo_accumulate(enero_ctx* ctx, enero_topo* topo, int n, const double* 
                          const double* bw, const int32_t* action, const float* old_prob,
                          const float* advantage, const float* ret, float inv_m, float entropy_beta,
                          float clipping_val, int ptr_kind);
+/* ppo_update's buffer (train script :326-365) kept on the device: the samples of one topology are uploaded once
+ * per update (enero_ppo_store, same arrays as enero_ppo_accumulate, host pointers) and each minibatch passes only the
+ * indices it drew into that store (idx_host int32[n]); otherwise identical to enero_ppo_accumulate. */
+int enero_ppo_store(enero_ctx* ctx, enero_topo* topo, int n, const double* loads, const int32_t* sd, const double* bw,
+                    const int32_t* action, const float* old_prob, const float* advantage, const float* ret);
+int enero_ppo_accumulate_stored(enero_ctx* ctx, enero_topo* topo, int n, const int32_t* idx_host, float inv_m,
+                                float entropy_beta, float clipping_val);
 /* tf.clip_by_global_norm(grad, clip_norm) over all 22 tensors + Adam.apply_gradients (train script
  * :317-320; Keras Adam dense update).  `step` = optimizer.iterations + 1.  Zeroes the gradient buffer.
- * grad_norm_host (nullable) receives the global norm before clipping. */
+ * grad_norm_host (nullable) receives the global norm before clipping -- and makes the call wait for the stream.
+ * hist_slot >= 0 records (norm, actor-loss sum, entropy sum, critic-loss sum) of this step in slot hist_slot of a
+ * device history instead, read back for n consecutive slots by enero_ppo_history (out fp32[n,4]): the 128 Adam
+ * steps of one ppo_update then run without a single host synchronisation. */
 int enero_ppo_apply(enero_ctx* ctx, float lr, float beta1, float beta2, float eps, float clip_norm,
-                    int64_t step, float* grad_norm_host);
+                    int64_t step, float* grad_norm_host, int hist_slot);
+int enero_ppo_history(enero_ctx* ctx, int first_slot, int n, float* out);
 /* host copies of the gradient buffer halves (any pointer may be NULL): actor/critic fp32[4201], sums fp32[3] */
 int enero_ppo_grad_download(enero_ctx* ctx, float* actor, float* critic, float* sums);
 /* Adam slot variables m, v of one model, flat fp32[4201] (checkpoint .OPTIMIZER_SLOT entries) */

@@ -1,6 +1,7 @@
-"""One rank of the sharded-PPO-step test (tests/test_gpu_train.py::test_sharded_step_matches_single).
-Both ranks use cuda:0 (the GPU test box has one GPU); gloo carries the all-reduce of the CUDA gradient
-buffer, which exercises the same code path NCCL does with one GPU per rank."""
+"""One rank of the sharded-PPO-step tests (tests/test_gpu_train.py::test_sharded_step_matches_single /
+::test_sharded_step_nccl).  argv[2] = backend: "gloo" -- both ranks on cuda:0 (a one-GPU box), the all-reduce of the
+CUDA gradient buffer staged by gloo; "nccl" -- one GPU per rank (LOCAL_RANK), the all-reduce enqueued on the
+library's stream exactly as a torchrun training job does."""
 import os
 import sys
 
@@ -11,14 +12,14 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
-def build_agent_and_samples(tmp, process_group=None):
+def build_agent_and_samples(tmp, process_group=None, device=0):
     from conftest import golden_weights
     from enero_b200.ppo import PPOActorCritic
     from enero_b200.runtime import Context
     from oracle import enero_oracle as orc
     from test_gpu_train import BETA, _critic_weights, _rollout
     weights = golden_weights()
-    ctx = Context(0)
+    ctx = Context(device)
     ag = PPOActorCritic(context=ctx, entropy_beta=BETA, process_group=process_group)
     ag.actor.set_weights([weights[k] for k in orc.WEIGHT_NAMES])
     cw = _critic_weights(weights)
@@ -45,11 +46,11 @@ def run_steps(ag):
     return wa, wc, np.array(losses)
 
 
-def main(out_dir):
+def main(out_dir, backend="gloo"):
     import torch.distributed as dist
     from enero_b200 import parallel as par
-    rank, world, _ = par.init_process_group("gloo")
-    ag = build_agent_and_samples(out_dir, process_group=dist.group.WORLD)
+    rank, world, local = par.init_process_group(backend)
+    ag = build_agent_and_samples(out_dir, process_group=dist.group.WORLD, device=local if backend == "nccl" else 0)
     wa, wc, losses = run_steps(ag)
     np.savez(os.path.join(out_dir, "rank%d.npz" % rank), wa=wa, wc=wc, losses=losses)
     dist.barrier()
@@ -57,4 +58,4 @@ def main(out_dir):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1])
+    main(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else "gloo")

@@ -227,37 +227,50 @@ def test_accumulate_rejects_bad_action(agent, weights, tmp_path_factory):
     ag.memory = []
 
 
-def test_sharded_step_matches_single(tmp_path):
-    """SURVEY 8e: the minibatch split over 2 ranks + one all-reduce of the gradient buffer gives the
-    weights of the single-process step (sum order differs: 1e-6 of the update scale) and identical
-    weights on both ranks."""
+def _run_two_ranks(tmp_path, backend):
     import os
     import socket
     import subprocess
     import sys
     here = os.path.dirname(os.path.abspath(__file__))
     sys.path.insert(0, os.path.join(here, "helpers"))
-    import ppo_worker
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
     procs = []
     for rank in range(2):
-        env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", LOCAL_RANK="0", MASTER_ADDR="127.0.0.1",
-                   MASTER_PORT=str(port))
-        procs.append(subprocess.Popen([sys.executable, os.path.join(here, "helpers", "ppo_worker.py"), str(tmp_path)],
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", LOCAL_RANK=str(rank) if backend == "nccl" else "0",
+                   MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, os.path.join(here, "helpers", "ppo_worker.py"), str(tmp_path), backend],
                                       env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
     outs = [p.communicate(timeout=600)[0].decode() for p in procs]
     assert all(p.returncode == 0 for p in procs), "\n".join(outs)
     r0 = np.load(os.path.join(str(tmp_path), "rank0.npz"))
     r1 = np.load(os.path.join(str(tmp_path), "rank1.npz"))
     assert np.array_equal(r0["wa"], r1["wa"]) and np.array_equal(r0["wc"], r1["wc"])
+    import ppo_worker
     ag = ppo_worker.build_agent_and_samples(str(tmp_path))
-    wa0 = np.concatenate([w.reshape(-1) for w in ag.context.download_weights(0)])
+    wa0 = np.concatenate([w.reshape(-1) for w in ag.actor.get_weights()])
     wa, wc, losses = ppo_worker.run_steps(ag)
     ag.context.close()
     upd = np.abs(wa - wa0).max()
     assert upd > 0
     assert np.abs(r0["wa"] - wa).max() <= 1e-3 * upd
     np.testing.assert_allclose(r0["losses"], losses, rtol=1e-4, atol=1e-6)
+
+
+def test_sharded_step_matches_single(tmp_path):
+    """SURVEY 8e: the minibatch split over 2 ranks + one all-reduce of the gradient buffer gives the
+    weights of the single-process step (sum order differs: 1e-6 of the update scale) and identical
+    weights on both ranks.  gloo, both ranks on one GPU: runs on any box."""
+    _run_two_ranks(tmp_path, "gloo")
+
+
+def test_sharded_step_nccl(tmp_path):
+    """the same step with one GPU per rank and the all-reduce carried by NCCL on the library's stream (what a
+    torchrun training job runs); needs two GPUs"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    _run_two_ranks(tmp_path, "nccl")
