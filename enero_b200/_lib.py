@@ -46,6 +46,8 @@ SIGNATURES = {
     "enero_ctx_stream": (_vp, [_vp]),
     "enero_ctx_set_math": (C.c_int, [_vp, C.c_int]),
     "enero_ctx_get_math": (C.c_int, [_vp]),
+    "enero_ctx_set_engine": (C.c_int, [_vp, C.c_int]),
+    "enero_ctx_get_engine": (C.c_int, [_vp]),
     "enero_ctx_profile_begin": (C.c_int, [_vp]),
     "enero_ctx_profile_end": (C.c_int, [_vp, _vp, _vp]),
     "enero_ctx_fp32_peak": (C.c_int, [_vp, _vp]),

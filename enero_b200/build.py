@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libenero_b200.so")
 SOURCES = ("topology.cpp", "ksp.cpp", "ingest.cpp", "api.cu")
-HEADERS = ("enero_internal.h", "ctx.cuh", "gnn_kernels.cuh", "env_kernels.cuh", "train_kernels.cuh", "train_api.cuh", "sap_kernels.cuh", "ubench.cuh",
+HEADERS = ("enero_internal.h", "ctx.cuh", "gnn_kernels.cuh", "mp_tc_kernel.cuh", "env_kernels.cuh", "train_kernels.cuh", "train_api.cuh", "sap_kernels.cuh", "ubench.cuh",
            os.path.join("..", "..", "include", "enero_b200.h"))
 
 NVCC_FLAGS = [
@@ -47,7 +47,8 @@ def is_stale() -> bool:
 def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + _sources()
+    extra = os.environ.get("ENERO_NVCC_EXTRA", "").split()
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + _sources()
     proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), proc.stdout))

@@ -17,6 +17,7 @@
 #include "enero_internal.h"
 #include "env_kernels.cuh"
 #include "gnn_kernels.cuh"
+#include "mp_tc_kernel.cuh"
 #include "sap_kernels.cuh"
 #include "train_kernels.cuh"
 #include "ubench.cuh"
@@ -82,6 +83,32 @@ extern "C" int enero_ctx_create(int device, enero_ctx** out) {
     }
     CUDA_TRY(cudaFuncSetAttribute(k_bwd_gates<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWG_SMEM_BYTES));
     CUDA_TRY(cudaFuncSetAttribute(k_bwd_gates<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWG_SMEM_BYTES));
+    {
+        int r = ENERO_OK;
+        auto setup_tc = [&](auto kern) {
+            if (r == ENERO_OK && (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES) != cudaSuccess ||
+                                  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess)) {
+                enero_set_error(std::string("k_mp_tc setup: ") + cudaGetErrorString(cudaGetLastError()));
+                r = ENERO_ERR_CUDA;
+            }
+        };
+        setup_tc(k_mp_tc<false, 20, false>); setup_tc(k_mp_tc<true, 20, false>); setup_tc(k_mp_tc<false, 3, false>);
+        setup_tc(k_mp_tc<false, 20, true>); setup_tc(k_mp_tc<true, 20, true>); setup_tc(k_mp_tc<false, 3, true>);
+        if (r != ENERO_OK) return r;
+        // resident CTAs per SM from the kernel's own resources (registers, shared memory, 128 of the 512 TMEM columns each):
+        // cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for this kernel on CUDA 12.9, which is not what the SM does
+        cudaFuncAttributes fa;
+        CUDA_TRY(cudaFuncGetAttributes(&fa, k_mp_tc<false, 20, false>));
+        const int by_regs = 65536 / (std::max(1, fa.numRegs) * TC_TPB);
+        const int by_smem = (int)((size_t)prop.sharedMemPerMultiprocessor / (TC_SMEM_BYTES + 1024));
+        c->occ_tc = std::max(1, std::min({by_regs, by_smem, 512 / (TC_GROUPS * TC_TMEM_COLS)}));
+    }
+    c->mp_engine = ENERO_MP_DEFAULT;
+    if (const char* e = std::getenv("ENERO_MP")) {
+        if (!std::strcmp(e, "ffma")) c->mp_engine = 0;
+        else if (!std::strcmp(e, "tc")) c->mp_engine = 1;
+        else return fail(ENERO_ERR_INVALID, "ENERO_MP must be 'ffma' or 'tc'");
+    }
     if (const char* e = std::getenv("ENERO_NO_GRAPHS")) c->no_graphs = std::atoi(e) != 0;
     c->math_acc = ENERO_MATH_DEFAULT;
     if (const char* e = std::getenv("ENERO_MATH")) {
@@ -119,6 +146,23 @@ extern "C" int enero_ctx_set_math(enero_ctx* c, int mode) {
     return ENERO_OK;
 }
 extern "C" int enero_ctx_get_math(enero_ctx* c) { return c ? c->math_acc : -1; }
+extern "C" int enero_ctx_set_engine(enero_ctx* c, int engine) {
+    if (!c || engine < 0 || engine > 1) return fail(ENERO_ERR_INVALID, "enero_ctx_set_engine: engine must be ENERO_MP_FFMA or ENERO_MP_TC");
+    c->mp_engine = engine;
+    return ENERO_OK;
+}
+extern "C" int enero_ctx_get_engine(enero_ctx* c) { return c ? c->mp_engine : -1; }
+#ifdef ENERO_TC_TIMING
+// debugging aid (build with -DENERO_TC_TIMING): cycles thread 0 of every k_mp_tc CTA spent per segment, summed; reading resets
+extern "C" int enero_debug_tc_counters(enero_ctx* c, unsigned long long* out) {
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaMemcpyFromSymbol(out, tc_dbg, 64));
+    out[7] = (unsigned long long)c->occ_tc;
+    unsigned long long z[8] = {};
+    CUDA_TRY(cudaMemcpyToSymbol(tc_dbg, z, 64));
+    return ENERO_OK;
+}
+#endif
 
 extern "C" int enero_ctx_profile_begin(enero_ctx* c) {
     if (!c) return fail(ENERO_ERR_INVALID, "null ctx");
@@ -257,6 +301,21 @@ static int launch_iteration(enero_ctx* c, const IDX& idx, int idx_kind, int whic
     const int grid = (int)std::min<int64_t>((ntiles + MP_WARPS - 1) / MP_WARPS, (int64_t)c->num_sms * occ);
     auto go = [&](auto kern) { kern<<<grid, MP_TPB, MP_SMEM_BYTES, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles, ctr); };
     constexpr bool TOPO = std::is_same<IDX, IdxTopo>::value;     // the 3-column first iteration exists for the fused path only
+    if constexpr (TOPO) {
+        if (c->mp_engine == 1) {                                 // tensor-core engine: 128-row tiles, one CTA of 128 threads each
+            const int64_t nt = (idx.rows() + TC_ROWS - 1) / TC_ROWS;
+            const int g = (int)std::min<int64_t>((nt + TC_GROUPS - 1) / TC_GROUPS, (int64_t)c->num_sms * std::max(1, c->occ_tc));
+            auto gtc = [&](auto kern) { kern<<<g, TC_TPB, TC_SMEM_BYTES, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, (int)nt); };
+            if (c->math_acc) {
+                if (last) gtc(k_mp_tc<true, 20, true>); else if (sparse) gtc(k_mp_tc<false, 3, true>); else gtc(k_mp_tc<false, 20, true>);
+            } else {
+                if (last) gtc(k_mp_tc<true, 20, false>); else if (sparse) gtc(k_mp_tc<false, 3, false>); else gtc(k_mp_tc<false, 20, false>);
+            }
+            LAUNCH_CHECK(c);
+            if (c->prof) { CUDA_TRY(cudaEventRecord(e1, c->stream)); c->prof_ev.emplace_back(e0, e1); }
+            return ENERO_OK;
+        }
+    }
     if (c->math_acc) {
         if (last) go(k_mp_iter<IDX, true, 20, true>);
         else if (TOPO && sparse) go(k_mp_iter<IDX, false, TOPO ? 3 : 20, true>);
@@ -741,7 +800,7 @@ static int greedy_step_graph(enero_batch* b) {
     TRY(ensure_rows(c, rows));                                   // no allocation may happen while capturing
     TRY(c->util.ensure((size_t)b->B * d.E * 4));
     const void* key[8] = {c->h[0].p, c->h[1].p, c->A[0].p, c->A[1].p, c->util.p, b->loads.p,
-                          (const void*)(intptr_t)(c->math_acc + 1), (const void*)b->t->dev.in_first};
+                          (const void*)(intptr_t)(c->math_acc + 1 + 4 * c->mp_engine), (const void*)b->t->dev.in_first};
     GreedyGraph& g = b->graph;
     if (g.exec && !std::memcmp(key, g.key, sizeof(key))) return ENERO_OK;
     g.release();

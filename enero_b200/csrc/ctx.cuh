@@ -55,6 +55,8 @@ struct enero_ctx {
     int* tile_ctr = nullptr;                 // [16] dynamic tile counters of k_mp_iter, one per launch of a sequence
     int tile_ctr_next = 16;                  // next unused counter (16 = re-zero first)
     // optional per-launch CUDA-event timing of the dominant kernel (bench.py roofline leg)
+    int mp_engine = 0;                       // ENERO_MP_FFMA (k_mp_iter) / ENERO_MP_TC (k_mp_tc); enero_ctx_set_engine, ENERO_MP
+    int occ_tc = 1;                          // resident CTAs/SM of k_mp_tc
     bool no_graphs = false;                  // ENERO_NO_GRAPHS=1: enqueue every launch of a greedy episode individually
     bool prof = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_ev;

@@ -97,6 +97,17 @@ class Context:
             raise ValueError("math mode must be 'fast' or 'accurate'")
         _lib.check(self._lib.enero_ctx_set_math(self._h, _lib.MATH_ACCURATE if mode == "accurate" else _lib.MATH_FAST))
 
+    @property
+    def engine(self) -> str:
+        """'ffma' (k_mp_iter, FP32 pipe) or 'tc' (k_mp_tc, tcgen05 tensor cores with 3xTF32 products)"""
+        return "tc" if self._lib.enero_ctx_get_engine(self._h) == 1 else "ffma"
+
+    @engine.setter
+    def engine(self, name: str):
+        if name not in ("ffma", "tc"):
+            raise ValueError("engine must be 'ffma' or 'tc'")
+        _lib.check(self._lib.enero_ctx_set_engine(self._h, 1 if name == "tc" else 0))
+
     def fp32_peak_tflops(self) -> float:
         """FP32 FMA peak of this device, measured live (FFMA2 register loop)"""
         v = C.c_double(0)

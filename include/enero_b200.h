@@ -46,6 +46,10 @@ extern "C" {
 #define ENERO_MATH_ACCURATE 1
 #define ENERO_MATH_DEFAULT ENERO_MATH_FAST
 
+#define ENERO_MP_FFMA 0
+#define ENERO_MP_TC 1
+#define ENERO_MP_DEFAULT ENERO_MP_TC
+
 #define ENERO_H 20            /* link_state_dim  (train_Enero_3top_script.py:83) */
 #define ENERO_NPARAMS 4201    /* parameters per model, Keras variable order (:238-248) */
 #define ENERO_GRAD_STRIDE 4204  /* floats between the actor and critic halves of the gradient buffer */
@@ -73,6 +77,11 @@ void* enero_ctx_stream(enero_ctx* ctx);
  * sets the mode a new ctx starts with.  get returns the mode, or -1 for a null ctx. */
 int enero_ctx_set_math(enero_ctx* ctx, int mode);
 int enero_ctx_get_math(enero_ctx* ctx);
+/* engine of the message-passing iterations of the fused paths (decision batch, value batch, training forward):
+ * ENERO_MP_FFMA = k_mp_iter (mat-vecs on the FP32 pipe), ENERO_MP_TC = k_mp_tc (tcgen05 tensor cores, 3xTF32
+ * fp32-grade products, accumulators in TMEM).  ENERO_MP=ffma|tc sets what a new ctx starts with. */
+int enero_ctx_set_engine(enero_ctx* ctx, int engine);
+int enero_ctx_get_engine(enero_ctx* ctx);
 
 /* per-launch CUDA-event timing of the dominant kernel (k_mp_iter) between begin and end:
  * total milliseconds and number of launches (bench.py's roofline leg; off by default) */
