@@ -566,6 +566,15 @@ struct enero_batch {
     int max_len = 0;
 };
 
+// A topology has ONE device mirror (the one-process-per-GPU model): if another context moved it to a different
+// device since this batch was created, every pointer the batch would hand to a kernel is stale -- refuse loudly.
+static int check_batch_device(const enero_batch* b, const char* who) {
+    if (b->t->dev_id != b->c->device)
+        return fail(ENERO_ERR_STATE, std::string(who) + ": the topology's device mirror now lives on another GPU "
+                    "(enero_topo_upload from a context of a different device); use one topology object per device");
+    return ENERO_OK;
+}
+
 static EpisodeView ep_view(enero_batch* b) {
     EpisodeView v;
     v.B = b->B; v.Dmax = b->Dmax; v.tm = b->tm.as<double>(); v.loads = b->loads.as<double>(); v.mid_cur = b->mid_cur.as<int>();
@@ -613,6 +622,7 @@ extern "C" int enero_batch_dmax(enero_batch* b) { return b ? b->Dmax : -1; }
 extern "C" int enero_batch_reset(enero_batch* b, const double* tms) {
     ENERO_TRACE("enero_batch_reset");
     if (!b || !tms) return fail(ENERO_ERR_INVALID, "enero_batch_reset: null argument");
+    TRY(check_batch_device(b, "enero_batch_reset"));
     enero_ctx* c = b->c; enero_topo* t = b->t;
     CUDA_TRY(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
@@ -692,6 +702,7 @@ extern "C" int enero_batch_restore(enero_batch* b) {
 extern "C" int enero_batch_policy(enero_batch* b, float* probs_host, int32_t* nK_host) {
     ENERO_TRACE("enero_batch_policy");
     if (!b) return fail(ENERO_ERR_INVALID, "enero_batch_policy: null batch");
+    TRY(check_batch_device(b, "enero_batch_policy"));
     if (!b->reset_done) return fail(ENERO_ERR_STATE, "enero_batch_policy: reset first");
     enero_ctx* c = b->c;
     CUDA_TRY(cudaSetDevice(c->device));
@@ -706,6 +717,7 @@ extern "C" int enero_batch_policy(enero_batch* b, float* probs_host, int32_t* nK
 
 extern "C" int enero_batch_value(enero_batch* b, float* values_host) {
     if (!b || !values_host) return fail(ENERO_ERR_INVALID, "enero_batch_value: null argument");
+    TRY(check_batch_device(b, "enero_batch_value"));
     if (!b->reset_done) return fail(ENERO_ERR_STATE, "enero_batch_value: reset first");
     enero_ctx* c = b->c;
     CUDA_TRY(cudaSetDevice(c->device));
@@ -746,6 +758,7 @@ static int step_dev(enero_batch* b) {
 extern "C" int enero_batch_step(enero_batch* b, const int32_t* actions, double* reward, uint8_t* done) {
     ENERO_TRACE("enero_batch_step");
     if (!b) return fail(ENERO_ERR_INVALID, "enero_batch_step: null batch");
+    TRY(check_batch_device(b, "enero_batch_step"));
     if (!b->reset_done) return fail(ENERO_ERR_STATE, "enero_batch_step: reset first");
     enero_ctx* c = b->c;
     CUDA_TRY(cudaSetDevice(c->device));
@@ -767,6 +780,7 @@ extern "C" int enero_batch_step_state(enero_batch* b, const int32_t* actions, do
                                       int32_t* cur, double* bw, double* max_uti, int32_t* max_edge) {
     ENERO_TRACE("enero_batch_step_state");
     if (!b || !actions) return fail(ENERO_ERR_INVALID, "enero_batch_step_state: null argument");
+    TRY(check_batch_device(b, "enero_batch_step_state"));
     if (!b->reset_done) return fail(ENERO_ERR_STATE, "enero_batch_step_state: reset first");
     enero_ctx* c = b->c;
     CUDA_TRY(cudaSetDevice(c->device));
@@ -827,6 +841,7 @@ static int greedy_step_graph(enero_batch* b) {
 extern "C" int enero_batch_run_greedy(enero_batch* b) {
     ENERO_TRACE("enero_batch_run_greedy");
     if (!b) return fail(ENERO_ERR_INVALID, "enero_batch_run_greedy: null batch");
+    TRY(check_batch_device(b, "enero_batch_run_greedy"));
     if (!b->reset_done) return fail(ENERO_ERR_STATE, "enero_batch_run_greedy: reset first");
     enero_ctx* c = b->c;
     CUDA_TRY(cudaSetDevice(c->device));
@@ -939,6 +954,7 @@ extern "C" int enero_batch_local_search(enero_batch* b, int mode, const int32_t*
                                         int32_t* moves, double* move_val) {
     ENERO_TRACE("enero_batch_local_search");
     if (!b) return fail(ENERO_ERR_INVALID, "enero_batch_local_search: null batch");
+    TRY(check_batch_device(b, "enero_batch_local_search"));
     if (mode < 0 || mode > 1 || max_moves < 0) return fail(ENERO_ERR_INVALID, "enero_batch_local_search: bad mode / max_moves");
     enero_ctx* c = b->c; enero_topo* t = b->t;
     CUDA_TRY(cudaSetDevice(c->device));
@@ -1047,6 +1063,7 @@ extern "C" int enero_batch_get_ls_eligible(enero_batch* b, int32_t* elig, int32_
 extern "C" int enero_batch_sap(enero_batch* b, const double* tms, int K, uint32_t seed, double* max_uti, int32_t* actions) {
     ENERO_TRACE("enero_batch_sap");
     if (!b || K < 1) return fail(ENERO_ERR_INVALID, "enero_batch_sap: bad argument");
+    TRY(check_batch_device(b, "enero_batch_sap"));
     if (!tms && !b->reset_done) return fail(ENERO_ERR_STATE, "enero_batch_sap: no traffic matrices (pass tms or reset the batch first)");
     enero_ctx* c = b->c; enero_topo* t = b->t;
     CUDA_TRY(cudaSetDevice(c->device));
@@ -1085,6 +1102,7 @@ extern "C" int enero_batch_sap(enero_batch* b, const double* tms, int K, uint32_
 extern "C" int enero_batch_ls_route_add(enero_batch* b, int episode, int src, int dst, double value, double* loads_host,
                                         double* max_uti, int32_t* max_edge) {
     if (!b || episode < 0 || episode >= b->B) return fail(ENERO_ERR_INVALID, "enero_batch_ls_route_add: bad episode");
+    TRY(check_batch_device(b, "enero_batch_ls_route_add"));
     enero_topo* t = b->t; enero_ctx* c = b->c;
     if (src < 0 || dst < 0 || src >= t->N || dst >= t->N || src == dst) return fail(ENERO_ERR_INVALID, "enero_batch_ls_route_add: bad path end points");
     CUDA_TRY(cudaSetDevice(c->device));

@@ -4,12 +4,17 @@ minibatches of 55), greedy evaluation on 20 TMs x 3 topologies, the tagged log-l
 (``a,`` ``c,`` ``;,`` ``+,`` ``<,`` ``>,`` ``ENTR,`` ``REW,`` ``lr,`` ``MAX REWD: x REWD_ID: n,``),
 ``ckpt_ACT-n`` / ``ckpt_CRT-n`` checkpoints and the ``(max_reward, lr)`` pickle.
 
-Differences from the reference, all in how the work is laid out, none in what is computed:
+Differences from the reference in how the work is laid out:
   * the 60 greedy evaluation episodes run as three device-resident batches of 20 instead of 60
     sequential Python episodes;
   * with a process group, every rank owns the rollouts of the topologies ``rank::world`` (per-topology
     numpy RNG streams), the sample records are all-gathered (a few KB each), and each PPO minibatch is
-    split over the ranks with one gradient all-reduce per Adam step.
+    split over the ranks with one gradient all-reduce per Adam step; only rank 0 writes the log
+    and the checkpoints.
+``run()`` reproduces the launch schedule of train_Enero_3top.py / train_Enero_3top_script.py:428-444 as the
+reference EXECUTES it (the logged learning rate compounds on the pickled value, the optimiser keeps the
+checkpointed learning rate, the Python / numpy RNGs are re-seeded at every 20-episode launch); the behaviour
+the script's author probably intended (the decayed rate actually applied) is behind ``apply_decayed_lr=True``.
 """
 from __future__ import annotations
 
@@ -41,6 +46,19 @@ def decayed_learning_rate(step, base=0.0002):
     return 10e-5 if lr < 10e-5 else lr
 
 
+def launch_schedule(first_iteration, n_iterations, lr, episodes_per_launch=20, base_entropy_beta=ENTROPY_BETA):
+    """(iteration, learning rate as logged / pickled, entropy weight, launch boundary?) for every PPO episode of
+    train_Enero_3top.py's loop, as the reference executes it (train_Enero_3top_script.py:428-444): at a launch
+    boundary whose iteration is a multiple of 60 the rate becomes lr * 0.96 ** (i / 60) floored at 1e-4, compounding
+    on the value pickled by the previous launch -- Logs/expSP_3top_15_B_NEWLogs.txt shows exactly this sequence
+    (0.0002, 0.000192, 0.0001769472, 0.0001565515579392, ...)."""
+    for i in range(first_iteration, first_iteration + n_iterations):
+        boundary = (i - first_iteration) % episodes_per_launch == 0
+        if boundary and i % DECAY_STEPS == 0:
+            lr = decayed_learning_rate(i, lr)
+        yield i, lr, (base_entropy_beta / 10 if i >= ENTROPY_STEP else base_entropy_beta), boundary
+
+
 class TrainingRun:
     def __init__(self, ctx, train_envs, eval_envs, quotas, percentage_demands=0.15, learning_rate=None,
                  entropy_beta=ENTROPY_BETA, log_path=None, checkpoint_dir=None, counter=1, max_reward=-1000.0,
@@ -53,7 +71,11 @@ class TrainingRun:
         self.agent = PPOActorCritic(context=ctx, buff_size=sum(self.quotas), learning_rate=self.lr,
                                     entropy_beta=entropy_beta, process_group=process_group)
         self.pg = process_group
-        self.log = open(log_path, "a") if log_path else None
+        self._rank0 = True
+        if process_group is not None:
+            import torch.distributed as dist
+            self._rank0 = dist.get_rank(process_group) == 0
+        self.log = open(log_path, "a") if (log_path and self._rank0) else None
         self.checkpoint_dir = checkpoint_dir
         self.counter = counter
         self.max_reward = max_reward
@@ -228,14 +250,22 @@ class TrainingRun:
         if self.log:
             self.log.flush()
         if self.checkpoint_dir:
-            os.makedirs(self.checkpoint_dir, exist_ok=True)
             self.agent.store_optimizer_state()
-            prefix = os.path.join(self.checkpoint_dir, "ckpt")
-            # a restored checkpoint carries save_counter = counter - 1, so save() writes ckpt_*-<counter>
-            self.checkpoint_actor.save_counter = self.counter - 1
-            self.checkpoint_critic.save_counter = self.counter - 1
-            self.checkpoint_actor.save(prefix + "_ACT")
-            self.checkpoint_critic.save(prefix + "_CRT")
+            if self._rank0:                       # one writer; files appear under their final names atomically
+                os.makedirs(self.checkpoint_dir, exist_ok=True)
+                tmp_dir = tempfile.mkdtemp(prefix=".ckpt_tmp_", dir=self.checkpoint_dir)
+                # a restored checkpoint carries save_counter = counter - 1, so save() writes ckpt_*-<counter>
+                self.checkpoint_actor.save_counter = self.counter - 1
+                self.checkpoint_critic.save_counter = self.counter - 1
+                self.checkpoint_actor.save(os.path.join(tmp_dir, "ckpt_ACT"))
+                self.checkpoint_critic.save(os.path.join(tmp_dir, "ckpt_CRT"))
+                names = sorted(os.listdir(tmp_dir), key=lambda f: f == "checkpoint")     # the `checkpoint` index file last
+                for f in names:
+                    os.replace(os.path.join(tmp_dir, f), os.path.join(self.checkpoint_dir, f))
+                os.rmdir(tmp_dir)
+            if self.pg is not None:
+                import torch.distributed as dist
+                dist.barrier(group=self.pg)
         self.counter += 1
         n = len(buf["tensors"])
         steps = 8 * ((n + 54) // 55)
@@ -243,20 +273,29 @@ class TrainingRun:
                 "actor_loss": actor_loss, "critic_loss": critic_loss, "eval_mean_reward": eval_mean,
                 "eval_max_uti": float(np.amax(max_link_uti)), "update_samples_per_s": 8 * n / (t2 - t1)}
 
-    def run(self, first_iteration, n_iterations, episodes_per_launch=20, base_lr=0.0002, base_entropy_beta=ENTROPY_BETA):
-        """the outer schedule of train_Enero_3top.py:28-34 + train script :438-444: the trainer is re-entered every
-        `episodes_per_launch` PPO episodes; at each entry the learning rate decays (x0.96^(i/60), floor 1e-4) when i is
-        a multiple of 60 and the entropy weight drops to a tenth from episode 60 on.  (The reference's restore then
-        overwrites the optimizer's learning rate with the checkpointed one; here the decayed value is
-        the one that is used, as the script's author intended.)"""
+    def run(self, first_iteration, n_iterations, episodes_per_launch=20, base_entropy_beta=ENTROPY_BETA,
+            apply_decayed_lr=False):
+        """The outer schedule of train_Enero_3top.py:28-34 + train_Enero_3top_script.py:428-444, one "launch" every
+        `episodes_per_launch` PPO episodes, exactly as the reference executes it:
+          * ``hparams['learning_rate']`` starts from the value the previous launch pickled (``self.lr``) and, when the
+            iteration is a multiple of 60, becomes ``lr * 0.96 ** (i / 60)`` floored at 1e-4 -- it COMPOUNDS on the
+            pickled value (:97-101, :433-440); this is the number the ``lr,`` log lines and the pickle carry;
+          * the optimiser does not see it: ``checkpoint.restore`` (:452-457) overwrites the freshly built Adam's
+            learning rate with the checkpointed one, so training continues at the rate of the first launch
+            (SURVEY quirk Q6).  ``apply_decayed_lr=True`` applies the decayed rate instead;
+          * the entropy weight is a tenth of its base value from iteration 60 on (:442-443);
+          * every launch is a fresh process that seeds ``random`` and ``numpy.random`` with 9 (:34-37), which restarts
+            the traffic-matrix and action sampling sequences."""
         stats = []
-        for i in range(first_iteration, first_iteration + n_iterations):
-            if (i - first_iteration) % episodes_per_launch == 0:
-                if i % DECAY_STEPS == 0:
-                    self.lr = decayed_learning_rate(i, base_lr)
-                    self.agent.optimizer.learning_rate = np.float32(self.lr)
-                self.entropy_beta = base_entropy_beta / 10 if i >= ENTROPY_STEP else base_entropy_beta
-                self.agent.entropy_beta = float(self.entropy_beta)
+        for i, lr, beta, boundary in launch_schedule(first_iteration, n_iterations, self.lr, episodes_per_launch, base_entropy_beta):
+            if boundary:
+                self.lr = lr
+                if apply_decayed_lr:
+                    self.agent.optimizer.learning_rate = np.float32(lr)
+                self.entropy_beta = beta
+                self.agent.entropy_beta = float(beta)
+                random.seed(SEED)
+                np.random.seed(SEED)
             stats.append(self.ppo_episode())
         return stats
 

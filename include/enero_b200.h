@@ -11,7 +11,9 @@
  * with a message available from enero_last_error() (thread-local).  No exceptions
  * cross the boundary.  The caller owns every buffer it passes; the library owns
  * handles until the matching *_destroy.  One ctx per (process, device); a ctx is
- * thread-compatible, not thread-safe.  Pointers named *_host are host memory,
+ * thread-compatible, not thread-safe.  A topology keeps ONE device mirror (the deployment model is one process
+ * per GPU): uploading it from a context of another device moves the mirror, and batches created on the first
+ * device then fail with ENERO_ERR_STATE instead of touching freed memory -- use one topology object per device.  Pointers named *_host are host memory,
  * *_dev are device memory on the ctx's device; `ptr_kind` selects per call
  * (ENERO_HOST = 0, ENERO_DEVICE = 1) where both are accepted.
  */
