@@ -44,6 +44,7 @@ SIGNATURES = {
     "enero_ctx_sync": (C.c_int, [_vp]),
     "enero_ctx_launch_count": (C.c_int64, [_vp]),
     "enero_ctx_stream": (_vp, [_vp]),
+    "enero_ctx_set_stream": (C.c_int, [_vp, _vp]),
     "enero_ctx_set_math": (C.c_int, [_vp, C.c_int]),
     "enero_ctx_get_math": (C.c_int, [_vp]),
     "enero_ctx_set_engine": (C.c_int, [_vp, C.c_int]),
@@ -86,6 +87,7 @@ SIGNATURES = {
     "enero_batch_get_ls_eligible": (C.c_int, [_vp, _vp, _vp, C.c_int]),
     "enero_batch_get_ls_state": (C.c_int, [_vp, _vp, _vp]),
     "enero_batch_ls_route_add": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_double, _vp, _vp, _vp]),
+    "enero_batch_rollout": (C.c_int, [_vp, C.c_uint64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "enero_topo_build_ksp": (C.c_int, [_vp, C.c_int]),
     "enero_topo_ksp_sizes": (C.c_int, [_vp, _vp]),
     "enero_topo_get_ksp": (C.c_int, [_vp, _vp, _vp, _vp]),

@@ -46,7 +46,8 @@ extern "C" int enero_ctx_create(int device, enero_ctx** out) {
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     c->num_sms = prop.multiProcessorCount;
-    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
     for (int i = 0; i < 2; ++i) {
         for (float** p : {&c->w[i], &c->adam_m[i], &c->adam_v[i]}) {
             CUDA_TRY(cudaMalloc(p, sizeof(float) * ENERO_GRAD_STRIDE));
@@ -127,7 +128,7 @@ extern "C" int enero_ctx_destroy(enero_ctx* c) {
     for (int i = 0; i < 2; ++i) { cudaFree(c->w[i]); cudaFree(c->adam_m[i]); cudaFree(c->adam_v[i]); }
     cudaFree(c->gradbuf); cudaFree(c->tile_ctr);
     train_release_stores(c);
-    cudaStreamDestroy(c->stream);
+    cudaStreamDestroy(c->own_stream);
     delete c;
     return ENERO_OK;
 }
@@ -139,6 +140,14 @@ extern "C" int enero_ctx_sync(enero_ctx* c) {
 }
 extern "C" int64_t enero_ctx_launch_count(enero_ctx* c) { return c ? c->launches : -1; }
 extern "C" void* enero_ctx_stream(enero_ctx* c) { return c ? (void*)c->stream : nullptr; }
+extern "C" int enero_ctx_set_stream(enero_ctx* c, void* stream) {
+    if (!c) return fail(ENERO_ERR_INVALID, "enero_ctx_set_stream: null ctx");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));                  // nothing of ours is left in flight on the old stream
+    c->stream = stream ? (cudaStream_t)stream : c->own_stream;
+    c->tile_ctr_next = 16;
+    return ENERO_OK;
+}
 
 extern "C" int enero_ctx_set_math(enero_ctx* c, int mode) {
     if (!c || mode < 0 || mode > 1) return fail(ENERO_ERR_INVALID, "enero_ctx_set_math: mode must be ENERO_MATH_FAST or ENERO_MATH_ACCURATE");
@@ -559,6 +568,7 @@ struct enero_batch {
         h_action, h_reward, h_max, last_reward, logits, probs, nK, action, values;
     DevBuf snap;                                    // enero_batch_snapshot image of the mutable state
     DevBuf sap_order, sap_loads, sap_mt, sap_idx, sap_max, sap_act;   // SAP baseline scratch
+    DevBuf r_loads, r_sd, r_bw, r_action, r_prob, r_value;            // rollout records
     DevBuf ls_loads, ls_mid, ls_elig, ls_elig_len, ls_val, ls_nmoves, ls_moves, ls_move_val, ls_max_edge;
     std::vector<int> h_cur; std::vector<uint8_t> h_done; bool mirror_valid = false;   // host mirror of (cur, done) for action checks
     std::vector<int> h_elig, h_elig_len;           // host mirror of list_eligible_demands
@@ -991,13 +1001,22 @@ extern "C" int enero_batch_local_search(enero_batch* b, int mode, const int32_t*
         CUDA_TRY(cudaMemcpyAsync(loads.data(), b->ls_loads.p, loads.size() * 8, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaMemcpyAsync(tm.data(), b->tm.p, tm.size() * 8, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
-        std::vector<int> sel;
-        for (int i = 0; i < B; ++i) {
-            topo_critical_demands(*t, loads.data() + (size_t)i * E, tm.data() + (size_t)i * NN,
-                                  routing + (size_t)i * rstride * 3, n_routing[i], b->pct, sel);
-            std::copy(sel.begin(), sel.end(), b->h_ls_elig.begin() + (size_t)i * cap);
-            b->h_ls_elig_len[i] = (int)sel.size();
-        }
+        // same host work as in enero_batch_reset (Python-dict ordering semantics): independent per
+        // episode, so it runs on all host cores
+        const int nthreads = (int)std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), (unsigned)((B + 63) / 64)));
+        auto work = [&](int tid) {
+            std::vector<int> sel;
+            for (int i = tid; i < B; i += nthreads) {
+                topo_critical_demands(*t, loads.data() + (size_t)i * E, tm.data() + (size_t)i * NN,
+                                      routing + (size_t)i * rstride * 3, n_routing[i], b->pct, sel);
+                std::copy(sel.begin(), sel.end(), b->h_ls_elig.begin() + (size_t)i * cap);
+                b->h_ls_elig_len[i] = (int)sel.size();
+            }
+        };
+        std::vector<std::thread> pool;
+        for (int tid = 1; tid < nthreads; ++tid) pool.emplace_back(work, tid);
+        work(0);
+        for (auto& th : pool) th.join();
     } else {
         for (int i = 0; i < B; ++i) {
             int n = 0;
@@ -1056,6 +1075,47 @@ extern "C" int enero_batch_get_ls_eligible(enero_batch* b, int32_t* elig, int32_
             elig[((size_t)i * cap + k) * 2 + 1] = sdi % N;
         }
     }
+    return ENERO_OK;
+}
+
+// ---- sampled-action rollouts -------------------------------------------------------------------------------------
+extern "C" int enero_batch_rollout(enero_batch* b, uint64_t seed, double* loads, int32_t* sd, double* bw, int32_t* action,
+                                   float* prob, float* value, double* reward, int32_t* steps, float* last_value) {
+    ENERO_TRACE("enero_batch_rollout");
+    if (!b) return fail(ENERO_ERR_INVALID, "enero_batch_rollout: null batch");
+    if (!b->reset_done) return fail(ENERO_ERR_STATE, "enero_batch_rollout: reset first");
+    TRY(check_batch_device(b, "enero_batch_rollout"));
+    enero_ctx* c = b->c; enero_topo* t = b->t;
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const size_t B = b->B, D = b->Dmax, E = t->E;
+    TRY(b->r_loads.ensure(B * D * E * 8)); TRY(b->r_sd.ensure(B * D * 8)); TRY(b->r_bw.ensure(B * D * 8));
+    TRY(b->r_action.ensure(B * D * 4)); TRY(b->r_prob.ensure(B * D * 4)); TRY(b->r_value.ensure(B * D * 4));
+    RolloutRec rec{b->r_loads.as<double>(), b->r_sd.as<int>(), b->r_bw.as<double>(), b->r_action.as<int>(), b->r_prob.as<float>(),
+                   b->r_value.as<float>()};
+    for (int s = 0; s < b->max_len; ++s) {
+        // actor over every candidate of the current demands, critic on the same link loads (train script :495-500)
+        TRY(decide_dev(c, t, b->B, b->loads.as<double>(), b->cur.as<int>(), b->cur_bw.as<double>(), b->done.as<uint8_t>(),
+                       b->logits.as<float>(), b->probs.as<float>(), b->nK.as<int>(), b->action.as<int>(), 5));
+        TRY(value_dev(c, t, b->B, b->loads.as<double>(), b->values.as<float>(), 5));
+        k_rollout_pick<<<(b->B + 3) / 4, 128, 0, st>>>(view_of(t), ep_view(b), t->Kmax, b->probs.as<float>(), b->nK.as<int>(),
+                                                       b->values.as<float>(), seed, rec, b->action.as<int>());
+        LAUNCH_CHECK(c);
+        TRY(step_dev(b));
+    }
+    // value of the state each environment is left in (the bootstrap of train script :622-625 uses the last one)
+    TRY(value_dev(c, t, b->B, b->loads.as<double>(), b->values.as<float>(), 5));
+    b->mirror_valid = false;
+    if (loads) CUDA_TRY(cudaMemcpyAsync(loads, b->r_loads.p, B * D * E * 8, cudaMemcpyDeviceToHost, st));
+    if (sd) CUDA_TRY(cudaMemcpyAsync(sd, b->r_sd.p, B * D * 8, cudaMemcpyDeviceToHost, st));
+    if (bw) CUDA_TRY(cudaMemcpyAsync(bw, b->r_bw.p, B * D * 8, cudaMemcpyDeviceToHost, st));
+    if (action) CUDA_TRY(cudaMemcpyAsync(action, b->r_action.p, B * D * 4, cudaMemcpyDeviceToHost, st));
+    if (prob) CUDA_TRY(cudaMemcpyAsync(prob, b->r_prob.p, B * D * 4, cudaMemcpyDeviceToHost, st));
+    if (value) CUDA_TRY(cudaMemcpyAsync(value, b->r_value.p, B * D * 4, cudaMemcpyDeviceToHost, st));
+    if (reward) CUDA_TRY(cudaMemcpyAsync(reward, b->h_reward.p, B * D * 8, cudaMemcpyDeviceToHost, st));
+    if (steps) CUDA_TRY(cudaMemcpyAsync(steps, b->steps.p, B * 4, cudaMemcpyDeviceToHost, st));
+    if (last_value) CUDA_TRY(cudaMemcpyAsync(last_value, b->values.p, B * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
     return ENERO_OK;
 }
 

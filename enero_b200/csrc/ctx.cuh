@@ -44,7 +44,8 @@ struct DevBuf {
 struct enero_ctx {
     int device = 0;
     int num_sms = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;           // stream every launch / copy of this ctx goes to (enero_ctx_set_stream)
+    cudaStream_t own_stream = nullptr;       // the non-blocking stream the ctx created for itself
     float* w[2] = {nullptr, nullptr};
     int64_t launches = 0;
     // scratch of the GNN engine

@@ -246,6 +246,54 @@ k_env_step(TopoView t, EpisodeView ep, const int* __restrict__ action) {
     }
 }
 
+// ---- sampled-action rollouts (train_Enero_3top_script.py:495-506) ---------------------------------------------
+// Philox4x32-10 counter-based generator: one uniform in [0, 1) per (seed, episode, step), independent of launch
+// geometry and of how the episodes are spread over GPUs.
+__device__ __forceinline__ void philox4x32_10(uint32_t (&ctr)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * ctr[0], p1 = (uint64_t)0xCD9E8D57u * ctr[2];
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ ctr[1] ^ k0, n2 = (uint32_t)(p0 >> 32) ^ ctr[3] ^ k1;
+        ctr[1] = (uint32_t)p1; ctr[3] = (uint32_t)p0; ctr[0] = n0; ctr[2] = n2;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+
+struct RolloutRec {      // per (episode, step) records of one sampled rollout, [B][Dmax] each (loads: [B][Dmax][E])
+    double* loads; int* sd; double* bw; int* action; float* prob; float* value;
+};
+
+// action = np.random.choice(K', p = probs) (train script :502) with a device generator: inverse CDF of the fp32
+// probabilities accumulated in fp64; also records what the PPO buffer keeps of the decision (the state the actor
+// saw, the action, its probability, the critic's value).  One warp per episode.
+__global__ void __launch_bounds__(128)
+k_rollout_pick(TopoView t, EpisodeView ep, int Kmax, const float* __restrict__ probs, const int* __restrict__ nK,
+               const float* __restrict__ values, uint64_t seed, RolloutRec rec, int* __restrict__ action) {
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= ep.B || ep.done[b]) return;
+    const int step = ep.steps[b], k = nK[b];
+    const float* p = probs + (int64_t)b * Kmax;
+    int a = k - 1;
+    if (lane == 0) {
+        uint32_t ctr[4] = {(uint32_t)b, (uint32_t)step, 0u, 0u};
+        philox4x32_10(ctr, (uint32_t)seed, (uint32_t)(seed >> 32));
+        const double u = ((double)ctr[0] * 4294967296.0 + (double)ctr[1]) * (1.0 / 18446744073709551616.0);
+        double tot = 0.0;
+        for (int i = 0; i < k; ++i) tot += (double)p[i];
+        double c = 0.0;
+        for (int i = 0; i < k; ++i) { c += (double)p[i] / tot; if (u < c) { a = i; break; } }
+    }
+    a = __shfl_sync(0xffffffffu, a, 0);
+    const int64_t slot = (int64_t)b * ep.Dmax + step;
+    for (int e = lane; e < t.E; e += 32) rec.loads[slot * t.E + e] = ep.loads[(int64_t)b * t.E + e];
+    if (lane == 0) {
+        action[b] = a;
+        rec.sd[2 * slot] = ep.cur[2 * b]; rec.sd[2 * slot + 1] = ep.cur[2 * b + 1];
+        rec.bw[slot] = ep.cur_bw[b]; rec.action[slot] = a; rec.prob[slot] = p[a]; rec.value[slot] = values[b];
+    }
+}
+
 // one allocate_to_destination_sp / decrease_links_utilization_sp (environment15.py:546-563, 150-165) on the
 // Local-Search loads of one episode, followed by the max-utilisation scan of step_hill_sp (:389-399)
 __global__ void k_ls_route_add(TopoView t, double* __restrict__ loads, int src, int dst, double v,

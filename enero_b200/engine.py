@@ -159,6 +159,18 @@ class EpisodeBatch:
                                                       _lib.ptr(moves), _lib.ptr(vals)))
         return {"start": start, "final": final, "n_moves": n_moves, "moves": moves, "move_val": vals}
 
+    def rollout(self, seed: int):
+        """Sampled-action episodes (train_Enero_3top_script.py:483-625) for the whole batch, device resident
+        -> dict of per-(episode, step) records: loads[B,Dmax,E], sd, bw, action, prob, value, reward, plus
+        steps[B] and last_value[B]."""
+        B, D, E = self.B, self.Dmax, self.topo.E
+        out = {"loads": np.zeros((B, D, E)), "sd": np.zeros((B, D, 2), np.int32), "bw": np.zeros((B, D)),
+               "action": np.zeros((B, D), np.int32), "prob": np.zeros((B, D), np.float32), "value": np.zeros((B, D), np.float32),
+               "reward": np.zeros((B, D)), "steps": np.zeros(B, np.int32), "last_value": np.zeros(B, np.float32)}
+        _lib.check(self._lib.enero_batch_rollout(self._h, int(seed) & 0xFFFFFFFFFFFFFFFF, *[_lib.ptr(out[k]) for k in
+                   ("loads", "sd", "bw", "action", "prob", "value", "reward", "steps", "last_value")]))
+        return out
+
     # ---- Env20 + SAPAgent ----------------------------------------------------------------------
     def sap(self, tms=None, K: int = 5, seed: int = 9, want_actions: bool = False):
         """play_sap_games (script_eval_on_single_topology.py:511-557) for every traffic matrix of the batch

@@ -250,11 +250,11 @@ class PPOActorCritic:
         for pos in range(n):
             a = np.asarray(actions[pos])
             act = int(np.argmax(a)) if a.ndim else int(a)
-            probs = np.asarray(actions_probs[pos], dtype=np.float32)
             sample = dict(tensors[pos])
-            # ratio's denominator: reduce_sum(old_act * old_policy_probs)  (:285)
-            sample.update(action=act, old_prob=np.float32(probs[act]), advantage=np.float32(advantages[pos]),
-                          **{'return': np.float32(returns[pos])})
+            # ratio's denominator: reduce_sum(old_act * old_policy_probs)  (:285); device rollouts record it directly
+            if actions_probs[pos] is not None:
+                sample["old_prob"] = np.float32(np.asarray(actions_probs[pos], dtype=np.float32)[act])
+            sample.update(action=act, advantage=np.float32(advantages[pos]), **{'return': np.float32(returns[pos])})
             self.memory.append(sample)
         self._bind(optimizer=True)
         self._store_memory()

@@ -114,6 +114,11 @@ class Context:
         _lib.check(self._lib.enero_ctx_fp32_peak(self._h, C.byref(v)))
         return v.value
 
+    def set_stream(self, stream=None):
+        """launch on the caller's CUDA stream (raw cudaStream_t as int, or a torch.cuda.Stream); None = the context's own"""
+        raw = getattr(stream, "cuda_stream", stream)
+        _lib.check(self._lib.enero_ctx_set_stream(self._h, C.c_void_p(int(raw)) if raw else None))
+
     def profile_begin(self):
         _lib.check(self._lib.enero_ctx_profile_begin(self._h))
 

@@ -62,7 +62,7 @@ def launch_schedule(first_iteration, n_iterations, lr, episodes_per_launch=20, b
 class TrainingRun:
     def __init__(self, ctx, train_envs, eval_envs, quotas, percentage_demands=0.15, learning_rate=None,
                  entropy_beta=ENTROPY_BETA, log_path=None, checkpoint_dir=None, counter=1, max_reward=-1000.0,
-                 process_group=None, eval_episodes=EVALUATION_EPISODES):
+                 process_group=None, eval_episodes=EVALUATION_EPISODES, rollout_mode="device"):
         self.ctx = ctx
         self.train_envs, self.eval_envs, self.quotas = list(train_envs), list(eval_envs), list(quotas)
         self.pct = percentage_demands
@@ -82,6 +82,8 @@ class TrainingRun:
         self.reward_id = 0
         self.eval_episodes = eval_episodes
         self.training_tm_ids = list(range(100))
+        self.rollout_mode = rollout_mode
+        self._tm_cache = {}
         self.checkpoint_actor = Checkpoint(model=self.agent.actor, optimizer=self.agent.optimizer)
         self.checkpoint_critic = Checkpoint(model=self.agent.critic, optimizer=self.agent.optimizer)
         random.seed(SEED)
@@ -146,8 +148,99 @@ class TrainingRun:
                     break
         return buf
 
+    # ---- rollouts, device resident and batched ------------------------------------------------------
+    def _tm(self, env, tm_id):
+        key = (id(env), int(tm_id))
+        if key not in self._tm_cache:
+            self._tm_cache[key] = ds.parse_demands_file(os.path.join(env.dataset_folder_name, "TM", "%s.%d.demands"
+                                                                     % (env.graph_topology_name, tm_id)), env.numNodes)
+        return self._tm_cache[key]
+
+    def collect_device(self):
+        """The rollouts of train script :483-625 as device-resident batches: every topology runs `episodes per quota`
+        episodes (quota / episode length = 5, 4, 6 with the reference's multipliers) at once through
+        enero_batch_rollout -- actor, critic, action sampling (Philox stream per episode) and Env16.step without a host
+        round trip -- and the records are cut to the topology's quota in (episode, step) order, so the buffer has the
+        reference's shape: topology 1, 2, 3, quota-truncated tails with mask = True, GAE running across the
+        boundaries (quirk Q5).  With a process group the (topology, episode) slots are dealt round-robin to the
+        ranks -- every GPU rolls out -- and the records are all-gathered.  Traffic matrices and action streams are drawn
+        from generators keyed by (SEED, PPO episode, topology, slot): the result does not depend on the number of ranks."""
+        world, rank = 1, 0
+        if self.pg is not None:
+            import torch.distributed as dist
+            world, rank = dist.get_world_size(self.pg), dist.get_rank(self.pg)
+        self.agent._bind()
+        per_topo = []
+        for i, (env, quota) in enumerate(zip(self.train_envs, self.quotas)):
+            d = env.topology.max_decisions(self.pct)
+            per_topo.append(max(1, -(-quota // max(1, d))))
+        rounds = 0
+        recs = {}                                    # (topology, slot) -> record dict of one episode
+        need = [True] * len(self.train_envs)
+        while any(need):
+            slots = [(i, rounds * per_topo[i] + j) for i in range(len(self.train_envs)) if need[i] for j in range(per_topo[i])]
+            mine = slots[rank::world]
+            out = {}
+            for i in sorted({s[0] for s in mine}):
+                env = self.train_envs[i]
+                js = [j for (ii, j) in mine if ii == i]
+                tm_ids = [int(np.random.RandomState((SEED, self.counter, i, j)).choice(self.training_tm_ids)) for j in js]
+                eb = EpisodeBatch(self.ctx, env.topology, len(js), self.pct)
+                try:
+                    eb.reset(np.stack([self._tm(env, t) for t in tm_ids]))
+                    r = eb.rollout(seed=(SEED << 40) ^ (self.counter << 20) ^ (i << 12) ^ js[0])
+                finally:
+                    eb.close()
+                for b, j in enumerate(js):
+                    n = int(r["steps"][b])
+                    out[(i, j)] = {k: np.array(r[k][b, :n]) for k in ("loads", "sd", "bw", "action", "prob", "value", "reward")}
+                    out[(i, j)]["last_value"] = float(r["last_value"][b])
+            if world > 1:
+                import torch.distributed as dist
+                gathered = [None] * world
+                dist.all_gather_object(gathered, out, group=self.pg)
+                for g in gathered:
+                    recs.update(g)
+            else:
+                recs.update(out)
+            rounds += 1
+            for i, quota in enumerate(self.quotas):
+                have = sum(len(v["bw"]) for (ii, _), v in recs.items() if ii == i)
+                need[i] = have < quota
+        buf = {k: [] for k in ("tensors", "critic_features", "actions", "values", "masks", "rewards", "actions_probs")}
+        boot = 0.0
+        for i, (env, quota) in enumerate(zip(self.train_envs, self.quotas)):
+            topo, taken = env.topology, 0
+            for j in sorted(jj for (ii, jj) in recs if ii == i):
+                e = recs[(i, j)]
+                n = len(e["bw"])
+                for s in range(n):
+                    if taken == quota:
+                        break
+                    k = len(topo.middlepoints(int(e["sd"][s, 0]), int(e["sd"][s, 1])))
+                    buf["tensors"].append({"topology": topo, "loads": e["loads"][s], "sd": (int(e["sd"][s, 0]), int(e["sd"][s, 1])),
+                                           "bw": float(e["bw"][s]), "num_candidates": k, "old_prob": np.float32(e["prob"][s])})
+                    buf["critic_features"].append({"topology": topo, "loads": e["loads"][s]})
+                    buf["actions"].append(int(e["action"][s]))
+                    buf["actions_probs"].append(None)
+                    buf["values"].append(np.float32(e["value"][s]))
+                    buf["masks"].append(s != n - 1)
+                    buf["rewards"].append(float(e["reward"][s]))
+                    taken += 1
+                    # value of the state this environment is left in after the sample (train script :622-625)
+                    boot = float(e["value"][s + 1]) if s + 1 < n else e["last_value"]
+                if taken == quota:
+                    break
+        buf["values"] = buf["values"] + [np.float32(boot)]
+        return buf
+
     def collect(self):
-        """-> the experience buffer of one PPO episode (lists, topology 1 then 2 then 3) + bootstrap value"""
+        """-> the experience buffer of one PPO episode (lists, topology 1 then 2 then 3) + bootstrap value.
+        rollout_mode "device" (default): batched device-resident rollouts (collect_device); "host": one environment
+        stepped from Python with the reference's global RNGs (random.sample for the TM, np.random.choice for the action),
+        which replays the reference's sampling sequence decision by decision."""
+        if self.rollout_mode == "device":
+            return self.collect_device()
         world, rank = 1, 0
         if self.pg is not None:
             import torch.distributed as dist

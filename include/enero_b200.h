@@ -75,6 +75,11 @@ int enero_ctx_sync(enero_ctx* ctx);
 int64_t enero_ctx_launch_count(enero_ctx* ctx);
 /* raw cudaStream_t the ctx launches on (for CUDA-event timing by the caller) */
 void* enero_ctx_stream(enero_ctx* ctx);
+/* Stream selection for every later entry point of this ctx, cuBLAS style (one setter instead of a stream argument on
+ * each of the ~40 compute calls): `stream` is the caller's cudaStream_t on the ctx's device, NULL = back to the
+ * ctx's own non-blocking stream.  Entry points documented as asynchronous only enqueue on it; the others return after
+ * it has drained.  The previous stream is synchronised first. */
+int enero_ctx_set_stream(enero_ctx* ctx, void* stream);
 /* math mode of every later launch on this ctx (ENERO_MATH_*); the environment variable ENERO_MATH=fast|accurate
  * sets the mode a new ctx starts with.  get returns the mode, or -1 for a null ctx. */
 int enero_ctx_set_math(enero_ctx* ctx, int mode);
@@ -221,6 +226,16 @@ int enero_batch_ls_route_add(enero_batch* b, int episode, int src, int dst, doub
 int enero_batch_get_ls_state(enero_batch* b, double* loads, int32_t* max_edge);
 /* critical demands chosen by the last enero_batch_local_search reset: elig int32[B,Dcap,2] */
 int enero_batch_get_ls_eligible(enero_batch* b, int32_t* elig, int32_t* elig_len, int cap);
+
+/* ---- sampled-action rollouts (train_Enero_3top_script.py:483-625) -------------------------------------------
+ * Every episode of the batch from its reset state to `done`, device resident: per decision the actor over all
+ * candidates, the critic on the same link loads, action ~ Categorical(probs) from a Philox4x32-10 stream keyed by
+ * (seed, episode, step), Env16.step.  Outputs (nullable), [B,Dmax] unless noted, valid for step < steps[b]:
+ * loads fp64[B,Dmax,E] (the state the actor saw), sd int32[B,Dmax,2], bw fp64, action int32, prob fp32 (old policy's
+ * probability of the action), value fp32 (critic), reward fp64; steps int32[B]; last_value fp32[B] = critic value of
+ * the state each episode ended in (the bootstrap value of :622-625). */
+int enero_batch_rollout(enero_batch* b, uint64_t seed, double* loads, int32_t* sd, double* bw, int32_t* action,
+                        float* prob, float* value, double* reward, int32_t* steps, float* last_value);
 
 /* ---- SAP baseline (GraphEnv-v20 + SAPAgent, results[8] of the evaluation records) -----------------------
  * enero_topo_build_ksp: Env20.compute_SPs (environment20.py:165-196): per node pair the K simple paths with the

@@ -369,3 +369,37 @@ def test_accurate_math_greedy_episode_identical(ctx, weights, tmp_path_factory):
         eb.close()
     finally:
         ctx.math = before
+
+
+def test_caller_stream_and_engines_agree(ctx, weights, tmp_path_factory):
+    """enero_ctx_set_stream (the stream-argument form SURVEY 8b asks for, cuBLAS style): the same decisions on a
+    caller-owned torch stream; and the two message-passing engines (k_mp_tc tensor cores, k_mp_iter FP32 pipe) agree
+    within the element-wise tolerance and on every greedy action."""
+    import torch
+    case, topo, ot = _topos("eli20", tmp_path_factory)
+    ep = case["episodes"][0]
+    tm = np.array(case["tms"][str(ep["tm_id"])])
+    decs = ep["decisions"][:10]
+    loads = np.array([dc["loads_before"] for dc in decs])
+    sd = np.array([[dc["s"], dc["d"]] for dc in decs], dtype=np.int32)
+    bw = np.array([tm[dc["s"], dc["d"]] for dc in decs])
+    base = ctx.decide_batch(topo, loads, sd, bw)
+    s = torch.cuda.Stream(device=ctx.device)
+    ctx.set_stream(s)
+    try:
+        assert ctx.stream == s.cuda_stream
+        mine = ctx.decide_batch(topo, loads, sd, bw)
+    finally:
+        ctx.set_stream(None)
+    for a, b in zip(base, mine):
+        assert np.array_equal(a, b)
+    before = ctx.engine
+    try:
+        out = {}
+        for eng in ("tc", "ffma"):
+            ctx.engine = eng
+            out[eng] = ctx.decide_batch(topo, loads, sd, bw)
+        np.testing.assert_allclose(out["tc"][0], out["ffma"][0], rtol=RTOL, atol=ATOL)
+        assert np.array_equal(out["tc"][3], out["ffma"][3]) and np.array_equal(out["tc"][2], out["ffma"][2])
+    finally:
+        ctx.engine = before

@@ -81,7 +81,8 @@ def test_sharded_eval_partitions(ctx, tmp_path):
     assert np.array_equal(got, full[1]["enero"])
 
 
-def test_training_loop_runs_and_checkpoints(ctx, tmp_path):
+@pytest.mark.parametrize("mode", ["device", "host"])
+def test_training_loop_runs_and_checkpoints(ctx, tmp_path, mode):
     """one PPO episode on three small synthetic topologies: buffer sizes follow the quota rule, the log
     protocol and the checkpoint files match the reference's layout, a restored run resumes the optimiser"""
     from enero_b200 import checkpoint as ckpt
@@ -90,7 +91,7 @@ def test_training_loop_runs_and_checkpoints(ctx, tmp_path):
     log = os.path.join(str(tmp_path), "expLogs.txt")
     cdir = os.path.join(str(tmp_path), "models")
     run = TrainingRun.synthetic(ctx, specs, n_train_tms=6, n_eval_tms=3, folder=os.path.join(str(tmp_path), "data"),
-                                log_path=log, checkpoint_dir=cdir, eval_episodes=3)
+                                log_path=log, checkpoint_dir=cdir, eval_episodes=3, rollout_mode=mode)
     assert run.quotas == [int(np.ceil(0.15 * n * (n - 1))) * m for (n, _, _), m in zip(specs, (5, 4, 6))]
     w0 = np.concatenate([w.reshape(-1) for w in ctx.download_weights(0)])
     st = run.ppo_episode()
