@@ -94,6 +94,7 @@ SIGNATURES = {
     "enero_batch_sap": (C.c_int, [_vp, _vp, C.c_int, C.c_uint32, _vp, _vp]),
     "enero_ppo_grad_buffer": (_vp, [_vp]),
     "enero_ppo_zero_grad": (C.c_int, [_vp]),
+    "enero_ppo_grad_ready": (C.c_int, [_vp]),
     "enero_ppo_accumulate": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_float, C.c_float,
                                        C.c_float, C.c_int]),
     "enero_ppo_store": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -27,6 +27,7 @@ using namespace enero;
 #include "ctx.cuh"
 
 void train_release_stores(enero_ctx* c);
+void train_release_lanes(enero_ctx* c);
 
 // ---------------------------------------------------------------------------------------
 extern "C" int enero_device_count(void) {
@@ -128,6 +129,7 @@ extern "C" int enero_ctx_destroy(enero_ctx* c) {
     for (int i = 0; i < 2; ++i) { cudaFree(c->w[i]); cudaFree(c->adam_m[i]); cudaFree(c->adam_v[i]); }
     cudaFree(c->gradbuf); cudaFree(c->tile_ctr);
     train_release_stores(c);
+    train_release_lanes(c);
     cudaStreamDestroy(c->own_stream);
     delete c;
     return ENERO_OK;
@@ -284,12 +286,14 @@ static TopoView view_of(const enero_topo* t) {
 // ---- message passing driver ---------------------------------------------------------------
 
 // a zeroed tile counter for the next k_mp_iter launch (re-zeroed in batches of 16 on the stream)
-static int next_tile_counter(enero_ctx* c, int** out) {
-    if (c->tile_ctr_next >= 16) {
-        CUDA_TRY(cudaMemsetAsync(c->tile_ctr, 0, 16 * sizeof(int), c->stream));
-        c->tile_ctr_next = 0;
+static int next_tile_counter(enero_ctx* c, int** out, TrainLane* lane = nullptr) {
+    int*& base = lane ? lane->tile_ctr : c->tile_ctr;
+    int& next = lane ? lane->tile_ctr_next : c->tile_ctr_next;
+    if (next >= 16) {
+        CUDA_TRY(cudaMemsetAsync(base, 0, 16 * sizeof(int), lane ? lane->st : c->stream));
+        next = 0;
     }
-    *out = c->tile_ctr + c->tile_ctr_next++;
+    *out = base + next++;
     return ENERO_OK;
 }
 
@@ -297,31 +301,33 @@ static int next_tile_counter(enero_ctx* c, int** out) {
 // sizes the persistent grid and, when profiling is on, brackets the launch with CUDA events
 template <class IDX>
 static int launch_iteration(enero_ctx* c, const IDX& idx, int idx_kind, int which, bool last, bool sparse, const float* hin,
-                            const float* Ain, float* hout, float* Aout) {
+                            const float* Ain, float* hout, float* Aout, TrainLane* lane = nullptr) {
     const int64_t ntiles = (idx.rows() + MP_WROWS - 1) / MP_WROWS;          // 64-row warp tiles
+    const cudaStream_t stream = lane ? lane->st : c->stream;
+    const bool prof = c->prof && !lane;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (c->prof) {
+    if (prof) {
         CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
-        CUDA_TRY(cudaEventRecord(e0, c->stream));
+        CUDA_TRY(cudaEventRecord(e0, stream));
     }
     int* ctr = nullptr;
-    TRY(next_tile_counter(c, &ctr));
+    if (c->mp_engine != 1 || !std::is_same<IDX, IdxTopo>::value) TRY(next_tile_counter(c, &ctr, lane));
     const int occ = std::max(1, c->occ_iter[c->math_acc][idx_kind][last ? 1 : 0]);
     const int grid = (int)std::min<int64_t>((ntiles + MP_WARPS - 1) / MP_WARPS, (int64_t)c->num_sms * occ);
-    auto go = [&](auto kern) { kern<<<grid, MP_TPB, MP_SMEM_BYTES, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles, ctr); };
+    auto go = [&](auto kern) { kern<<<grid, MP_TPB, MP_SMEM_BYTES, stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles, ctr); };
     constexpr bool TOPO = std::is_same<IDX, IdxTopo>::value;     // the 3-column first iteration exists for the fused path only
     if constexpr (TOPO) {
         if (c->mp_engine == 1) {                                 // tensor-core engine: 128-row tiles, one CTA of 128 threads each
             const int64_t nt = (idx.rows() + TC_ROWS - 1) / TC_ROWS;
             const int g = (int)std::min<int64_t>((nt + TC_GROUPS - 1) / TC_GROUPS, (int64_t)c->num_sms * std::max(1, c->occ_tc));
-            auto gtc = [&](auto kern) { kern<<<g, TC_TPB, TC_SMEM_BYTES, c->stream>>>(idx, c->w[which], hin, Ain, hout, Aout, (int)nt); };
+            auto gtc = [&](auto kern) { kern<<<g, TC_TPB, TC_SMEM_BYTES, stream>>>(idx, c->w[which], hin, Ain, hout, Aout, (int)nt); };
             if (c->math_acc) {
                 if (last) gtc(k_mp_tc<true, 20, true>); else if (sparse) gtc(k_mp_tc<false, 3, true>); else gtc(k_mp_tc<false, 20, true>);
             } else {
                 if (last) gtc(k_mp_tc<true, 20, false>); else if (sparse) gtc(k_mp_tc<false, 3, false>); else gtc(k_mp_tc<false, 20, false>);
             }
             LAUNCH_CHECK(c);
-            if (c->prof) { CUDA_TRY(cudaEventRecord(e1, c->stream)); c->prof_ev.emplace_back(e0, e1); }
+            if (prof) { CUDA_TRY(cudaEventRecord(e1, stream)); c->prof_ev.emplace_back(e0, e1); }
             return ENERO_OK;
         }
     }
@@ -335,12 +341,12 @@ static int launch_iteration(enero_ctx* c, const IDX& idx, int idx_kind, int whic
         else go(k_mp_iter<IDX, false, 20, false>);
     }
     LAUNCH_CHECK(c);
-    if (c->prof) { CUDA_TRY(cudaEventRecord(e1, c->stream)); c->prof_ev.emplace_back(e0, e1); }
+    if (prof) { CUDA_TRY(cudaEventRecord(e1, stream)); c->prof_ev.emplace_back(e0, e1); }
     return ENERO_OK;
 }
 static int launch_topo_iteration(enero_ctx* c, const IdxTopo& idx, int which, bool last, bool sparse, const float* hin,
-                                 const float* Ain, float* hout, float* Aout) {
-    return launch_iteration(c, idx, 1, which, last, sparse, hin, Ain, hout, Aout);
+                                 const float* Ain, float* hout, float* Aout, TrainLane* lane = nullptr) {
+    return launch_iteration(c, idx, 1, which, last, sparse, hin, Ain, hout, Aout, lane);
 }
 
 // sparse_first: the rows of iteration 0 have at most 3 non-zero leading columns (fused feature path)

@@ -41,6 +41,27 @@ struct DevBuf {
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+// One concurrent pipeline of the PPO update (train_api.cuh): its own stream, activation / gradient scratch, tile
+// counters and gradient accumulator.  A minibatch holds up to three topologies x {actor, critic}: six independent
+// forward+backward passes of a few thousand rows each, latency bound one by one, which run side by side on six lanes
+// and meet in a fixed-order sum (deterministic) before clip + Adam.
+struct TrainLane {
+    cudaStream_t st = nullptr;
+    cudaEvent_t done = nullptr;
+    bool busy = false;                       // work enqueued since the last join
+    DevBuf t_h[8], t_A[8];                   // h_0..h_T, A_0..A_{T-1} of a training forward
+    DevBuf t_agg, t_G, t_dB, t_dA, t_B, t_dagg, t_dhpart, t_dh[2], t_V, t_dlogit, t_partials;
+    DevBuf util, t_nK, t_logits, t_loss, t_ent;
+    float* grad = nullptr;                   // [ENERO_GRAD_STRIDE + 4]: gradient of this lane's model | its loss sums
+    int* tile_ctr = nullptr; int tile_ctr_next = 16;
+};
+struct TrainGroup {                          // the samples of one topology in the current minibatch + its two lanes
+    DevBuf t_loads, t_sd, t_bw, t_action, t_oldp, t_adv, t_ret;
+    cudaEvent_t ready = nullptr;
+    TrainLane lane[2];                       // [ENERO_ACTOR], [ENERO_CRITIC]
+};
+constexpr int TRAIN_GROUPS = 3;
+
 struct enero_ctx {
     int device = 0;
     int num_sms = 0;
@@ -68,9 +89,10 @@ struct enero_ctx {
     float* grad[2] = {nullptr, nullptr};      // views into gradbuf
     float* adam_m[2] = {nullptr, nullptr};
     float* adam_v[2] = {nullptr, nullptr};
-    DevBuf t_h[8], t_A[8];   // h_0..h_T, A_0..A_{T-1} of a training forward
-    DevBuf t_agg, t_G, t_dB, t_dA, t_B, t_dagg, t_dhpart, t_dh[2], t_V, t_dlogit, t_partials;
-    DevBuf t_loads, t_sd, t_bw, t_action, t_oldp, t_adv, t_ret, t_logits, t_probs, t_nK, t_loss, t_ent, t_norm, t_hist;
+    TrainGroup* groups = nullptr;             // [TRAIN_GROUPS], created on first use
+    int group_cursor = 0;
+    float** lane_ptrs = nullptr;              // device array of the lanes' gradient buffers (k_join_lanes)
+    DevBuf t_norm, t_hist;
     void* sample_stores = nullptr;            // topology -> device-resident PPO samples (train_api.cuh)
 };
 

@@ -16,6 +16,7 @@ struct TrainTopo {           // launch geometry of one model's pass over n sampl
 
 int ensure_ones(enero_ctx* c, int B) {
     if (c->ones.cap >= (size_t)B * 4) return ENERO_OK;
+    CUDA_TRY(cudaDeviceSynchronize());                           // lanes may still be reading the old buffer
     TRY(c->ones.ensure((size_t)B * 4));
     std::vector<int> one((size_t)c->ones.cap / 4, 1);
     CUDA_TRY(cudaMemcpyAsync(c->ones.p, one.data(), one.size() * 4, cudaMemcpyHostToDevice, c->stream));
@@ -23,88 +24,164 @@ int ensure_ones(enero_ctx* c, int B) {
     return ENERO_OK;
 }
 
+int ensure_lanes(enero_ctx* c) {
+    if (c->groups) return ENERO_OK;
+    c->groups = new TrainGroup[TRAIN_GROUPS];
+    for (int g = 0; g < TRAIN_GROUPS; ++g) {
+        CUDA_TRY(cudaEventCreateWithFlags(&c->groups[g].ready, cudaEventDisableTiming));
+        for (TrainLane& L : c->groups[g].lane) {
+            CUDA_TRY(cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking));
+            CUDA_TRY(cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming));
+            CUDA_TRY(cudaMalloc(&L.grad, sizeof(float) * (ENERO_GRAD_STRIDE + 4)));
+            CUDA_TRY(cudaMemset(L.grad, 0, sizeof(float) * (ENERO_GRAD_STRIDE + 4)));
+            CUDA_TRY(cudaMalloc(&L.tile_ctr, 16 * sizeof(int)));
+        }
+    }
+    return ENERO_OK;
+}
+
 // forward with saved activations: h_0/A_0 must already be in t_h[0]/t_A[0]
-int train_forward(enero_ctx* c, const IdxTopo& idx, int which, int T, int64_t rows) {
+int train_forward(enero_ctx* c, TrainLane& L, const IdxTopo& idx, int which, int T, int64_t rows) {
     if (rows >= (int64_t)1 << 31) return fail(ENERO_ERR_INVALID, "more than 2^31 link-state rows in one launch: split the minibatch");
     for (int it = 0; it < T; ++it) {
         const bool last = (it == T - 1);
-        TRY(launch_topo_iteration(c, idx, which, last, it == 0 && !last, c->t_h[it].as<float>(), c->t_A[it].as<float>(),
-                                  c->t_h[it + 1].as<float>(), last ? nullptr : c->t_A[it + 1].as<float>()));
+        TRY(launch_topo_iteration(c, idx, which, last, it == 0 && !last, L.t_h[it].as<float>(), L.t_A[it].as<float>(),
+                                  L.t_h[it + 1].as<float>(), last ? nullptr : L.t_A[it + 1].as<float>(), &L));
     }
     return ENERO_OK;
 }
 
 // backward through the readout and the T message-passing iterations; dlogit [n*Kmax] on device
-int train_backward(enero_ctx* c, enero_topo* t, const TrainTopo& g, int which, int T, const float* dlogit) {
+int train_backward(enero_ctx* c, TrainLane& L, enero_topo* t, const TrainTopo& g, int which, int T, const float* dlogit) {
     const TopoDev& d = t->dev;
-    cudaStream_t st = c->stream;
+    cudaStream_t st = L.st;
     const int64_t rows = g.rows;
     const size_t rb = (size_t)rows * H * sizeof(float);
-    TRY(c->t_agg.ensure(rb)); TRY(c->t_G.ensure(4 * rb)); TRY(c->t_dB.ensure(rb)); TRY(c->t_dA.ensure(rb));
-    TRY(c->t_B.ensure(rb)); TRY(c->t_dagg.ensure(rb)); TRY(c->t_dhpart.ensure(rb));
-    TRY(c->t_dh[0].ensure(rb)); TRY(c->t_dh[1].ensure(rb));
+    TRY(L.t_agg.ensure(rb)); TRY(L.t_G.ensure(4 * rb)); TRY(L.t_dB.ensure(rb)); TRY(L.t_dA.ensure(rb));
+    TRY(L.t_B.ensure(rb)); TRY(L.t_dagg.ensure(rb)); TRY(L.t_dhpart.ensure(rb));
+    TRY(L.t_dh[0].ensure(rb)); TRY(L.t_dh[1].ensure(rb));
     const int n_graphs = g.n * g.Kmax;
-    TRY(c->t_V.ensure((size_t)n_graphs * 6 * H * 4));
-    const int wg_grid = (int)std::min<int64_t>((rows + WG_ROWS - 1) / WG_ROWS, 2 * (int64_t)c->num_sms);
-    const int rw_grid = (n_graphs + RW_CHUNK - 1) / RW_CHUNK;
-    TRY(c->t_partials.ensure(std::max((size_t)wg_grid * WG_PART, (size_t)rw_grid * RW_NOUT) * 4));
+    TRY(L.t_V.ensure((size_t)n_graphs * 6 * H * 4));
+    const int wg_grid = (int)std::min<int64_t>((rows + WG_ROWS - 1) / WG_ROWS, (int64_t)c->num_sms);
+    TRY(L.t_partials.ensure((size_t)wg_grid * WG_PART * 4));
     IdxTopo idx{rows, g.E, d.off_f, d.off_s, g.RPD, g.nK, d.in_off, d.in_first};
     OutTopo out{g.E, d.off_f, d.off_s, g.RPD, g.nK, d.out_off, d.out_second};
     GraphsTopo gr{g.n, g.Kmax, g.E, g.RPD, g.nK};
-    float* grad = c->grad[which];
+    float* grad = L.grad;
     const float* w = c->w[which];
-    k_readout_bwd<<<(n_graphs + 3) / 4, 128, 0, st>>>(gr, w, c->t_h[T].as<float>(), dlogit, c->t_dh[0].as<float>(), c->t_V.as<float>());
+    k_readout_bwd<<<(n_graphs + 3) / 4, 128, 0, st>>>(gr, w, L.t_h[T].as<float>(), dlogit, L.t_dh[0].as<float>(), L.t_V.as<float>());
     LAUNCH_CHECK(c);
-    k_readout_wgrad<<<rw_grid, 256, 0, st>>>(n_graphs, g.Kmax, g.nK, c->t_V.as<float>(), c->t_partials.as<float>()); LAUNCH_CHECK(c);
-    k_reduce_rows<<<(RW_NOUT + 255) / 256, 256, 0, st>>>(rw_grid, RW_NOUT, c->t_partials.as<float>(), grad + W_R1_K); LAUNCH_CHECK(c);
+    k_readout_wgrad<<<(RW_NOUT + 127) / 128, 128, 0, st>>>(n_graphs, g.Kmax, g.nK, L.t_V.as<float>(), grad + W_R1_K); LAUNCH_CHECK(c);
     const int bgrid = (int)((rows + BW_TPB - 1) / BW_TPB);
     int cur = 0;
     for (int it = T - 1; it >= 0; --it) {
-        const float* ht = c->t_h[it].as<float>();
-        const float* At = c->t_A[it].as<float>();
+        const float* ht = L.t_h[it].as<float>();
+        const float* At = L.t_A[it].as<float>();
         auto gates = [&](auto kern) {
-            kern<<<bgrid, BW_TPB, BWG_SMEM_BYTES, st>>>(idx, w, ht, At, c->t_dh[cur].as<float>(), c->t_agg.as<float>(), c->t_G.as<float>(),
-                                                        c->t_B.as<float>(), c->t_dagg.as<float>(), c->t_dhpart.as<float>());
+            kern<<<bgrid, BW_TPB, BWG_SMEM_BYTES, st>>>(idx, w, ht, At, L.t_dh[cur].as<float>(), L.t_agg.as<float>(), L.t_G.as<float>(),
+                                                        L.t_B.as<float>(), L.t_dagg.as<float>(), L.t_dhpart.as<float>());
         };
         if (c->math_acc) gates(k_bwd_gates<true>); else gates(k_bwd_gates<false>);
         LAUNCH_CHECK(c);
         auto msgs = [&](auto kern, float* dh_prev) {
-            kern<<<bgrid, BW_TPB, 0, st>>>(idx, out, w, At, c->t_B.as<float>(), c->t_dagg.as<float>(), c->t_dhpart.as<float>(),
-                                           c->t_dB.as<float>(), c->t_dA.as<float>(), dh_prev);
+            kern<<<bgrid, BW_TPB, 0, st>>>(idx, out, w, At, L.t_B.as<float>(), L.t_dagg.as<float>(), L.t_dhpart.as<float>(),
+                                           L.t_dB.as<float>(), L.t_dA.as<float>(), dh_prev);
         };
         if (it > 0) {
-            if (c->math_acc) msgs(k_bwd_msgs<true, true>, c->t_dh[cur ^ 1].as<float>());
-            else msgs(k_bwd_msgs<true, false>, c->t_dh[cur ^ 1].as<float>());
+            if (c->math_acc) msgs(k_bwd_msgs<true, true>, L.t_dh[cur ^ 1].as<float>());
+            else msgs(k_bwd_msgs<true, false>, L.t_dh[cur ^ 1].as<float>());
         } else {
             if (c->math_acc) msgs(k_bwd_msgs<false, true>, nullptr);
             else msgs(k_bwd_msgs<false, false>, nullptr);
         }
         LAUNCH_CHECK(c);
-        WgradIter wi{ht, c->t_agg.as<float>(), c->t_G.as<float>(), c->t_dB.as<float>(), c->t_dA.as<float>()};
-        k_wgrad<<<wg_grid, WG_TPB, 0, st>>>(idx, wi, (rows + WG_ROWS - 1) / WG_ROWS, c->t_partials.as<float>()); LAUNCH_CHECK(c);
-        k_reduce_partials<<<(W_MP_FLOATS + 255) / 256, 256, 0, st>>>(wg_grid, c->t_partials.as<float>(), grad); LAUNCH_CHECK(c);
+        WgradIter wi{ht, L.t_agg.as<float>(), L.t_G.as<float>(), L.t_dB.as<float>(), L.t_dA.as<float>()};
+        k_wgrad<<<wg_grid, WG_TPB, 0, st>>>(idx, wi, (rows + WG_ROWS - 1) / WG_ROWS, L.t_partials.as<float>()); LAUNCH_CHECK(c);
+        k_reduce_partials<<<(W_MP_FLOATS + 255) / 256, 256, 0, st>>>(wg_grid, L.t_partials.as<float>(), grad); LAUNCH_CHECK(c);
         cur ^= 1;
     }
     return ENERO_OK;
 }
 
-int ensure_train_rows(enero_ctx* c, int T, int64_t rows) {
+int ensure_train_rows(TrainLane& L, int T, int64_t rows) {
     const size_t rb = (size_t)rows * H * sizeof(float);
     if (T + 1 > 8) return fail(ENERO_ERR_INVALID, "training supports T <= 7");
-    for (int i = 0; i <= T; ++i) TRY(c->t_h[i].ensure(rb));
-    for (int i = 0; i < T; ++i) TRY(c->t_A[i].ensure(rb));
+    for (int i = 0; i <= T; ++i) TRY(L.t_h[i].ensure(rb));
+    for (int i = 0; i < T; ++i) TRY(L.t_A[i].ensure(rb));
+    return ENERO_OK;
+}
+
+// lane gradients -> the context's gradient buffer, lanes in a fixed order (deterministic), lane buffers zeroed
+__global__ void k_join_lanes(float* __restrict__ gradbuf, float* const* __restrict__ lane_grad, int n_lanes) {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= ENERO_GRAD_STRIDE + 4) return;
+    for (int l = 0; l < n_lanes; ++l) {
+        float* g = lane_grad[l];
+        const float v = g[o];
+        g[o] = 0.f;
+        const int which = l & 1;                                  // lane order: group-major, actor then critic
+        if (o < ENERO_GRAD_STRIDE) gradbuf[which * ENERO_GRAD_STRIDE + o] += v;
+        else if (o < ENERO_GRAD_STRIDE + 3) {
+            // loss sums: an actor lane holds (loss, entropy, -), a critic lane (critic loss, -, -)
+            const int k = o - ENERO_GRAD_STRIDE;
+            if (which == 0 && k < 2) gradbuf[2 * ENERO_GRAD_STRIDE + k] += v;
+            if (which == 1 && k == 0) gradbuf[2 * ENERO_GRAD_STRIDE + 2] += v;
+        }
+    }
+}
+
+// every lane's work joins the context's stream; their gradients are folded into the gradient buffer
+int join_lanes(enero_ctx* c) {
+    if (!c->groups) return ENERO_OK;
+    bool any = false;
+    for (int g = 0; g < TRAIN_GROUPS; ++g)
+        for (TrainLane& L : c->groups[g].lane)
+            if (L.busy) { CUDA_TRY(cudaStreamWaitEvent(c->stream, L.done, 0)); L.busy = false; any = true; }
+    if (!any) return ENERO_OK;
+    if (!c->lane_ptrs) {
+        std::vector<float*> p;
+        for (int g = 0; g < TRAIN_GROUPS; ++g) for (TrainLane& L : c->groups[g].lane) p.push_back(L.grad);
+        CUDA_TRY(cudaMalloc(&c->lane_ptrs, p.size() * sizeof(float*)));
+        CUDA_TRY(cudaMemcpy(c->lane_ptrs, p.data(), p.size() * sizeof(float*), cudaMemcpyHostToDevice));
+    }
+    k_join_lanes<<<(ENERO_GRAD_STRIDE + 4 + 255) / 256, 256, 0, c->stream>>>(c->gradbuf, c->lane_ptrs, 2 * TRAIN_GROUPS);
+    LAUNCH_CHECK(c);
+    c->group_cursor = 0;
     return ENERO_OK;
 }
 
 }  // namespace
+
+void train_release_lanes(enero_ctx* c) {
+    if (!c->groups) return;
+    for (int g = 0; g < TRAIN_GROUPS; ++g) {
+        cudaEventDestroy(c->groups[g].ready);
+        for (TrainLane& L : c->groups[g].lane) {
+            cudaStreamSynchronize(L.st);
+            cudaStreamDestroy(L.st); cudaEventDestroy(L.done); cudaFree(L.grad); cudaFree(L.tile_ctr);
+        }
+    }
+    delete[] c->groups;
+    c->groups = nullptr;
+    cudaFree(c->lane_ptrs);
+    c->lane_ptrs = nullptr;
+}
 
 extern "C" void* enero_ppo_grad_buffer(enero_ctx* c) { return c ? (void*)c->gradbuf : nullptr; }
 
 extern "C" int enero_ppo_zero_grad(enero_ctx* c) {
     if (!c) return fail(ENERO_ERR_INVALID, "null ctx");
     CUDA_TRY(cudaSetDevice(c->device));
+    TRY(join_lanes(c));                                          // folds (and clears) whatever the lanes still hold
     CUDA_TRY(cudaMemsetAsync(c->gradbuf, 0, sizeof(float) * ENERO_GRAD_FLOATS, c->stream));
     return ENERO_OK;
+}
+
+// the gradient buffer is complete on the context's stream after this (called by everything that reads it)
+extern "C" int enero_ppo_grad_ready(enero_ctx* c) {
+    if (!c) return fail(ENERO_ERR_INVALID, "null ctx");
+    CUDA_TRY(cudaSetDevice(c->device));
+    return join_lanes(c);
 }
 
 // validate what a kernel could not report (host copies of the demands / actions)
@@ -118,9 +195,27 @@ static int validate_samples(const enero_topo* t, int n, const int32_t* sd, const
     return ENERO_OK;
 }
 
-static int accumulate_dev(enero_ctx* c, enero_topo* t, int n, const double* loads, const int32_t* sd, const double* bw,
+static int accumulate_dev(enero_ctx* c, TrainGroup& G, enero_topo* t, int n, const double* loads, const int32_t* sd, const double* bw,
                           const int32_t* action, const float* old_prob, const float* advantage, const float* ret,
                           float inv_m, float entropy_beta, float clipping_val);
+
+// next group of lanes for one topology's share of the minibatch; the context's stream first waits for whatever the
+// group's lanes were still doing with its sample buffers
+static int acquire_group(enero_ctx* c, TrainGroup** out) {
+    TRY(ensure_lanes(c));
+    TrainGroup& G = c->groups[c->group_cursor % TRAIN_GROUPS];
+    c->group_cursor++;
+    for (TrainLane& L : G.lane)
+        if (L.busy) CUDA_TRY(cudaStreamWaitEvent(c->stream, L.done, 0));
+    *out = &G;
+    return ENERO_OK;
+}
+static int ensure_group_inputs(TrainGroup& G, int n, int E) {
+    TRY(G.t_loads.ensure((size_t)n * E * 8)); TRY(G.t_sd.ensure((size_t)n * 8)); TRY(G.t_bw.ensure((size_t)n * 8));
+    TRY(G.t_action.ensure((size_t)n * 4)); TRY(G.t_oldp.ensure((size_t)n * 4)); TRY(G.t_adv.ensure((size_t)n * 4));
+    TRY(G.t_ret.ensure((size_t)n * 4));
+    return ENERO_OK;
+}
 
 extern "C" int enero_ppo_accumulate(enero_ctx* c, enero_topo* t, int n, const double* loads, const int32_t* sd,
                                     const double* bw, const int32_t* action, const float* old_prob,
@@ -133,22 +228,22 @@ extern "C" int enero_ppo_accumulate(enero_ctx* c, enero_topo* t, int n, const do
     CUDA_TRY(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
     const int E = t->dev.E;
+    TrainGroup* G = nullptr;
+    TRY(acquire_group(c, &G));
     if (ptr_kind == ENERO_HOST) {
         TRY(validate_samples(t, n, sd, action, "enero_ppo_accumulate"));
-        TRY(c->t_loads.ensure((size_t)n * E * 8)); TRY(c->t_sd.ensure((size_t)n * 8)); TRY(c->t_bw.ensure((size_t)n * 8));
-        TRY(c->t_action.ensure((size_t)n * 4)); TRY(c->t_oldp.ensure((size_t)n * 4)); TRY(c->t_adv.ensure((size_t)n * 4));
-        TRY(c->t_ret.ensure((size_t)n * 4));
-        CUDA_TRY(cudaMemcpyAsync(c->t_loads.p, loads, (size_t)n * E * 8, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(c->t_sd.p, sd, (size_t)n * 8, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(c->t_bw.p, bw, (size_t)n * 8, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(c->t_action.p, action, (size_t)n * 4, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(c->t_oldp.p, old_prob, (size_t)n * 4, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(c->t_adv.p, advantage, (size_t)n * 4, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(c->t_ret.p, ret, (size_t)n * 4, cudaMemcpyHostToDevice, st));
-        loads = c->t_loads.as<double>(); sd = c->t_sd.as<int>(); bw = c->t_bw.as<double>();
-        action = c->t_action.as<int>(); old_prob = c->t_oldp.as<float>(); advantage = c->t_adv.as<float>(); ret = c->t_ret.as<float>();
+        TRY(ensure_group_inputs(*G, n, E));
+        CUDA_TRY(cudaMemcpyAsync(G->t_loads.p, loads, (size_t)n * E * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(G->t_sd.p, sd, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(G->t_bw.p, bw, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(G->t_action.p, action, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(G->t_oldp.p, old_prob, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(G->t_adv.p, advantage, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(G->t_ret.p, ret, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        loads = G->t_loads.as<double>(); sd = G->t_sd.as<int>(); bw = G->t_bw.as<double>();
+        action = G->t_action.as<int>(); old_prob = G->t_oldp.as<float>(); advantage = G->t_adv.as<float>(); ret = G->t_ret.as<float>();
     }
-    return accumulate_dev(c, t, n, loads, sd, bw, action, old_prob, advantage, ret, inv_m, entropy_beta, clipping_val);
+    return accumulate_dev(c, *G, t, n, loads, sd, bw, action, old_prob, advantage, ret, inv_m, entropy_beta, clipping_val);
 }
 
 // ---- device-resident sample store ----------------------------------------------------------------------------------
@@ -225,69 +320,84 @@ extern "C" int enero_ppo_accumulate_stored(enero_ctx* c, enero_topo* t, int n, c
     CUDA_TRY(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
     const int E = t->dev.E;
-    TRY(c->t_loads.ensure((size_t)n * E * 8)); TRY(c->t_sd.ensure((size_t)n * 8)); TRY(c->t_bw.ensure((size_t)n * 8));
-    TRY(c->t_action.ensure((size_t)n * 4)); TRY(c->t_oldp.ensure((size_t)n * 4)); TRY(c->t_adv.ensure((size_t)n * 4));
-    TRY(c->t_ret.ensure((size_t)n * 4));
+    TrainGroup* G = nullptr;
+    TRY(acquire_group(c, &G));
+    TRY(ensure_group_inputs(*G, n, E));
     if (s.idx.cap < (size_t)n * 4) TRY(s.idx.ensure((size_t)n * 4));
     CUDA_TRY(cudaMemcpyAsync(s.idx.p, idx, (size_t)n * 4, cudaMemcpyHostToDevice, st));
     k_gather_samples<<<n, 64, 0, st>>>(n, E, s.idx.as<int>(), s.loads.as<double>(), s.sd.as<int>(), s.bw.as<double>(), s.action.as<int>(),
-                                       s.oldp.as<float>(), s.adv.as<float>(), s.ret.as<float>(), c->t_loads.as<double>(), c->t_sd.as<int>(),
-                                       c->t_bw.as<double>(), c->t_action.as<int>(), c->t_oldp.as<float>(), c->t_adv.as<float>(),
-                                       c->t_ret.as<float>());
+                                       s.oldp.as<float>(), s.adv.as<float>(), s.ret.as<float>(), G->t_loads.as<double>(), G->t_sd.as<int>(),
+                                       G->t_bw.as<double>(), G->t_action.as<int>(), G->t_oldp.as<float>(), G->t_adv.as<float>(),
+                                       G->t_ret.as<float>());
     LAUNCH_CHECK(c);
-    return accumulate_dev(c, t, n, c->t_loads.as<double>(), c->t_sd.as<int>(), c->t_bw.as<double>(), c->t_action.as<int>(),
-                          c->t_oldp.as<float>(), c->t_adv.as<float>(), c->t_ret.as<float>(), inv_m, entropy_beta, clipping_val);
+    return accumulate_dev(c, *G, t, n, G->t_loads.as<double>(), G->t_sd.as<int>(), G->t_bw.as<double>(), G->t_action.as<int>(),
+                          G->t_oldp.as<float>(), G->t_adv.as<float>(), G->t_ret.as<float>(), inv_m, entropy_beta, clipping_val);
 }
 
-static int accumulate_dev(enero_ctx* c, enero_topo* t, int n, const double* loads, const int32_t* sd, const double* bw,
+static int accumulate_dev(enero_ctx* c, TrainGroup& G, enero_topo* t, int n, const double* loads, const int32_t* sd, const double* bw,
                           const int32_t* action, const float* old_prob, const float* advantage, const float* ret,
                           float inv_m, float entropy_beta, float clipping_val) {
-    cudaStream_t st = c->stream;
     const TopoDev& d = t->dev;
     const int E = d.E, Kmax = d.Kmax, T = 5;
     TopoView tv = view_of(t);
-    TRY(c->util.ensure((size_t)n * E * 4)); TRY(c->t_nK.ensure((size_t)n * 4));
-    TRY(c->t_logits.ensure((size_t)n * Kmax * 4)); TRY(c->t_dlogit.ensure((size_t)n * Kmax * 4));
-    TRY(c->t_loss.ensure((size_t)n * 4)); TRY(c->t_ent.ensure((size_t)n * 4));
-    float* sums = c->gradbuf + 2 * ENERO_GRAD_STRIDE;
-    // ---- actor: K' candidate graphs per sample
+    TRY(ensure_ones(c, n));
+    CUDA_TRY(cudaEventRecord(G.ready, c->stream));               // the group's samples are in place after this point
+    // ---- actor lane: K' candidate graphs per sample
     {
+        TrainLane& L = G.lane[ENERO_ACTOR];
+        cudaStream_t st = L.st;
+        CUDA_TRY(cudaStreamWaitEvent(st, G.ready, 0));
         const int RPD = Kmax * E;
         const int64_t rows = (int64_t)n * RPD;
-        TRY(ensure_train_rows(c, T, rows));
-        int* nK = c->t_nK.as<int>();
-        CUDA_TRY(cudaMemsetAsync(c->t_logits.p, 0, (size_t)n * Kmax * 4, st));
-        k_decision_prep<<<(int)(((int64_t)n * E + 255) / 256), 256, 0, st>>>(tv, n, loads, sd, nullptr, nK, c->util.as<float>()); LAUNCH_CHECK(c);
-        k_features<<<(int)((rows + MP_TPB - 1) / MP_TPB), MP_TPB, 0, st>>>(tv, n, RPD, sd, bw, nK, c->util.as<float>(), c->w[ENERO_ACTOR],
-                                                                         c->t_h[0].as<float>(), c->t_A[0].as<float>()); LAUNCH_CHECK(c);
+        TRY(ensure_train_rows(L, T, rows));
+        TRY(L.util.ensure((size_t)n * E * 4)); TRY(L.t_nK.ensure((size_t)n * 4));
+        TRY(L.t_logits.ensure((size_t)n * Kmax * 4)); TRY(L.t_dlogit.ensure((size_t)n * Kmax * 4));
+        TRY(L.t_loss.ensure((size_t)n * 4)); TRY(L.t_ent.ensure((size_t)n * 4));
+        int* nK = L.t_nK.as<int>();
+        float* sums = L.grad + ENERO_GRAD_STRIDE;
+        CUDA_TRY(cudaMemsetAsync(L.t_logits.p, 0, (size_t)n * Kmax * 4, st));
+        k_decision_prep<<<(int)(((int64_t)n * E + 255) / 256), 256, 0, st>>>(tv, n, loads, sd, nullptr, nK, L.util.as<float>()); LAUNCH_CHECK(c);
+        k_features<<<(int)((rows + MP_TPB - 1) / MP_TPB), MP_TPB, 0, st>>>(tv, n, RPD, sd, bw, nK, L.util.as<float>(), c->w[ENERO_ACTOR],
+                                                                         L.t_h[0].as<float>(), L.t_A[0].as<float>()); LAUNCH_CHECK(c);
         IdxTopo idx{rows, E, d.off_f, d.off_s, RPD, nK, d.in_off, d.in_first};
-        TRY(train_forward(c, idx, ENERO_ACTOR, T, rows));
+        TRY(train_forward(c, L, idx, ENERO_ACTOR, T, rows));
         GraphsTopo gr{n, Kmax, E, RPD, nK};
-        k_readout<GraphsTopo><<<(n * Kmax + 3) / 4, 128, 0, st>>>(gr, c->w[ENERO_ACTOR], c->t_h[T].as<float>(), c->t_logits.as<float>()); LAUNCH_CHECK(c);
-        k_ppo_actor_head<<<(n + 3) / 4, 128, 0, st>>>(n, Kmax, nK, c->t_logits.as<float>(), action, old_prob, advantage, inv_m,
-                                                      entropy_beta, clipping_val, c->t_dlogit.as<float>(), c->t_loss.as<float>(),
-                                                      c->t_ent.as<float>()); LAUNCH_CHECK(c);
-        k_sum_into<<<1, 32, 0, st>>>(n, c->t_loss.as<float>(), sums + 0); LAUNCH_CHECK(c);
-        k_sum_into<<<1, 32, 0, st>>>(n, c->t_ent.as<float>(), sums + 1); LAUNCH_CHECK(c);
+        k_readout<GraphsTopo><<<(n * Kmax + 3) / 4, 128, 0, st>>>(gr, c->w[ENERO_ACTOR], L.t_h[T].as<float>(), L.t_logits.as<float>()); LAUNCH_CHECK(c);
+        k_ppo_actor_head<<<(n + 3) / 4, 128, 0, st>>>(n, Kmax, nK, L.t_logits.as<float>(), action, old_prob, advantage, inv_m,
+                                                      entropy_beta, clipping_val, L.t_dlogit.as<float>(), L.t_loss.as<float>(),
+                                                      L.t_ent.as<float>()); LAUNCH_CHECK(c);
+        k_sum_into<<<1, 32, 0, st>>>(n, L.t_loss.as<float>(), sums + 0); LAUNCH_CHECK(c);
+        k_sum_into<<<1, 32, 0, st>>>(n, L.t_ent.as<float>(), sums + 1); LAUNCH_CHECK(c);
         TrainTopo g{n, Kmax, E, RPD, rows, nK};
-        TRY(train_backward(c, t, g, ENERO_ACTOR, T, c->t_dlogit.as<float>()));
+        TRY(train_backward(c, L, t, g, ENERO_ACTOR, T, L.t_dlogit.as<float>()));
+        CUDA_TRY(cudaEventRecord(L.done, st));
+        L.busy = true;
     }
-    // ---- critic: one graph per sample
+    // ---- critic lane: one graph per sample, concurrently with the actor lane
     {
+        TrainLane& L = G.lane[ENERO_CRITIC];
+        cudaStream_t st = L.st;
+        CUDA_TRY(cudaStreamWaitEvent(st, G.ready, 0));
         const int64_t rows = (int64_t)n * E;
-        TRY(ensure_ones(c, n));
+        TRY(ensure_train_rows(L, T, rows));
+        TRY(L.util.ensure((size_t)n * E * 4)); TRY(L.t_nK.ensure((size_t)n * 4));
+        TRY(L.t_logits.ensure((size_t)n * 4)); TRY(L.t_dlogit.ensure((size_t)n * 4)); TRY(L.t_loss.ensure((size_t)n * 4));
         const int* ones = c->ones.as<int>();
-        k_features_critic<<<(int)((rows + MP_TPB - 1) / MP_TPB), MP_TPB, 0, st>>>(tv, n, c->util.as<float>(), c->w[ENERO_CRITIC],
-                                                                                c->t_h[0].as<float>(), c->t_A[0].as<float>()); LAUNCH_CHECK(c);
+        float* sums = L.grad + ENERO_GRAD_STRIDE;
+        k_decision_prep<<<(int)(((int64_t)n * E + 255) / 256), 256, 0, st>>>(tv, n, loads, sd, nullptr, L.t_nK.as<int>(), L.util.as<float>()); LAUNCH_CHECK(c);
+        k_features_critic<<<(int)((rows + MP_TPB - 1) / MP_TPB), MP_TPB, 0, st>>>(tv, n, L.util.as<float>(), c->w[ENERO_CRITIC],
+                                                                                L.t_h[0].as<float>(), L.t_A[0].as<float>()); LAUNCH_CHECK(c);
         IdxTopo idx{rows, E, d.off_f, d.off_s, E, ones, d.in_off, d.in_first};
-        TRY(train_forward(c, idx, ENERO_CRITIC, T, rows));
+        TRY(train_forward(c, L, idx, ENERO_CRITIC, T, rows));
         GraphsTopo gr{n, 1, E, E, ones};
-        k_readout<GraphsTopo><<<(n + 3) / 4, 128, 0, st>>>(gr, c->w[ENERO_CRITIC], c->t_h[T].as<float>(), c->t_logits.as<float>()); LAUNCH_CHECK(c);
-        k_ppo_critic_head<<<(n + 127) / 128, 128, 0, st>>>(n, c->t_logits.as<float>(), ret, inv_m, c->t_dlogit.as<float>(), c->t_loss.as<float>());
+        k_readout<GraphsTopo><<<(n + 3) / 4, 128, 0, st>>>(gr, c->w[ENERO_CRITIC], L.t_h[T].as<float>(), L.t_logits.as<float>()); LAUNCH_CHECK(c);
+        k_ppo_critic_head<<<(n + 127) / 128, 128, 0, st>>>(n, L.t_logits.as<float>(), ret, inv_m, L.t_dlogit.as<float>(), L.t_loss.as<float>());
         LAUNCH_CHECK(c);
-        k_sum_into<<<1, 32, 0, st>>>(n, c->t_loss.as<float>(), sums + 2); LAUNCH_CHECK(c);
+        k_sum_into<<<1, 32, 0, st>>>(n, L.t_loss.as<float>(), sums + 0); LAUNCH_CHECK(c);
         TrainTopo g{n, 1, E, E, rows, ones};
-        TRY(train_backward(c, t, g, ENERO_CRITIC, T, c->t_dlogit.as<float>()));
+        TRY(train_backward(c, L, t, g, ENERO_CRITIC, T, L.t_dlogit.as<float>()));
+        CUDA_TRY(cudaEventRecord(L.done, st));
+        L.busy = true;
     }
     // no synchronisation: H2D copies from pageable host memory have left the caller's buffers when
     // cudaMemcpyAsync returns, and the device staging buffers are reused in stream order
@@ -300,6 +410,7 @@ extern "C" int enero_ppo_apply(enero_ctx* c, float lr, float beta1, float beta2,
     if (!c || step < 1 || !(clip_norm > 0) || hist_slot >= ENERO_PPO_HISTORY)
         return fail(ENERO_ERR_INVALID, "enero_ppo_apply: bad argument");
     CUDA_TRY(cudaSetDevice(c->device));
+    TRY(join_lanes(c));
     // Keras Adam._prepare_local in fp32: lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t)
     const float t = (float)step;
     const float alpha = lr * std::sqrt(1.0f - std::pow(beta2, t)) / (1.0f - std::pow(beta1, t));
@@ -329,6 +440,7 @@ extern "C" int enero_ppo_history(enero_ctx* c, int first_slot, int n, float* out
 extern "C" int enero_ppo_grad_download(enero_ctx* c, float* actor, float* critic, float* sums) {
     if (!c) return fail(ENERO_ERR_INVALID, "null ctx");
     CUDA_TRY(cudaSetDevice(c->device));
+    TRY(join_lanes(c));
     if (actor) CUDA_TRY(cudaMemcpyAsync(actor, c->grad[0], sizeof(float) * ENERO_NPARAMS, cudaMemcpyDeviceToHost, c->stream));
     if (critic) CUDA_TRY(cudaMemcpyAsync(critic, c->grad[1], sizeof(float) * ENERO_NPARAMS, cudaMemcpyDeviceToHost, c->stream));
     if (sums) CUDA_TRY(cudaMemcpyAsync(sums, c->gradbuf + 2 * ENERO_GRAD_STRIDE, sizeof(float) * 3, cudaMemcpyDeviceToHost, c->stream));

@@ -151,6 +151,7 @@ class PPOActorCritic:
             self._grad_view = _device_view(self._lib.enero_ppo_grad_buffer(self.context.handle), _lib.GRAD_FLOATS,
                                            self.context.device)
             self._ext_stream = torch.cuda.ExternalStream(self.context.stream, device=torch.device("cuda", self.context.device))
+        _lib.check(self._lib.enero_ppo_grad_ready(self.context.handle))      # lanes joined, gradient buffer complete
         if dist.get_backend(self._pg) == "nccl":
             with torch.cuda.stream(self._ext_stream):
                 dist.all_reduce(self._grad_view, op=dist.ReduceOp.SUM, group=self._pg)

@@ -261,6 +261,12 @@ int enero_batch_sap(enero_batch* b, const double* tms_host, int K, uint32_t seed
  * A rank of a sharded PPO step all-reduces (sum) exactly this array, then every rank applies. */
 void* enero_ppo_grad_buffer(enero_ctx* ctx);
 int enero_ppo_zero_grad(enero_ctx* ctx);
+/* enero_ppo_accumulate* run the (up to three topologies) x (actor, critic) passes of a minibatch concurrently on
+ * internal streams ("lanes"), each with its own gradient accumulator; enero_ppo_grad_ready joins them into the
+ * ctx's stream and folds the lane gradients into the gradient buffer in a fixed order (deterministic).  A caller
+ * that reads enero_ppo_grad_buffer itself (the all-reduce of a sharded step) calls it first; enero_ppo_apply,
+ * enero_ppo_grad_download and enero_ppo_zero_grad do so themselves. */
+int enero_ppo_grad_ready(enero_ctx* ctx);
 /* _train_step_combined (train script :293-315), gradient part, for n samples that share one topology:
  * actor forward over the K' candidate graphs of demand sd[i] (bandwidth bw[i]) on link loads loads[i]
  * (the same state pred_action_distrib_sp saw), critic forward on the same loads, the per-sample losses
