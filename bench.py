@@ -42,8 +42,8 @@ UNIT = "decisions/s"
 WORKLOAD = "cfg2: zoo_like(N=30,L=50,seed=1000) E=100 links, uniform TMs seed 2000+j, ckpt_ACT-1835, greedy DRL decisions"
 TOPO = (30, 50, 1000)
 GOLD = os.path.join(ROOT, "tests", "golden")
-NCU_FULL = os.path.join("profiles", "r02_k_mp_iter_ncu_full.csv")       # measured DRAM traffic of the dominant kernel
-NCU_FULL_FALLBACK = os.path.join("profiles", "r01_v7_k_mp_iter_ncu_full.csv")
+# measured DRAM traffic of the dominant kernel, per engine (ncu --set full captures summarised by tools/ncu_summary.py)
+NCU_FULL = {"tc": os.path.join("profiles", "r02_k_mp_tc_ncu_full.csv"), "ffma": os.path.join("profiles", "r01_v7_k_mp_iter_ncu_full.csv")}
 
 
 def load_weights():
@@ -230,11 +230,11 @@ def run_reference(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------------
-def _ncu_traffic(B):
-    """measured DRAM bytes of one k_mp_iter launch from the committed ncu --set full capture (taken at 1024
-    episodes per GPU on this workload; scaled linearly with the batch)"""
+def _ncu_traffic(B, engine):
+    """measured DRAM bytes of one message-passing launch from the committed ncu --set full capture of the engine in
+    use (taken at 1024 episodes per GPU on this workload; scaled linearly with the batch)"""
     import csv
-    for rel in (NCU_FULL, NCU_FULL_FALLBACK):
+    for rel in (NCU_FULL[engine],):
         prof = os.path.join(ROOT, rel)
         if not os.path.isfile(prof):
             continue
@@ -333,9 +333,25 @@ def run_ours(args, rank, world, local_rank):
     achieved = flops_alg / launch_s / 1e12 if launch_s else 0.0
     # API-boundary bytes of one decision (inputs materialised as the reference's call signature has them)
     bytes_api = mean_k * E * 80.0 + mean_k * E * 4.0 + 2.0 * mean_k * P * 4.0 + mean_k * 4.0
-    traffic, traffic_src = _ncu_traffic(B)
+    traffic, traffic_src = _ncu_traffic(B, ctx.engine)
+    tc = ctx.engine == "tc"
+    # tensor-core engine: executed tensor FLOPs = 3 TF32 products (3xTF32) x 2 x 24 (K padded) x (80 + 64 + 32) columns per
+    # row and iteration, over every row of the launch (padding rows of a tile are multiplied too); TF32 dense peak
+    # = half of the measured bf16 peak (MEASURED_PEAKS.json bf16_tflops; nominal 1.1 vs 2.25 PFLOP/s)
+    rows_launched = float(B) * topo.Kmax * E
+    tensor = None
+    if tc:
+        tf32_peak = float(peaks.get("bf16_tflops", 1590.0)) / 2.0
+        t_exec = rows_launched * 3 * 2 * 24 * (80 + 64 + 32)
+        tensor = {"executed_tflops": t_exec / launch_s / 1e12 if launch_s else None, "peak_tflops": tf32_peak,
+                  "frac": t_exec / launch_s / 1e12 / tf32_peak if launch_s else None,
+                  "peak_source": "MEASURED_PEAKS.json bf16_tflops / 2 (TF32 dense = half of bf16)" if peaks else "fallback 1.59 PFLOP/s bf16 / 2",
+                  "note": "the tensor pipe is not the limit (ncu: 16 % active); gather / gate latency and instruction issue are"}
     roofline = {
-        "bound": "fp32", "kernel": "k_mp_iter<IdxTopo> (5 launches per decision step, ~94 % of it)",
+        "bound": "fp32",
+        "kernel": ("k_mp_tc<IdxTopo> (tcgen05 3xTF32; 5 launches per decision step, ~92 % of it)" if tc
+                   else "k_mp_iter<IdxTopo> (5 launches per decision step, ~94 % of it)"),
+        "engine": ctx.engine, "tensor": tensor,
         "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak if fp32_peak else None,
         "peak_source": "enero_ctx_fp32_peak: FFMA2 register loop timed on this GPU just now (nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4)",
         "flops_per_launch_algorithmic": flops_alg, "flops_per_launch_executed": flops_exec,
@@ -346,8 +362,11 @@ def run_ours(args, rank, world, local_rank):
         "algorithmic_bytes_per_decision": bytes_api,
         "algorithmic_frac": B * bytes_api / step_s / 1e9 / hbm_peak,
         "hbm_peak_gbs": hbm_peak, "hbm_peak_source": "MEASURED_PEAKS.json hbm_gbs (burst)" if peaks else "fallback 6.65 TB/s",
-        "note": "arithmetic intensity ~290 FLOP/B against the API-boundary bytes: FP32-FMA bound, not HBM bound (SURVEY 8d); "
-                "dram_frac = measured DRAM bytes per launch / launch time / HBM peak, algorithmic_frac = 8(d)(i) bytes per step / step time / HBM peak",
+        "note": "achieved = SURVEY 8(d) algorithmic FLOPs (dense per-pair formulation) / launch time, against the FP32-pipe peak: the "
+                "rate at which the reference's fp32 work gets done (with the tensor-core engine the mat-muls run as 3xTF32 on tcgen05, so "
+                "this can exceed what the FP32 pipe alone could reach; fp32_frac_executed counts the factored formulation's FLOPs). "
+                "Arithmetic intensity ~290 FLOP/B against the API-boundary bytes: not HBM bound (SURVEY 8d). dram_frac = measured DRAM bytes "
+                "per launch / launch time / HBM peak; algorithmic_frac = 8(d)(i) bytes per step / step time / HBM peak",
     }
 
     # ---- end to end through the public API with host buffers: whole greedy episodes
@@ -433,7 +452,7 @@ def run_ours(args, rank, world, local_rank):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "episodes_per_gpu": B, "decisions_per_step": world * B,
-                       "mean_candidates": mean_k, "links": E, "pairs": P, "math": ctx.math,
+                       "mean_candidates": mean_k, "links": E, "pairs": P, "math": ctx.math, "engine": ctx.engine,
                        "l2": "inputs larger than L2 (%.0f MB of link-state rows per step)" % (B * topo.Kmax * E * 320 / 1e6),
                        "parallelism": "episodes sharded x%d, no collective" % world},
             "clocks": clk.summary(), "gpu_launches": int(launches), "roofline": roofline,

@@ -15,7 +15,9 @@ KEYS = ['Kernel Name', 'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__
         'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'lts__t_sector_hit_rate.pct', 'l1tex__t_sector_hit_rate.pct',
         'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
         'smsp__thread_inst_executed_per_inst_executed.ratio', 'sm__cycles_elapsed.max',
-        'smsp__inst_executed.sum', 'sm__inst_executed.sum']
+        'smsp__inst_executed.sum', 'sm__inst_executed.sum',
+        'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_tensor.avg.pct_of_peak_sustained_active', 'launch__shared_mem_per_block_dynamic', 'launch__occupancy_limit_warps']
 STALLS = 'smsp__pcsamp_warps_issue_stalled_'
 
 
