@@ -96,6 +96,7 @@ extern "C" int enero_ctx_create(int device, enero_ctx** out) {
         };
         setup_tc(k_mp_tc<false, 20, false>); setup_tc(k_mp_tc<true, 20, false>); setup_tc(k_mp_tc<false, 3, false>);
         setup_tc(k_mp_tc<false, 20, true>); setup_tc(k_mp_tc<true, 20, true>); setup_tc(k_mp_tc<false, 3, true>);
+        setup_tc(k_mp_tc<false, 3, false, true>); setup_tc(k_mp_tc<false, 3, true, true>);
         if (r != ENERO_OK) return r;
         // resident CTAs per SM from the kernel's own resources (registers, shared memory, 128 of the 512 TMEM columns each):
         // cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for this kernel on CUDA 12.9, which is not what the SM does
@@ -112,6 +113,7 @@ extern "C" int enero_ctx_create(int device, enero_ctx** out) {
         else return fail(ENERO_ERR_INVALID, "ENERO_MP must be 'ffma' or 'tc'");
     }
     if (const char* e = std::getenv("ENERO_NO_GRAPHS")) c->no_graphs = std::atoi(e) != 0;
+    if (const char* e = std::getenv("ENERO_UNFUSED_FEATURES")) c->prof_unfused = std::atoi(e) != 0;
     c->math_acc = ENERO_MATH_DEFAULT;
     if (const char* e = std::getenv("ENERO_MATH")) {
         if (!std::strcmp(e, "fast")) c->math_acc = 0;
@@ -320,7 +322,7 @@ static int launch_iteration(enero_ctx* c, const IDX& idx, int idx_kind, int whic
         if (c->mp_engine == 1) {                                 // tensor-core engine: 128-row tiles, one CTA of 128 threads each
             const int64_t nt = (idx.rows() + TC_ROWS - 1) / TC_ROWS;
             const int g = (int)std::min<int64_t>((nt + TC_GROUPS - 1) / TC_GROUPS, (int64_t)c->num_sms * std::max(1, c->occ_tc));
-            auto gtc = [&](auto kern) { kern<<<g, TC_TPB, TC_SMEM_BYTES, stream>>>(idx, c->w[which], hin, Ain, hout, Aout, (int)nt); };
+            auto gtc = [&](auto kern) { kern<<<g, TC_TPB, TC_SMEM_BYTES, stream>>>(idx, c->w[which], hin, Ain, hout, Aout, (int)nt, FeatSrc()); };
             if (c->math_acc) {
                 if (last) gtc(k_mp_tc<true, 20, true>); else if (sparse) gtc(k_mp_tc<false, 3, true>); else gtc(k_mp_tc<false, 20, true>);
             } else {
@@ -445,10 +447,30 @@ static int decide_dev(enero_ctx* c, enero_topo* t, int B, const double* loads, c
     TopoView tv = view_of(t);
     CUDA_TRY(cudaMemsetAsync(logits, 0, (size_t)B * d.Kmax * 4, st));
     k_decision_prep<<<(int)(((int64_t)B * d.E + 255) / 256), 256, 0, st>>>(tv, B, loads, sd, skip, nK, c->util.as<float>()); LAUNCH_CHECK(c);
-    k_features<<<(int)((rows + MP_TPB - 1) / MP_TPB), MP_TPB, 0, st>>>(tv, B, RPD, sd, bw, nK, c->util.as<float>(), c->w[ENERO_ACTOR],
-                                                                     c->h[0].as<float>(), c->A[0].as<float>()); LAUNCH_CHECK(c);
     IdxTopo idx{rows, d.E, d.off_f, d.off_s, RPD, nK, d.in_off, d.in_first};
-    TRY(run_iterations(c, idx, ENERO_ACTOR, T, rows, 1, T > 1));
+    if (c->mp_engine == 1 && T > 1 && !c->prof_unfused) {
+        // tensor-core engine: iteration 0 rebuilds the feature rows from tables (no k_features, no h_0 / A_0 in HBM)
+        const int W = (d.E + 31) / 32;
+        TRY(c->bwcap.ensure((size_t)B * d.E * 4)); TRY(c->marks.ensure((size_t)B * d.Kmax * W * 4));
+        const int64_t work = std::max<int64_t>((int64_t)B * d.E, (int64_t)B * d.Kmax);
+        k_decision_marks<<<(int)((work + 255) / 256), 256, 0, st>>>(tv, B, W, sd, bw, nK, c->bwcap.as<float>(), c->marks.as<uint32_t>()); LAUNCH_CHECK(c);
+        FeatSrc fs{c->util.as<float>(), c->bwcap.as<float>(), d.capf, c->marks.as<uint32_t>(), W, d.Kmax};
+        const int64_t nt = (rows + TC_ROWS - 1) / TC_ROWS;
+        const int g = (int)std::min<int64_t>((nt + TC_GROUPS - 1) / TC_GROUPS, (int64_t)c->num_sms * std::max(1, c->occ_tc));
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (c->prof) { CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1)); CUDA_TRY(cudaEventRecord(e0, st)); }
+        if (c->math_acc) k_mp_tc<false, 3, true, true><<<g, TC_TPB, TC_SMEM_BYTES, st>>>(idx, c->w[ENERO_ACTOR], nullptr, nullptr, c->h[1].as<float>(), c->A[1].as<float>(), (int)nt, fs);
+        else k_mp_tc<false, 3, false, true><<<g, TC_TPB, TC_SMEM_BYTES, st>>>(idx, c->w[ENERO_ACTOR], nullptr, nullptr, c->h[1].as<float>(), c->A[1].as<float>(), (int)nt, fs);
+        LAUNCH_CHECK(c);
+        if (c->prof) { CUDA_TRY(cudaEventRecord(e1, st)); c->prof_ev.emplace_back(e0, e1); }
+        for (int it = 1; it < T; ++it)
+            TRY(launch_iteration(c, idx, 1, ENERO_ACTOR, it == T - 1, false, c->h[it & 1].as<float>(), c->A[it & 1].as<float>(),
+                                 c->h[(it + 1) & 1].as<float>(), c->A[(it + 1) & 1].as<float>()));
+    } else {
+        k_features<<<(int)((rows + MP_TPB - 1) / MP_TPB), MP_TPB, 0, st>>>(tv, B, RPD, sd, bw, nK, c->util.as<float>(), c->w[ENERO_ACTOR],
+                                                                         c->h[0].as<float>(), c->A[0].as<float>()); LAUNCH_CHECK(c);
+        TRY(run_iterations(c, idx, ENERO_ACTOR, T, rows, 1, T > 1));
+    }
     GraphsTopo gr{B, d.Kmax, d.E, RPD, nK};
     k_readout<GraphsTopo><<<(B * d.Kmax + 3) / 4, 128, 0, st>>>(gr, c->w[ENERO_ACTOR], c->h[T & 1].as<float>(), logits); LAUNCH_CHECK(c);
     k_policy<<<(B + 3) / 4, 128, 0, st>>>(B, d.Kmax, nK, logits, probs, action); LAUNCH_CHECK(c);
@@ -829,8 +851,9 @@ static int greedy_step_graph(enero_batch* b) {
     const int64_t rows = (int64_t)b->B * d.Kmax * d.E;
     TRY(ensure_rows(c, rows));                                   // no allocation may happen while capturing
     TRY(c->util.ensure((size_t)b->B * d.E * 4));
+    TRY(c->bwcap.ensure((size_t)b->B * d.E * 4)); TRY(c->marks.ensure((size_t)b->B * d.Kmax * ((d.E + 31) / 32) * 4));
     const void* key[8] = {c->h[0].p, c->h[1].p, c->A[0].p, c->A[1].p, c->util.p, b->loads.p,
-                          (const void*)(intptr_t)(c->math_acc + 1 + 4 * c->mp_engine), (const void*)b->t->dev.in_first};
+                          (const void*)(intptr_t)(c->math_acc + 1 + 4 * c->mp_engine), (const void*)c->marks.p};
     GreedyGraph& g = b->graph;
     if (g.exec && !std::memcmp(key, g.key, sizeof(key))) return ENERO_OK;
     g.release();

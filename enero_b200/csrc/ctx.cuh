@@ -70,6 +70,8 @@ struct enero_ctx {
     float* w[2] = {nullptr, nullptr};
     int64_t launches = 0;
     // scratch of the GNN engine
+    DevBuf bwcap, marks;                      // tables of the fused first iteration (k_decision_marks)
+    bool prof_unfused = false;               // ENERO_UNFUSED_FEATURES=1: keep k_features + generic iteration 0 (A/B measurements)
     DevBuf h[2], A[2], util, nK, logits, probs, action, in_loads, in_sd, in_bw, ones;
     DevBuf x_ls, x_gid, x_first, x_second, x_cnt, x_off, x_cur, x_slot, x_src, x_goff, x_err, x_out;
     int occ_iter[2][2][2] = {};              // [math][indexer][last] resident CTAs/SM of k_mp_iter

@@ -37,6 +37,29 @@ __global__ void k_decision_prep(TopoView t, int B, const double* __restrict__ lo
     }
 }
 
+// Tables of the fused first iteration (k_mp_tc<FUSED0>): bwcap[b][e] = fp32(bw / cap) (the double-rounded mark value of
+// mark_action_sp, environment16.py:723) and one bit per (decision, candidate, link): link on path(s,mid) U path(mid,d).
+__global__ void k_decision_marks(TopoView t, int B, int W, const int* __restrict__ sd, const double* __restrict__ bw,
+                                 const int* __restrict__ nK, float* __restrict__ bwcap, uint32_t* __restrict__ mask) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < (int64_t)B * t.E) {
+        const int b = (int)(i / t.E), e = (int)(i - (int64_t)b * t.E);
+        bwcap[i] = (float)(bw[b] / t.cap[e]);
+    }
+    if (i < (int64_t)B * t.Kmax) {
+        const int b = (int)(i / t.Kmax), k = (int)(i - (int64_t)b * t.Kmax);
+        uint32_t* m = mask + i * W;
+        for (int w = 0; w < W; ++w) m[w] = 0u;
+        if (k < nK[b]) {
+            const int s = sd[2 * b], d = sd[2 * b + 1];
+            const int mid = t.mids[t.mid_off[s * t.N + d] + k];
+            for (int q = t.sp_off[s * t.N + mid]; q < t.sp_off[s * t.N + mid + 1]; ++q) m[t.sp_edge[q] >> 5] |= 1u << (t.sp_edge[q] & 31);
+            if (mid != d)
+                for (int q = t.sp_off[mid * t.N + d]; q < t.sp_off[mid * t.N + d + 1]; ++q) m[t.sp_edge[q] >> 5] |= 1u << (t.sp_edge[q] & 31);
+        }
+    }
+}
+
 // ---- candidate features (kernel 6, feature half) ----------------------------------------
 // Row (b, k, e) of the batched link_state = [util, cap/maxCap, mark, 0 x 17]
 // (mark_action_sp, environment16.py:711-725: assignment bw/cap on every link of

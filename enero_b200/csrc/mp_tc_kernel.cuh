@@ -46,7 +46,7 @@ constexpr int TC_W_F4 = (TC_N1 + TC_N2 + TC_N3) * TC_KC;          // float4 per 
 constexpr int TC_GROUPS = 2;                     // independent 128-thread tile pipelines per CTA (they share the weight images)
 constexpr int TC_TPB = TC_GROUPS * TC_ROWS;
 constexpr size_t TC_GROUP_BYTES = (size_t)2 * TC_KC * TC_ROWS * 16 + (size_t)TC_ROWS * H * 4 + 32;   // operands hi/lo, stage, 2 mbarriers
-constexpr size_t TC_SMEM_BYTES = (size_t)2 * TC_W_F4 * 16 + 576 + 16 + TC_GROUPS * TC_GROUP_BYTES;
+constexpr size_t TC_SMEM_BYTES = (size_t)2 * TC_W_F4 * 16 + 832 + 16 + TC_GROUPS * TC_GROUP_BYTES;   // 208 floats: biases + Wm[0:3]
 
 __device__ __forceinline__ uint64_t tc_desc(const void* p, uint32_t lbo_bytes) {
     // K-major, no swizzle: 8 rows x 16 B core matrices, rows 16 B apart; SBO (next 8 rows) = 128 B, LBO (next
@@ -142,6 +142,29 @@ __device__ __forceinline__ void tc_stage_weights(float4* w_hi, float4* w_lo, int
     }
 }
 
+// Iteration 0 of the fused decision path without a materialised h_0 / A_0: a link-state row of candidate graph k of
+// decision b is [util(b,e), cap(e)/maxCap, on_path(b,k,e) ? bw(b)/cap(e) : 0, 0 x 17] (mark_action_sp + get_graph_features,
+// environment16.py:711-725, script_eval_on_single_topology.py:131-160), so both the tile's own rows and the operand
+// rows its gather needs are rebuilt from three small L1/L2-resident tables and one bit mask per candidate instead
+// of being written by a feature kernel (160 B per row) and read back (80 B per row + 80 B per pair).
+struct FeatSrc {
+    const float* util;        // [B][E]   fp32(load / cap)
+    const float* bwcap;       // [B][E]   fp32(bw / cap)
+    const float* capf;        // [E]      fp32(cap / maxCap)
+    const uint32_t* mask;     // [B][Kmax][W] bit e = link e is on path(s, mid_k) U path(mid_k, d)
+    int W, Kmax;
+};
+__device__ __forceinline__ void tc_feature_row(const FeatSrc& f, const IdxTopo& idx, int64_t r, float& f0, float& f1, float& f2) {
+    const unsigned b = (unsigned)r / (unsigned)idx.RPD;
+    const unsigned lr = (unsigned)r - b * (unsigned)idx.RPD;
+    const unsigned k = lr / (unsigned)idx.E, e = lr - k * (unsigned)idx.E;
+    const unsigned be = b * (unsigned)idx.E + e;
+    f0 = f.util[be];
+    f1 = f.capf[e];
+    const uint32_t m = f.mask[((size_t)b * f.Kmax + k) * f.W + (e >> 5)];
+    f2 = ((m >> (e & 31)) & 1u) ? f.bwcap[be] : 0.f;
+}
+
 // KH: leading link-state columns that can be non-zero on entry (3 for iteration 0 of the fused path: phase 1 then
 // needs one k-step instead of three).  LAST: no A' (phase 3 skipped).
 //
@@ -152,10 +175,11 @@ __device__ __forceinline__ void tc_stage_weights(float4* w_hi, float4* w_lo, int
 // per row tile -> 4 tiles of 128 rows in the 512 columns.
 __device__ __forceinline__ void tc_group_sync(int g) { asm volatile("bar.sync %0, %1;" :: "r"(1 + g), "r"(TC_ROWS) : "memory"); }
 
-template <bool LAST, int KH, bool ACC>
+// FUSED0 (with KH = 3): iteration 0 rebuilt from the feature tables (`feat`), h_in / A_in unused.
+template <bool LAST, int KH, bool ACC, bool FUSED0 = false>
 __global__ void __launch_bounds__(TC_TPB, 2)
 k_mp_tc(const IdxTopo idx, const float* __restrict__ wflat, const float* __restrict__ h_in, const float* __restrict__ A_in,
-        float* __restrict__ h_out, float* __restrict__ A_out, int ntiles) {
+        float* __restrict__ h_out, float* __restrict__ A_out, int ntiles, const FeatSrc feat = FeatSrc()) {
     extern __shared__ __align__(1024) unsigned char tc_smem[];
     float4* w1_hi = reinterpret_cast<float4*>(tc_smem);
     float4* w1_lo = w1_hi + TC_KC * TC_N1;
@@ -164,7 +188,8 @@ k_mp_tc(const IdxTopo idx, const float* __restrict__ wflat, const float* __restr
     float4* w3_hi = w2_lo + TC_KC * TC_N2;
     float4* w3_lo = w3_hi + TC_KC * TC_N3;
     float* sbias = reinterpret_cast<float*>(w3_lo + TC_KC * TC_N3);            // msg bias [20] | gru bias [2][60]
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(sbias + 144);
+    float* swm3 = sbias + 144;                                                 // Wm[0:3][0:20]: first message operand of a feature row
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(sbias + 208);
     const int g = threadIdx.x / TC_ROWS, t = threadIdx.x - g * TC_ROWS, wg = t >> 5;      // group, row in tile, warp in group
     unsigned char* gbase = reinterpret_cast<unsigned char*>(s_tmem + 4) + (size_t)g * TC_GROUP_BYTES;
     float4* a_hi = reinterpret_cast<float4*>(gbase);
@@ -186,6 +211,7 @@ k_mp_tc(const IdxTopo idx, const float* __restrict__ wflat, const float* __restr
     tc_stage_weights(w2_hi, w2_lo, TC_N2, [&](int k, int n) { return (k >= H || n >= 60) ? 0.f : wflat[W_GRU_K + k * 60 + n]; });
     tc_stage_weights(w3_hi, w3_lo, TC_N3, [&](int k, int n) { return (k >= H || n >= H) ? 0.f : wflat[W_MSG_K + k * H + n]; });
     for (int i = threadIdx.x; i < 140; i += TC_TPB) sbias[i] = i < H ? wflat[W_MSG_B + i] : wflat[W_GRU_B + i - H];
+    for (int i = threadIdx.x; i < 3 * H; i += TC_TPB) swm3[i] = wflat[W_MSG_K + i];
     a_hi[5 * TC_ROWS + t] = make_float4(0.f, 0.f, 0.f, 0.f);                   // k = 20..23: never written again
     a_lo[5 * TC_ROWS + t] = make_float4(0.f, 0.f, 0.f, 0.f);
     fence_proxy_async();
@@ -215,14 +241,16 @@ k_mp_tc(const IdxTopo idx, const float* __restrict__ wflat, const float* __restr
         if (tl >= ntiles) return;
         const int64_t r0 = (int64_t)tl * TC_ROWS;
         idx.ref(r0 + t, r);
-        // one prefetch per operand row (its first sector; prefetching all three sectors of the 80-byte row was
-        // measured 2.5 % slower: the extra instructions cost more than the remaining misses)
-        for (int p = r.pb; p < r.pe; ++p)
-            asm volatile("prefetch.global.L2 [%0];" :: "l"(A_in + ((int64_t)r.list[p] + r.add) * H));
-        if (t == 0) {
-            const uint32_t bytes = (uint32_t)min((int64_t)TC_ROWS, total - r0) * H * 4;
-            mbar_expect_tx(bar + 1, bytes);
-            bulk_g2s(stage, h_in + r0 * H, bytes, bar + 1);
+        if (!FUSED0) {
+            // one prefetch per operand row (its first sector; prefetching all three sectors of the 80-byte row was
+            // measured 2.5 % slower: the extra instructions cost more than the remaining misses)
+            for (int p = r.pb; p < r.pe; ++p)
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(A_in + ((int64_t)r.list[p] + r.add) * H));
+            if (t == 0) {
+                const uint32_t bytes = (uint32_t)min((int64_t)TC_ROWS, total - r0) * H * 4;
+                mbar_expect_tx(bar + 1, bytes);
+                bulk_g2s(stage, h_in + r0 * H, bytes, bar + 1);
+            }
         }
     };
     int tile = live_from((int)blockIdx.x * TC_GROUPS + g);
@@ -233,11 +261,13 @@ k_mp_tc(const IdxTopo idx, const float* __restrict__ wflat, const float* __restr
         const bool ok = ref.ok;
         const int next = live_from(tile + stride);
         float h[H];
-        mbar_wait(bar + 1, parity_tma); parity_tma ^= 1u;
-        if (ok) load_row(h, stage + t * H);
-        else {
 #pragma unroll
-            for (int j = 0; j < H; ++j) h[j] = 0.f;
+        for (int j = 0; j < H; ++j) h[j] = 0.f;
+        if (FUSED0) {
+            if (ok) tc_feature_row(feat, idx, row, h[0], h[1], h[2]);
+        } else {
+            mbar_wait(bar + 1, parity_tma); parity_tma ^= 1u;
+            if (ok) load_row(h, stage + t * H);
         }
         tc_store_operand<KH <= 8 ? 2 : 5>(a_hi, a_lo, t, h);
         fence_proxy_async();
@@ -260,7 +290,18 @@ k_mp_tc(const IdxTopo idx, const float* __restrict__ wflat, const float* __restr
 #pragma unroll
         for (int j = 0; j < H / 2; ++j) { t2[j] = pack2(B[2 * j] + sbias[2 * j], B[2 * j + 1] + sbias[2 * j + 1]); agg2[j] = 0ull; }
         // ---- agg = sum over incoming pairs (ascending pair index) of selu(A[first] + B); two operand rows in flight
-        {
+        if (FUSED0) {
+            for (int p = cur.pb; p < cur.pe; ++p) {
+                float f0, f1, f2, a[H];
+                tc_feature_row(feat, idx, (int64_t)cur.list[p] + cur.add, f0, f1, f2);
+#pragma unroll
+                for (int j = 0; j < H; ++j) a[j] = fmaf(f2, swm3[2 * H + j], fmaf(f1, swm3[H + j], fmaf(f0, swm3[j], 0.f)));   // = k_features' A_0
+                mp_accumulate<ACC>(agg2, a, t2);
+            }
+        } else {
+            // two operand rows in flight.  Tried and dropped at the 128-register budget of two CTAs per SM: resolving the
+            // source rows a tile ahead (four more registers live across the tile) 1.74 ms per launch, and requesting
+            // rows before the wait on the phase-1 MMAs / four at once 1.93 ms, against 1.41 ms -- both spill in the hot loop.
             int p = cur.pb;
             for (; p + 1 < cur.pe; p += 2) {
                 float a0[H], a1[H];
