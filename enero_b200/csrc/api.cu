@@ -94,14 +94,16 @@ extern "C" int enero_ctx_create(int device, enero_ctx** out) {
                 r = ENERO_ERR_CUDA;
             }
         };
-        setup_tc(k_mp_tc<false, 20, false>); setup_tc(k_mp_tc<true, 20, false>); setup_tc(k_mp_tc<false, 3, false>);
-        setup_tc(k_mp_tc<false, 20, true>); setup_tc(k_mp_tc<true, 20, true>); setup_tc(k_mp_tc<false, 3, true>);
-        setup_tc(k_mp_tc<false, 3, false, true>); setup_tc(k_mp_tc<false, 3, true, true>);
+        setup_tc(k_mp_tc<IdxTopo, false, 20, false>); setup_tc(k_mp_tc<IdxTopo, true, 20, false>); setup_tc(k_mp_tc<IdxTopo, false, 3, false>);
+        setup_tc(k_mp_tc<IdxTopo, false, 20, true>); setup_tc(k_mp_tc<IdxTopo, true, 20, true>); setup_tc(k_mp_tc<IdxTopo, false, 3, true>);
+        setup_tc(k_mp_tc<IdxTopo, false, 3, false, true>); setup_tc(k_mp_tc<IdxTopo, false, 3, true, true>);
+        setup_tc(k_mp_tc<IdxExplicit, false, 20, false>); setup_tc(k_mp_tc<IdxExplicit, true, 20, false>);
+        setup_tc(k_mp_tc<IdxExplicit, false, 20, true>); setup_tc(k_mp_tc<IdxExplicit, true, 20, true>);
         if (r != ENERO_OK) return r;
         // resident CTAs per SM from the kernel's own resources (registers, shared memory, 128 of the 512 TMEM columns each):
         // cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for this kernel on CUDA 12.9, which is not what the SM does
         cudaFuncAttributes fa;
-        CUDA_TRY(cudaFuncGetAttributes(&fa, k_mp_tc<false, 20, false>));
+        CUDA_TRY(cudaFuncGetAttributes(&fa, k_mp_tc<IdxTopo, false, 20, false>));
         const int by_regs = 65536 / (std::max(1, fa.numRegs) * TC_TPB);
         const int by_smem = (int)((size_t)prop.sharedMemPerMultiprocessor / (TC_SMEM_BYTES + 1024));
         c->occ_tc = std::max(1, std::min({by_regs, by_smem, 512 / (TC_GROUPS * TC_TMEM_COLS)}));
@@ -313,25 +315,23 @@ static int launch_iteration(enero_ctx* c, const IDX& idx, int idx_kind, int whic
         CUDA_TRY(cudaEventRecord(e0, stream));
     }
     int* ctr = nullptr;
-    if (c->mp_engine != 1 || !std::is_same<IDX, IdxTopo>::value) TRY(next_tile_counter(c, &ctr, lane));
+    if (c->mp_engine != 1) TRY(next_tile_counter(c, &ctr, lane));
     const int occ = std::max(1, c->occ_iter[c->math_acc][idx_kind][last ? 1 : 0]);
     const int grid = (int)std::min<int64_t>((ntiles + MP_WARPS - 1) / MP_WARPS, (int64_t)c->num_sms * occ);
     auto go = [&](auto kern) { kern<<<grid, MP_TPB, MP_SMEM_BYTES, stream>>>(idx, c->w[which], hin, Ain, hout, Aout, ntiles, ctr); };
     constexpr bool TOPO = std::is_same<IDX, IdxTopo>::value;     // the 3-column first iteration exists for the fused path only
-    if constexpr (TOPO) {
-        if (c->mp_engine == 1) {                                 // tensor-core engine: 128-row tiles, one CTA of 128 threads each
-            const int64_t nt = (idx.rows() + TC_ROWS - 1) / TC_ROWS;
-            const int g = (int)std::min<int64_t>((nt + TC_GROUPS - 1) / TC_GROUPS, (int64_t)c->num_sms * std::max(1, c->occ_tc));
-            auto gtc = [&](auto kern) { kern<<<g, TC_TPB, TC_SMEM_BYTES, stream>>>(idx, c->w[which], hin, Ain, hout, Aout, (int)nt, FeatSrc()); };
-            if (c->math_acc) {
-                if (last) gtc(k_mp_tc<true, 20, true>); else if (sparse) gtc(k_mp_tc<false, 3, true>); else gtc(k_mp_tc<false, 20, true>);
-            } else {
-                if (last) gtc(k_mp_tc<true, 20, false>); else if (sparse) gtc(k_mp_tc<false, 3, false>); else gtc(k_mp_tc<false, 20, false>);
-            }
-            LAUNCH_CHECK(c);
-            if (prof) { CUDA_TRY(cudaEventRecord(e1, stream)); c->prof_ev.emplace_back(e0, e1); }
-            return ENERO_OK;
+    if (c->mp_engine == 1) {                                     // tensor-core engine: 128-row tiles, two tile pipelines per CTA
+        const int64_t nt = (idx.rows() + TC_ROWS - 1) / TC_ROWS;
+        const int g = (int)std::min<int64_t>((nt + TC_GROUPS - 1) / TC_GROUPS, (int64_t)c->num_sms * std::max(1, c->occ_tc));
+        auto gtc = [&](auto kern) { kern<<<g, TC_TPB, TC_SMEM_BYTES, stream>>>(idx, c->w[which], hin, Ain, hout, Aout, (int)nt, FeatSrc()); };
+        if (c->math_acc) {
+            if (last) gtc(k_mp_tc<IDX, true, 20, true>); else if (TOPO && sparse) gtc(k_mp_tc<IDX, false, TOPO ? 3 : 20, true>); else gtc(k_mp_tc<IDX, false, 20, true>);
+        } else {
+            if (last) gtc(k_mp_tc<IDX, true, 20, false>); else if (TOPO && sparse) gtc(k_mp_tc<IDX, false, TOPO ? 3 : 20, false>); else gtc(k_mp_tc<IDX, false, 20, false>);
         }
+        LAUNCH_CHECK(c);
+        if (prof) { CUDA_TRY(cudaEventRecord(e1, stream)); c->prof_ev.emplace_back(e0, e1); }
+        return ENERO_OK;
     }
     if (c->math_acc) {
         if (last) go(k_mp_iter<IDX, true, 20, true>);
@@ -459,8 +459,8 @@ static int decide_dev(enero_ctx* c, enero_topo* t, int B, const double* loads, c
         const int g = (int)std::min<int64_t>((nt + TC_GROUPS - 1) / TC_GROUPS, (int64_t)c->num_sms * std::max(1, c->occ_tc));
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (c->prof) { CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1)); CUDA_TRY(cudaEventRecord(e0, st)); }
-        if (c->math_acc) k_mp_tc<false, 3, true, true><<<g, TC_TPB, TC_SMEM_BYTES, st>>>(idx, c->w[ENERO_ACTOR], nullptr, nullptr, c->h[1].as<float>(), c->A[1].as<float>(), (int)nt, fs);
-        else k_mp_tc<false, 3, false, true><<<g, TC_TPB, TC_SMEM_BYTES, st>>>(idx, c->w[ENERO_ACTOR], nullptr, nullptr, c->h[1].as<float>(), c->A[1].as<float>(), (int)nt, fs);
+        if (c->math_acc) k_mp_tc<IdxTopo, false, 3, true, true><<<g, TC_TPB, TC_SMEM_BYTES, st>>>(idx, c->w[ENERO_ACTOR], nullptr, nullptr, c->h[1].as<float>(), c->A[1].as<float>(), (int)nt, fs);
+        else k_mp_tc<IdxTopo, false, 3, false, true><<<g, TC_TPB, TC_SMEM_BYTES, st>>>(idx, c->w[ENERO_ACTOR], nullptr, nullptr, c->h[1].as<float>(), c->A[1].as<float>(), (int)nt, fs);
         LAUNCH_CHECK(c);
         if (c->prof) { CUDA_TRY(cudaEventRecord(e1, st)); c->prof_ev.emplace_back(e0, e1); }
         for (int it = 1; it < T; ++it)

@@ -176,9 +176,9 @@ __device__ __forceinline__ void tc_feature_row(const FeatSrc& f, const IdxTopo& 
 __device__ __forceinline__ void tc_group_sync(int g) { asm volatile("bar.sync %0, %1;" :: "r"(1 + g), "r"(TC_ROWS) : "memory"); }
 
 // FUSED0 (with KH = 3): iteration 0 rebuilt from the feature tables (`feat`), h_in / A_in unused.
-template <bool LAST, int KH, bool ACC, bool FUSED0 = false>
+template <class IDX, bool LAST, int KH, bool ACC, bool FUSED0 = false>
 __global__ void __launch_bounds__(TC_TPB, 2)
-k_mp_tc(const IdxTopo idx, const float* __restrict__ wflat, const float* __restrict__ h_in, const float* __restrict__ A_in,
+k_mp_tc(const IDX idx, const float* __restrict__ wflat, const float* __restrict__ h_in, const float* __restrict__ A_in,
         float* __restrict__ h_out, float* __restrict__ A_out, int ntiles, const FeatSrc feat = FeatSrc()) {
     extern __shared__ __align__(1024) unsigned char tc_smem[];
     float4* w1_hi = reinterpret_cast<float4*>(tc_smem);
@@ -264,7 +264,7 @@ k_mp_tc(const IdxTopo idx, const float* __restrict__ wflat, const float* __restr
 #pragma unroll
         for (int j = 0; j < H; ++j) h[j] = 0.f;
         if (FUSED0) {
-            if (ok) tc_feature_row(feat, idx, row, h[0], h[1], h[2]);
+            if constexpr (FUSED0) { if (ok) tc_feature_row(feat, idx, row, h[0], h[1], h[2]); }
         } else {
             mbar_wait(bar + 1, parity_tma); parity_tma ^= 1u;
             if (ok) load_row(h, stage + t * H);
@@ -292,8 +292,8 @@ k_mp_tc(const IdxTopo idx, const float* __restrict__ wflat, const float* __restr
         // ---- agg = sum over incoming pairs (ascending pair index) of selu(A[first] + B); two operand rows in flight
         if (FUSED0) {
             for (int p = cur.pb; p < cur.pe; ++p) {
-                float f0, f1, f2, a[H];
-                tc_feature_row(feat, idx, (int64_t)cur.list[p] + cur.add, f0, f1, f2);
+                float f0 = 0.f, f1 = 0.f, f2 = 0.f, a[H];
+                if constexpr (FUSED0) tc_feature_row(feat, idx, (int64_t)cur.list[p] + cur.add, f0, f1, f2);
 #pragma unroll
                 for (int j = 0; j < H; ++j) a[j] = fmaf(f2, swm3[2 * H + j], fmaf(f1, swm3[H + j], fmaf(f0, swm3[j], 0.f)));   // = k_features' A_0
                 mp_accumulate<ACC>(agg2, a, t2);
