@@ -255,6 +255,7 @@ static void topo_free_dev(enero_topo* t) {
     TopoDev& d = t->dev;
     cudaFree(d.cap); cudaFree(d.capf); cudaFree(d.in_off); cudaFree(d.in_first);
     cudaFree(d.sp_off); cudaFree(d.sp_edge); cudaFree(d.mid_off); cudaFree(d.mids); cudaFree(d.out_off); cudaFree(d.out_second);
+    cudaFree(d.cross_off); cudaFree(d.cross_sd);
     d = TopoDev();
     cudaFree(t->d_ksp_pair_off); cudaFree(t->d_ksp_edge_off); cudaFree(t->d_ksp_edge);
     t->d_ksp_pair_off = t->d_ksp_edge_off = t->d_ksp_edge = nullptr;
@@ -279,6 +280,7 @@ extern "C" int enero_topo_upload(enero_ctx* c, enero_topo* t) {
     TRY(upload_vec(&d.sp_off, t->sp_off)); TRY(upload_vec(&d.sp_edge, t->sp_edge));
     TRY(upload_vec(&d.mid_off, t->mid_off)); TRY(upload_vec(&d.mids, t->mids));
     TRY(upload_vec(&d.out_off, t->out_off)); TRY(upload_vec(&d.out_second, t->out_second));
+    TRY(upload_vec(&d.cross_off, t->cross_off)); TRY(upload_vec(&d.cross_sd, t->cross_sd));
     t->dev_id = c->device;
     return ENERO_OK;
 }
@@ -597,6 +599,7 @@ struct enero_batch {
     DevBuf snap;                                    // enero_batch_snapshot image of the mutable state
     DevBuf sap_order, sap_loads, sap_mt, sap_idx, sap_max, sap_act;   // SAP baseline scratch
     DevBuf r_loads, r_sd, r_bw, r_action, r_prob, r_value;            // rollout records
+    DevBuf crit_scratch, ls_routing, ls_nrouting;                      // critical-demand selection scratch
     DevBuf ls_loads, ls_mid, ls_elig, ls_elig_len, ls_val, ls_nmoves, ls_moves, ls_move_val, ls_max_edge;
     std::vector<int> h_cur; std::vector<uint8_t> h_done; bool mirror_valid = false;   // host mirror of (cur, done) for action checks
     std::vector<int> h_elig, h_elig_len;           // host mirror of list_eligible_demands
@@ -670,34 +673,24 @@ extern "C" int enero_batch_reset(enero_batch* b, const double* tms) {
     TopoView tv = view_of(t);
     k_route_loads<<<B, 256, (size_t)E * 8, st>>>(tv, b->tm.as<double>(), nullptr, b->loads.as<double>(), b->max_uti.as<double>(), b->max_edge.as<int>());
     LAUNCH_CHECK(c);
-    std::vector<double> loads((size_t)B * E);
-    CUDA_TRY(cudaMemcpyAsync(loads.data(), b->loads.p, loads.size() * 8, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    b->h_elig.assign((size_t)B * D, 0); b->h_elig_len.assign(B, 0);
-    b->max_len = 0;
+    // critical-demand selection on the device (one CTA per episode); the host keeps a mirror of the lists for the
+    // getters and the best-routing reconstruction
+    TRY(b->crit_scratch.ensure((size_t)B * NN * 4));
     {
-        // critical-demand selection is host work with Python-dict ordering semantics; the episodes
-        // are independent, so it runs on all host cores
-        const int nthreads = (int)std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), (unsigned)((B + 63) / 64)));
-        auto work = [&](int tid) {
-            std::vector<int> sel;
-            for (int i = tid; i < B; i += nthreads) {
-                topo_critical_demands(*t, loads.data() + (size_t)i * E, tms + (size_t)i * NN, nullptr, 0, b->pct, sel);
-                std::copy(sel.begin(), sel.end(), b->h_elig.begin() + (size_t)i * D);
-                b->h_elig_len[i] = (int)sel.size();
-            }
-        };
-        std::vector<std::thread> pool;
-        for (int tid = 1; tid < nthreads; ++tid) pool.emplace_back(work, tid);
-        work(0);
-        for (auto& th : pool) th.join();
+        CritView cv{t->dev.cross_off, t->dev.cross_sd, nullptr, nullptr, nullptr, 0, D, D, b->crit_scratch.as<int>()};
+        const size_t smem = (size_t)E * 8 + (size_t)((NN + 31) / 32) * 4;
+        k_critical_demands<<<B, 256, smem, st>>>(tv, cv, b->loads.as<double>(), b->tm.as<double>(), b->elig.as<int>(), b->elig_len.as<int>());
+        LAUNCH_CHECK(c);
     }
+    b->h_elig.assign((size_t)B * D, 0); b->h_elig_len.assign(B, 0);
+    CUDA_TRY(cudaMemcpyAsync(b->h_elig.data(), b->elig.p, b->h_elig.size() * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(b->h_elig_len.data(), b->elig_len.p, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    b->max_len = 0;
     for (int i = 0; i < B; ++i) {
         if (b->h_elig_len[i] == 0) return fail(ENERO_ERR_INVALID, "enero_batch_reset: traffic matrix yields no eligible demand");
         b->max_len = std::max(b->max_len, b->h_elig_len[i]);
     }
-    CUDA_TRY(cudaMemcpyAsync(b->elig.p, b->h_elig.data(), b->h_elig.size() * 4, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(b->elig_len.p, b->h_elig_len.data(), (size_t)B * 4, cudaMemcpyHostToDevice, st));
     k_episode_begin<<<(B + 3) / 4, 128, 0, st>>>(tv, ep_view(b)); LAUNCH_CHECK(c);
     CUDA_TRY(cudaStreamSynchronize(st));
     b->reset_done = true; b->policy_valid = false; b->mirror_valid = false;
@@ -1025,27 +1018,22 @@ extern "C" int enero_batch_local_search(enero_batch* b, int mode, const int32_t*
     const int cap = mode == 0 ? D : N * (N - 1);
     b->ls_cap = cap;
     b->h_ls_elig.assign((size_t)B * cap, 0); b->h_ls_elig_len.assign(B, 0);
+    TRY(b->ls_elig.ensure((size_t)B * cap * 4)); TRY(b->ls_elig_len.ensure((size_t)B * 4));
     if (mode == 0) {
-        std::vector<double> loads((size_t)B * E), tm((size_t)B * NN);
-        CUDA_TRY(cudaMemcpyAsync(loads.data(), b->ls_loads.p, loads.size() * 8, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaMemcpyAsync(tm.data(), b->tm.p, tm.size() * 8, cudaMemcpyDeviceToHost, st));
+        // critical demands of the restored routing, selected on the device (same kernel as enero_batch_reset, with
+        // the re-routed demands taken out of the direct crossing lists and appended in snapshot order)
+        TRY(b->ls_routing.ensure((size_t)B * rstride * 3 * 4)); TRY(b->ls_nrouting.ensure((size_t)B * 4));
+        TRY(b->crit_scratch.ensure((size_t)B * NN * 4));
+        CUDA_TRY(cudaMemcpyAsync(b->ls_routing.p, routing, (size_t)B * rstride * 3 * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(b->ls_nrouting.p, n_routing, (size_t)B * 4, cudaMemcpyHostToDevice, st));
+        CritView cv{t->dev.cross_off, t->dev.cross_sd, b->ls_mid.as<int>(), b->ls_routing.as<int>(), b->ls_nrouting.as<int>(), rstride,
+                    D, cap, b->crit_scratch.as<int>()};
+        const size_t csm = (size_t)E * 8 + (size_t)((NN + 31) / 32) * 4;
+        k_critical_demands<<<B, 256, csm, st>>>(tv, cv, b->ls_loads.as<double>(), b->tm.as<double>(), b->ls_elig.as<int>(), b->ls_elig_len.as<int>());
+        LAUNCH_CHECK(c);
+        CUDA_TRY(cudaMemcpyAsync(b->h_ls_elig.data(), b->ls_elig.p, b->h_ls_elig.size() * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(b->h_ls_elig_len.data(), b->ls_elig_len.p, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
-        // same host work as in enero_batch_reset (Python-dict ordering semantics): independent per
-        // episode, so it runs on all host cores
-        const int nthreads = (int)std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), (unsigned)((B + 63) / 64)));
-        auto work = [&](int tid) {
-            std::vector<int> sel;
-            for (int i = tid; i < B; i += nthreads) {
-                topo_critical_demands(*t, loads.data() + (size_t)i * E, tm.data() + (size_t)i * NN,
-                                      routing + (size_t)i * rstride * 3, n_routing[i], b->pct, sel);
-                std::copy(sel.begin(), sel.end(), b->h_ls_elig.begin() + (size_t)i * cap);
-                b->h_ls_elig_len[i] = (int)sel.size();
-            }
-        };
-        std::vector<std::thread> pool;
-        for (int tid = 1; tid < nthreads; ++tid) pool.emplace_back(work, tid);
-        work(0);
-        for (auto& th : pool) th.join();
     } else {
         for (int i = 0; i < B; ++i) {
             int n = 0;
@@ -1053,10 +1041,11 @@ extern "C" int enero_batch_local_search(enero_batch* b, int mode, const int32_t*
             b->h_ls_elig_len[i] = n;
         }
     }
-    TRY(b->ls_elig.ensure((size_t)B * cap * 4)); TRY(b->ls_elig_len.ensure((size_t)B * 4));
     TRY(b->ls_moves.ensure((size_t)B * std::max(1, max_moves) * 12)); TRY(b->ls_move_val.ensure((size_t)B * std::max(1, max_moves) * 8));
-    CUDA_TRY(cudaMemcpyAsync(b->ls_elig.p, b->h_ls_elig.data(), b->h_ls_elig.size() * 4, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaMemcpyAsync(b->ls_elig_len.p, b->h_ls_elig_len.data(), (size_t)B * 4, cudaMemcpyHostToDevice, st));
+    if (mode != 0) {
+        CUDA_TRY(cudaMemcpyAsync(b->ls_elig.p, b->h_ls_elig.data(), b->h_ls_elig.size() * 4, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(b->ls_elig_len.p, b->h_ls_elig_len.data(), (size_t)B * 4, cudaMemcpyHostToDevice, st));
+    }
     if (start) CUDA_TRY(cudaMemcpyAsync(start, b->ls_val.p, (size_t)B * 8, cudaMemcpyDeviceToHost, st));
     LsView lv{B, cap, max_moves, b->tm.as<double>(), b->ls_loads.as<double>(), b->ls_mid.as<int>(), b->ls_elig.as<int>(),
               b->ls_elig_len.as<int>(), b->ls_val.as<double>(), b->ls_nmoves.as<int>(), b->ls_moves.as<int>(), b->ls_move_val.as<double>()};

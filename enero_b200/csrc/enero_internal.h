@@ -31,6 +31,8 @@ struct TopoDev {               // device mirrors (all int32 unless noted)
     int* mids = nullptr;          // [mid_total]
     int* out_off = nullptr;       // [E+1] CSR by `first` (pairs leaving a link), pair order
     int* out_second = nullptr;    // [P]
+    int* cross_off = nullptr;     // [E+1] direct-SP crossing lists per link: (s*N+d), row-major
+    int* cross_sd = nullptr;
 };
 
 struct enero_topo {
@@ -69,9 +71,3 @@ inline void topo_route(const enero_topo& t, int s, int d, int mid, std::vector<i
     if (mid < 0 || mid == d) seg(s, d);
     else { seg(s, mid); seg(mid, d); }
 }
-
-// Critical-demand selection shared by Env16.reset and Env15.reset_DRL_hill_sp (host side).
-// loads: [E]; tm: [N*N]; routing: ordered (s,d,mid) re-routes applied on top of direct SPs.
-void topo_critical_demands(const enero_topo& t, const double* loads, const double* tm,
-                           const int* routing, int n_routing, double percentage,
-                           std::vector<int>& out_sd);

@@ -185,6 +185,114 @@ k_route_loads(TopoView t, const double* __restrict__ tm, const int* __restrict__
     }
 }
 
+// ---- critical-demand selection (environment16.py:672-674,188-200; environment15.py:537-538,471-483) -----------
+// One CTA per episode.  The five links with the largest RAW load (stable: ties keep link-id order); walking them in
+// that order, the demands crossing each -- first the un-rerouted ones in row-major (s,d) order (the direct-SP crossing
+// list of the link), then the re-routed ones whose route crosses it, in snapshot (insertion) order -- appended if not
+// seen yet; stable sort by bandwidth descending; truncation to ceil(N(N-1) * pct).  mid_cur / routing == NULL: no demand
+// is re-routed (Env16.reset).  Order-preserving appends go through a warp ballot; the sort is a rank sort (keys
+// (bandwidth, position) are distinct).
+struct CritView {
+    const int* cross_off; const int* cross_sd;      // direct-SP crossing lists per link
+    const int* mid_cur;                             // [B][N*N] re-route middlepoint or -1, or NULL
+    const int* routing; const int* n_routing; int rstride;   // [B][rstride][3] snapshot order, or NULL
+    int lim, cap;                                   // truncation, row stride of elig
+    int* scratch;                                   // [B][N*N] candidate list before sorting
+};
+__global__ void __launch_bounds__(256)
+k_critical_demands(TopoView t, CritView cv, const double* __restrict__ loads, const double* __restrict__ tm,
+                   int* __restrict__ elig, int* __restrict__ elig_len) {
+    extern __shared__ unsigned char crit_smem[];
+    double* sl = reinterpret_cast<double*>(crit_smem);                 // [E] loads (consumed by the top-5 selection)
+    uint32_t* seen = reinterpret_cast<uint32_t*>(sl + t.E);            // [ceil(N*N/32)]
+    __shared__ int s_top[5]; __shared__ int s_n;
+    const int b = blockIdx.x, NN = t.N * t.N, tid = threadIdx.x, lane = tid & 31;
+    const double* ld = loads + (int64_t)b * t.E;
+    const double* tmb = tm + (int64_t)b * NN;
+    const int* mid = cv.mid_cur ? cv.mid_cur + (int64_t)b * NN : nullptr;
+    int* lst = cv.scratch + (int64_t)b * NN;
+    for (int e = tid; e < t.E; e += blockDim.x) sl[e] = ld[e];
+    for (int i = tid; i < (NN + 31) / 32; i += blockDim.x) seen[i] = 0u;
+    if (tid == 0) s_n = 0;
+    __syncthreads();
+    const int ncrit = min(5, t.E);
+    if (tid < 32) {                                                    // sorted(..., key=load, reverse=True)[:5], stable
+        for (int c = 0; c < ncrit; ++c) {
+            double bv = -1.0; int be = 0x7fffffff;
+            for (int e = lane; e < t.E; e += 32) { const double v = sl[e]; if (v > bv) { bv = v; be = e; } }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oe = __shfl_xor_sync(0xffffffffu, be, o);
+                if (ov > bv || (ov == bv && oe < be)) { bv = ov; be = oe; }
+            }
+            if (lane == 0) { s_top[c] = be; sl[be] = -2.0; }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    if (tid < 32) {                                                    // one warp builds the list in reference order
+        int n = 0;
+        for (int c = 0; c < ncrit; ++c) {
+            const int e = s_top[c];
+            const int i0 = cv.cross_off[e], i1 = cv.cross_off[e + 1];
+            for (int base = i0; base < i1; base += 32) {               // entries of one crossing list are distinct
+                const int i = base + lane;
+                int sd = -1; bool keep = false;
+                if (i < i1) {
+                    sd = cv.cross_sd[i];
+                    keep = !(mid && mid[sd] >= 0) && !((seen[sd >> 5] >> (sd & 31)) & 1u);
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, keep);
+                if (keep) { lst[n + __popc(m & ((1u << lane) - 1u))] = sd; atomicOr(&seen[sd >> 5], 1u << (sd & 31)); }
+                n += __popc(m);
+                __syncwarp();
+            }
+            if (cv.routing) {                                          // re-routed demands crossing e, snapshot order
+                const int nr = cv.n_routing[b];
+                const int* rt = cv.routing + (int64_t)b * cv.rstride * 3;
+                for (int base = 0; base < nr; base += 32) {
+                    const int i = base + lane;
+                    int sd = -1; bool keep = false;
+                    if (i < nr) {
+                        const int s = rt[3 * i], d = rt[3 * i + 1], mm = rt[3 * i + 2];
+                        sd = s * t.N + d;
+                        if (mm != d && mid[sd] == mm && !((seen[sd >> 5] >> (sd & 31)) & 1u)) {
+                            bool on = false;
+                            for (int q = t.sp_off[s * t.N + mm]; q < t.sp_off[s * t.N + mm + 1]; ++q) on |= t.sp_edge[q] == e;
+                            for (int q = t.sp_off[mm * t.N + d]; q < t.sp_off[mm * t.N + d + 1]; ++q) on |= t.sp_edge[q] == e;
+                            keep = on;
+                        }
+                    }
+                    // the same (s,d) may appear twice in a snapshot: the first occurrence within this batch wins
+                    for (int o = 0; o < 32; ++o) {
+                        const int osd = __shfl_sync(0xffffffffu, sd, o);
+                        const bool ok = __shfl_sync(0xffffffffu, keep, o);
+                        if (o < lane && ok && osd == sd) keep = false;
+                    }
+                    const unsigned m = __ballot_sync(0xffffffffu, keep);
+                    if (keep) { lst[n + __popc(m & ((1u << lane) - 1u))] = sd; atomicOr(&seen[sd >> 5], 1u << (sd & 31)); }
+                    n += __popc(m);
+                    __syncwarp();
+                }
+            }
+        }
+        if (lane == 0) s_n = n;
+    }
+    __syncthreads();
+    const int n = s_n;
+    __threadfence_block();
+    // sorted(key=bw, reverse=True), stable: rank = #{j : bw_j > bw_i or (bw_j == bw_i and j < i)}
+    for (int i = tid; i < n; i += blockDim.x) {
+        const int sdi = lst[i];
+        const double v = tmb[sdi];
+        int rank = 0;
+        for (int j = 0; j < n; ++j) { const double o = tmb[lst[j]]; rank += (o > v || (o == v && j < i)) ? 1 : 0; }
+        if (rank < cv.lim) elig[(int64_t)b * cv.cap + rank] = sdi;
+    }
+    if (tid == 0) elig_len[b] = min(n, cv.lim);
+}
+
 // ---- episode state ------------------------------------------------------------------------
 struct EpisodeView {
     int B, Dmax;

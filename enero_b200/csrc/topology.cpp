@@ -6,8 +6,8 @@
 //   shortest paths                 environment16.py:478-505 (hop-count shortest, lexicographically
 //                                  smallest node sequence == BFS next-hop table)
 //   candidate middlepoints         environment16.py:395-476
-// and the critical-demand selection of reset / reset_DRL_hill_sp
-//   environment16.py:672-674,188-200 ; environment15.py:537-538,471-483.
+// plus the per-link crossing lists of the direct shortest paths that the device-side critical-demand selection
+// (k_critical_demands; environment16.py:672-674,188-200 ; environment15.py:537-538,471-483) walks.
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -115,44 +115,6 @@ void middlepoints(enero_topo& t) {
 }
 
 }  // namespace
-
-void topo_critical_demands(const enero_topo& t, const double* loads, const double* tm,
-                           const int* routing, int n_routing, double percentage,
-                           std::vector<int>& out_sd) {
-    const int N = t.N, E = t.E;
-    std::vector<int> order(E);
-    std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return loads[a] > loads[b]; });
-    const int ncrit = std::min(5, E);                           // num_critical_links
-    std::vector<int> rer((size_t)N * N, -2);                    // -2: not re-routed
-    for (int i = 0; i < n_routing; ++i) {
-        int s = routing[3 * i], d = routing[3 * i + 1], m = routing[3 * i + 2];
-        if (m != d) rer[(size_t)s * N + d] = m;
-    }
-    std::vector<char> seen((size_t)N * N, 0);
-    std::vector<int> lst, route;
-    for (int c = 0; c < ncrit; ++c) {
-        const int e = order[c];
-        for (int i = t.cross_off[e]; i < t.cross_off[e + 1]; ++i) {
-            int sd = t.cross_sd[i];
-            if (rer[sd] != -2) continue;                        // deleted by decrease_links_utilization_sp
-            if (!seen[sd]) { seen[sd] = 1; lst.push_back(sd); }
-        }
-        for (int i = 0; i < n_routing; ++i) {                   // re-added at the end, in snapshot order
-            int s = routing[3 * i], d = routing[3 * i + 1], m = routing[3 * i + 2];
-            if (m == d) continue;
-            int sd = s * N + d;
-            if (rer[sd] != m) continue;                         // a later duplicate key wins its first slot only
-            topo_route(t, s, d, m, route);
-            if (std::find(route.begin(), route.end(), e) == route.end()) continue;
-            if (!seen[sd]) { seen[sd] = 1; lst.push_back(sd); }
-        }
-    }
-    std::stable_sort(lst.begin(), lst.end(), [&](int a, int b) { return tm[a] > tm[b]; });
-    const int lim = (int)std::ceil((double)(N * (N - 1)) * percentage);
-    if ((int)lst.size() > lim) lst.resize(lim);
-    out_sd.swap(lst);
-}
 
 extern "C" int enero_topo_build(int N, int E, const int32_t* edge_src, const int32_t* edge_dst,
                                 const double* capacity, int K, const int32_t* sp_off,
