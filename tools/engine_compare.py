@@ -1,5 +1,9 @@
+"""Tensor-core engine (k_mp_tc) against the FP32-pipe engine (k_mp_iter) on the GPU box: logits of golden decisions (vs each
+other and vs the reference-recorded oracle logits), throughput and per-launch time at 4 096 episodes of cfg2, and greedy
+episode identity over the whole batch.    python tools/engine_compare.py"""
 import sys, os, tempfile, time
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import numpy as np
 from conftest import *
 from oracle import enero_oracle as orc

@@ -1,5 +1,9 @@
+"""Where a k_mp_tc tile spends its time: build with  ENERO_NVCC_EXTRA=-DENERO_TC_TIMING python -m enero_b200.build --force  and
+run this on the GPU box; thread 0 of every group accumulates clock64() per segment of the tile loop (operand store, MMA waits,
+gather, gates, read-back), printed as shares.  Without the macro only the throughput lines are printed."""
 import sys, os, tempfile, time, ctypes
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import numpy as np
 from conftest import *
 from oracle import enero_oracle as orc
