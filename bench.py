@@ -160,7 +160,8 @@ _WORKER = {}
 def _cpu_episodes(args):
     """(tms [n,N,N], torch threads) -> (decisions, seconds): n whole greedy episodes, reset included, one after the
     other -- what one worker process of eval_on_single_topology.py does for its traffic matrix."""
-    tms, threads = args
+    tms, threads = args[0], args[1]
+    max_dec = args[2] if len(args) > 2 else 0          # 0 = whole episodes; tests bound the work
     import torch
     torch.set_num_threads(int(threads))
     from oracle import enero_oracle as orc
@@ -183,6 +184,8 @@ def _cpu_episodes(args):
                 a = int(torch.argmax(torch.softmax(logits, dim=0)))
             _, done, _, _, s, d, _, _, _ = env.step(a)
             n += 1
+            if max_dec and n >= max_dec:
+                return n, time.perf_counter() - t0
     return n, time.perf_counter() - t0
 
 
@@ -202,7 +205,7 @@ def run_reference(args, rank, world):
         for i in range(args.warmup + args.steps):
             tms = make_tms(gf, sigma, cores, 2000 + 64 * i)
             t0 = time.perf_counter()
-            res = pool.map(_cpu_episodes, [(tms[j:j + 1], 1) for j in range(cores)], chunksize=1)
+            res = pool.map(_cpu_episodes, [(tms[j:j + 1], 1, args.ref_decisions) for j in range(cores)], chunksize=1)
             wall = time.perf_counter() - t0
             if i >= args.warmup:
                 vals.append((sum(r[0] for r in res), wall))
@@ -212,9 +215,9 @@ def run_reference(args, rank, world):
     # BASELINE.md section 2 also asks for the single-process numbers: one thread and all threads
     os.environ["OMP_NUM_THREADS"] = str(cores)
     one_tm = make_tms(gf, sigma, 1, 1999)
-    _cpu_episodes((one_tm, 1))
-    n1, t1 = _cpu_episodes((one_tm, 1))
-    na, ta = _cpu_episodes((one_tm, cores))
+    _cpu_episodes((one_tm, 1, args.ref_decisions))
+    n1, t1 = _cpu_episodes((one_tm, 1, args.ref_decisions))
+    na, ta = _cpu_episodes((one_tm, cores, args.ref_decisions))
     sample = ("%d whole greedy episodes per step (one per process, %d single-threaded processes, ~%d decisions each): torch-CPU "
               "actor with index_add_ segment sums + reference env semantics" % (cores, cores, tot // max(1, len(vals) * cores)))
     line = {
@@ -546,6 +549,8 @@ def main():
     ap.add_argument("--batch", type=int, default=4096, help="episodes per GPU")
     ap.add_argument("--e2e-batch", type=int, default=4096)
     ap.add_argument("--cpu-decisions", type=int, default=1000, help="CPU-baseline sample (about 15 s on one core)")
+    ap.add_argument("--ref-decisions", type=int, default=0,
+                    help="--impl reference: cap every worker at this many decisions per step (0 = whole episodes; tests use a small cap)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-sweep", action="store_true", help="skip the 1..16384-episode batch sweep of the N=1 run")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
