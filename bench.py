@@ -405,18 +405,25 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         # second stage on the same batch (Local Search reported separately): hill climbing to
         # convergence from the DRL routing, on device; informative extras, not part of `value`
-        t0 = time.perf_counter()
-        ls = eb2.local_search(None, mode=0, want_moves=False)
-        ctx.sync()
-        t_ls = time.perf_counter() - t0
-        t0 = time.perf_counter()
-        sap = eb2.sap(None)
-        t_sap = time.perf_counter() - t0
-        extras = {"local_search": {"tms_per_s": Be / t_ls, "ms": 1000.0 * t_ls, "episodes": Be, "moves_applied": int(ls["n_moves"].sum()),
+        # (each stage twice, the second timed: the first call pays allocations, the K-shortest-path tables and
+        # module loading; it is reported as first_call_ms)
+        t_ls = t_sap = first_ls = first_sap = None
+        for rep in range(2):
+            eb2.reset(tms_e); eb2.run_greedy(); ctx.sync()
+            t0 = time.perf_counter()
+            ls = eb2.local_search(None, mode=0, want_moves=False)
+            ctx.sync()
+            t_ls = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            sap = eb2.sap(None)
+            t_sap = time.perf_counter() - t0
+            if rep == 0:
+                first_ls, first_sap = t_ls, t_sap
+        extras = {"local_search": {"tms_per_s": Be / t_ls, "ms": 1000.0 * t_ls, "first_call_ms": 1000.0 * first_ls, "episodes": Be, "moves_applied": int(ls["n_moves"].sum()),
                                    "mean_max_uti_drl": float(best.mean()), "mean_max_uti_enero": float(ls["final"].mean()),
                                    "mean_max_uti_ospf": float(ospf.mean())},
                   "full_enero_tms_per_s": Be / (t_best + t_ls),
-                  "sap_baseline": {"tms_per_s": Be / t_sap, "mean_max_uti": float(sap.mean())}}
+                  "sap_baseline": {"tms_per_s": Be / t_sap, "ms": 1000.0 * t_sap, "first_call_ms": 1000.0 * first_sap, "mean_max_uti": float(sap.mean())}}
     eb2.close()
     eb.close()
 

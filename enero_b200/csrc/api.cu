@@ -116,6 +116,7 @@ extern "C" int enero_ctx_create(int device, enero_ctx** out) {
     }
     if (const char* e = std::getenv("ENERO_NO_GRAPHS")) c->no_graphs = std::atoi(e) != 0;
     if (const char* e = std::getenv("ENERO_UNFUSED_FEATURES")) c->prof_unfused = std::atoi(e) != 0;
+    if (const char* e = std::getenv("ENERO_FUSED_TAIL")) c->tail_mode = std::atoi(e) != 0;
     c->math_acc = ENERO_MATH_DEFAULT;
     if (const char* e = std::getenv("ENERO_MATH")) {
         if (!std::strcmp(e, "fast")) c->math_acc = 0;
@@ -439,7 +440,8 @@ extern "C" int enero_gnn_forward(enero_ctx* c, int which, const float* link_stat
 // ---- fused decision batch (device pointers) -------------------------------------------------------
 // logits/probs [B,Kmax], nK/action [B]; skip: u8[B] or NULL
 static int decide_dev(enero_ctx* c, enero_topo* t, int B, const double* loads, const int* sd, const double* bw,
-                      const uint8_t* skip, float* logits, float* probs, int* nK, int* action, int T) {
+                      const uint8_t* skip, float* logits, float* probs, int* nK, int* action, int T,
+                      const EpisodeView* step_ep = nullptr) {
     const TopoDev& d = t->dev;
     const int RPD = d.Kmax * d.E;
     const int64_t rows = (int64_t)B * RPD;
@@ -447,16 +449,17 @@ static int decide_dev(enero_ctx* c, enero_topo* t, int B, const double* loads, c
     TRY(ensure_rows(c, rows));
     TRY(c->util.ensure((size_t)B * d.E * 4));
     TopoView tv = view_of(t);
-    CUDA_TRY(cudaMemsetAsync(logits, 0, (size_t)B * d.Kmax * 4, st));
-    k_decision_prep<<<(int)(((int64_t)B * d.E + 255) / 256), 256, 0, st>>>(tv, B, loads, sd, skip, nK, c->util.as<float>()); LAUNCH_CHECK(c);
     IdxTopo idx{rows, d.E, d.off_f, d.off_s, RPD, nK, d.in_off, d.in_first};
-    if (c->mp_engine == 1 && T > 1 && !c->prof_unfused) {
+    const bool fused0 = c->mp_engine == 1 && T > 1 && !c->prof_unfused;
+    if (!fused0) { k_decision_prep<<<(int)(((int64_t)B * d.E + 255) / 256), 256, 0, st>>>(tv, B, loads, sd, skip, nK, c->util.as<float>()); LAUNCH_CHECK(c); }
+    if (fused0) {
         // tensor-core engine: iteration 0 rebuilds the feature rows from tables (no k_features, no h_0 / A_0 in HBM)
         const int W = (d.E + 31) / 32;
-        TRY(c->bwcap.ensure((size_t)B * d.E * 4)); TRY(c->marks.ensure((size_t)B * d.Kmax * W * 4));
+        TRY(c->bwcap.ensure((size_t)B * d.E * 4)); TRY(c->marks.ensure((size_t)B * d.Kmax * W * 4)); TRY(c->ptab.ensure((size_t)B * d.E * 2 * H * 4));
         const int64_t work = std::max<int64_t>((int64_t)B * d.E, (int64_t)B * d.Kmax);
-        k_decision_marks<<<(int)((work + 255) / 256), 256, 0, st>>>(tv, B, W, sd, bw, nK, c->bwcap.as<float>(), c->marks.as<uint32_t>()); LAUNCH_CHECK(c);
-        FeatSrc fs{c->util.as<float>(), c->bwcap.as<float>(), d.capf, c->marks.as<uint32_t>(), W, d.Kmax};
+        k_decision_tables<<<(int)((work + 255) / 256), 256, 0, st>>>(tv, B, W, loads, sd, bw, skip, c->w[ENERO_ACTOR], nK, c->util.as<float>(), c->bwcap.as<float>(),
+                                                                     c->marks.as<uint32_t>(), c->ptab.as<float>()); LAUNCH_CHECK(c);
+        FeatSrc fs{c->util.as<float>(), c->bwcap.as<float>(), d.capf, c->marks.as<uint32_t>(), c->ptab.as<float>(), W, d.Kmax};
         const int64_t nt = (rows + TC_ROWS - 1) / TC_ROWS;
         const int g = (int)std::min<int64_t>((nt + TC_GROUPS - 1) / TC_GROUPS, (int64_t)c->num_sms * std::max(1, c->occ_tc));
         cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -474,8 +477,21 @@ static int decide_dev(enero_ctx* c, enero_topo* t, int B, const double* loads, c
         TRY(run_iterations(c, idx, ENERO_ACTOR, T, rows, 1, T > 1));
     }
     GraphsTopo gr{B, d.Kmax, d.E, RPD, nK};
-    k_readout<GraphsTopo><<<(B * d.Kmax + 3) / 4, 128, 0, st>>>(gr, c->w[ENERO_ACTOR], c->h[T & 1].as<float>(), logits); LAUNCH_CHECK(c);
-    k_policy<<<(B + 3) / 4, 128, 0, st>>>(B, d.Kmax, nK, logits, probs, action); LAUNCH_CHECK(c);
+    // read-out + soft-max + arg-max (+ Env16.step with the greedy action when the caller runs the episode on the device)
+    // One launch for the tail wins while the step is latency bound (-2 % per decision at <= 16 episodes); from a few
+    // hundred decisions on, three full-width launches beat CTAs whose warp 0 runs the serial part (+0.8 % at 4 096).
+    const bool fused_tail = c->tail_mode < 0 ? B < 512 : c->tail_mode != 0;
+    if (!fused_tail) {
+        CUDA_TRY(cudaMemsetAsync(logits, 0, (size_t)B * d.Kmax * 4, st));
+        k_readout<GraphsTopo><<<(B * d.Kmax + 3) / 4, 128, 0, st>>>(gr, c->w[ENERO_ACTOR], c->h[T & 1].as<float>(), logits); LAUNCH_CHECK(c);
+        k_policy<<<(B + 3) / 4, 128, 0, st>>>(B, d.Kmax, nK, logits, probs, action); LAUNCH_CHECK(c);
+        if (step_ep) { k_env_step<<<(B + 3) / 4, 128, 0, st>>>(tv, *step_ep, action); LAUNCH_CHECK(c); }
+        return ENERO_OK;
+    }
+    const int ftpb = FIN_TPB;
+    if (step_ep) k_decision_finish<true><<<B, ftpb, 0, st>>>(gr, c->w[ENERO_ACTOR], c->h[T & 1].as<float>(), logits, probs, action, tv, *step_ep);
+    else k_decision_finish<false><<<B, ftpb, 0, st>>>(gr, c->w[ENERO_ACTOR], c->h[T & 1].as<float>(), logits, probs, action, tv, EpisodeView{});
+    LAUNCH_CHECK(c);
     return ENERO_OK;
 }
 
@@ -584,7 +600,7 @@ extern "C" int enero_value_batch(enero_ctx* c, enero_topo* t, int B, const doubl
 // captured greedy decision step (enero_batch_run_greedy): executable graph + what its nodes baked in
 struct GreedyGraph {
     cudaGraphExec_t exec = nullptr;
-    const void* key[8] = {};
+    const void* key[10] = {};
     int kernels = 0;
     void release() { if (exec) cudaGraphExecDestroy(exec); exec = nullptr; }
 };
@@ -835,8 +851,8 @@ extern "C" int enero_batch_step_state(enero_batch* b, const int32_t* actions, do
     return ENERO_OK;
 }
 
-// One greedy decision step (decide_dev + step_dev) captured as a CUDA graph and replayed max_len times: at small
-// batch sizes the episode is bound by launch latency (10 launches per decision), and a graph replay hands the whole
+// One greedy decision step (decide_dev with the env step in its last kernel) captured as a CUDA graph and replayed max_len times: at small
+// batch sizes the episode is bound by launch latency (7 launches per decision), and a graph replay hands the whole
 // step to the GPU in one submission.  The graph is keyed on everything its nodes baked in (buffer addresses, math
 // mode) and re-captured when any of it changes.
 static int greedy_step_graph(enero_batch* b) {
@@ -845,17 +861,18 @@ static int greedy_step_graph(enero_batch* b) {
     TRY(ensure_rows(c, rows));                                   // no allocation may happen while capturing
     TRY(c->util.ensure((size_t)b->B * d.E * 4));
     TRY(c->bwcap.ensure((size_t)b->B * d.E * 4)); TRY(c->marks.ensure((size_t)b->B * d.Kmax * ((d.E + 31) / 32) * 4));
-    const void* key[8] = {c->h[0].p, c->h[1].p, c->A[0].p, c->A[1].p, c->util.p, b->loads.p,
-                          (const void*)(intptr_t)(c->math_acc + 1 + 4 * c->mp_engine), (const void*)c->marks.p};
+    TRY(c->ptab.ensure((size_t)b->B * d.E * 2 * H * 4));
+    const void* key[10] = {c->ptab.p, c->bwcap.p, c->h[0].p, c->h[1].p, c->A[0].p, c->A[1].p, c->util.p, b->loads.p,
+                          (const void*)(intptr_t)(c->math_acc + 1 + 4 * c->mp_engine + 16 * (c->tail_mode + 1)), (const void*)c->marks.p};
     GreedyGraph& g = b->graph;
     if (g.exec && !std::memcmp(key, g.key, sizeof(key))) return ENERO_OK;
     g.release();
     c->tile_ctr_next = 16;                                       // the captured step starts by zeroing its own tile counters
     const int64_t l0 = c->launches;
     CUDA_TRY(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-    int r = decide_dev(c, b->t, b->B, b->loads.as<double>(), b->cur.as<int>(), b->cur_bw.as<double>(), b->done.as<uint8_t>(),
-                       b->logits.as<float>(), b->probs.as<float>(), b->nK.as<int>(), b->action.as<int>(), 5);
-    if (r == ENERO_OK) r = step_dev(b);
+    const EpisodeView ep = ep_view(b);
+    const int r = decide_dev(c, b->t, b->B, b->loads.as<double>(), b->cur.as<int>(), b->cur_bw.as<double>(), b->done.as<uint8_t>(),
+                             b->logits.as<float>(), b->probs.as<float>(), b->nK.as<int>(), b->action.as<int>(), 5, &ep);
     cudaGraph_t graph = nullptr;
     const cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
     g.kernels = (int)(c->launches - l0);
@@ -878,11 +895,11 @@ extern "C" int enero_batch_run_greedy(enero_batch* b) {
     enero_ctx* c = b->c;
     CUDA_TRY(cudaSetDevice(c->device));
     if (c->prof || c->no_graphs) {                               // per-launch event timing needs individual launches
-        for (int s = 0; s < b->max_len; ++s) {
+        const EpisodeView ep = ep_view(b);
+        for (int s = 0; s < b->max_len; ++s)
             TRY(decide_dev(c, b->t, b->B, b->loads.as<double>(), b->cur.as<int>(), b->cur_bw.as<double>(), b->done.as<uint8_t>(),
-                           b->logits.as<float>(), b->probs.as<float>(), b->nK.as<int>(), b->action.as<int>(), 5));
-            TRY(step_dev(b));
-        }
+                           b->logits.as<float>(), b->probs.as<float>(), b->nK.as<int>(), b->action.as<int>(), 5, &ep));
+        b->policy_valid = false;
     } else {
         TRY(greedy_step_graph(b));
         for (int s = 0; s < b->max_len; ++s) CUDA_TRY(cudaGraphLaunch(b->graph.exec, c->stream));

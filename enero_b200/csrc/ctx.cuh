@@ -70,7 +70,9 @@ struct enero_ctx {
     float* w[2] = {nullptr, nullptr};
     int64_t launches = 0;
     // scratch of the GNN engine
-    DevBuf bwcap, marks;                      // tables of the fused first iteration (k_decision_marks)
+    DevBuf bwcap, marks, ptab;                      // tables of the fused first iteration (k_decision_tables)
+    int tail_mode = -1;                      // decision tail: 1 = k_decision_finish, 0 = k_readout + k_policy + k_env_step, -1 = by batch
+                                             // size (ENERO_FUSED_TAIL=0/1 forces one; measured cross-over in DESIGN.md)
     bool prof_unfused = false;               // ENERO_UNFUSED_FEATURES=1: keep k_features + generic iteration 0 (A/B measurements)
     DevBuf h[2], A[2], util, nK, logits, probs, action, in_loads, in_sd, in_bw, ones;
     DevBuf x_ls, x_gid, x_first, x_second, x_cnt, x_off, x_cur, x_slot, x_src, x_goff, x_err, x_out;

@@ -22,35 +22,55 @@ struct TopoView {   // by-value kernel argument
 // ---- per-decision prologue: candidate count + fp32 utilisation feature -----------------
 // utilization feature = fp32(load / capacity): fp64 divide then cast
 // (script_eval_on_single_topology.py:144).
+__device__ __forceinline__ int candidate_count(const TopoView& t, const int* __restrict__ sd, const uint8_t* __restrict__ skip, int b) {
+    const int s = sd[2 * b], d = sd[2 * b + 1];
+    if ((skip && skip[b]) || s < 0 || d < 0 || s >= t.N || d >= t.N || s == d) return 0;
+    return t.mid_off[s * t.N + d + 1] - t.mid_off[s * t.N + d];
+}
+
 __global__ void k_decision_prep(TopoView t, int B, const double* __restrict__ loads, const int* __restrict__ sd,
                                 const uint8_t* __restrict__ skip, int* __restrict__ nK, float* __restrict__ util) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)B * t.E) return;
     const int b = (int)(i / t.E), e = (int)(i - (int64_t)b * t.E);
     util[i] = (float)(loads[i] / t.cap[e]);
-    if (e == 0) {
-        const int s = sd[2 * b], d = sd[2 * b + 1];
-        int k = 0;
-        if (!(skip && skip[b]) && s >= 0 && d >= 0 && s < t.N && d < t.N && s != d)
-            k = t.mid_off[s * t.N + d + 1] - t.mid_off[s * t.N + d];
-        nK[b] = k;
-    }
+    if (e == 0) nK[b] = candidate_count(t, sd, skip, b);
 }
 
 // Tables of the fused first iteration (k_mp_tc<FUSED0>): bwcap[b][e] = fp32(bw / cap) (the double-rounded mark value of
 // mark_action_sp, environment16.py:723) and one bit per (decision, candidate, link): link on path(s,mid) U path(mid,d).
-__global__ void k_decision_marks(TopoView t, int B, int W, const int* __restrict__ sd, const double* __restrict__ bw,
-                                 const int* __restrict__ nK, float* __restrict__ bwcap, uint32_t* __restrict__ mask) {
+// ptab[b][e][0 / 1][20]: the first message operand A_0 = h_0 . Wm[0:20] of link e of decision b, unmarked / marked, with
+// the fma order of k_features (a zero mark feature adds nothing: fma(0, w, x) = x).
+// The prologue (util, nK) is part of the same launch.
+__global__ void k_decision_tables(TopoView t, int B, int W, const double* __restrict__ loads, const int* __restrict__ sd,
+                                  const double* __restrict__ bw, const uint8_t* __restrict__ skip, const float* __restrict__ wflat,
+                                  int* __restrict__ nK, float* __restrict__ util, float* __restrict__ bwcap,
+                                  uint32_t* __restrict__ mask, float* __restrict__ ptab) {
+    __shared__ __align__(16) float sw[3 * H];
+    if (threadIdx.x < 3 * H) sw[threadIdx.x] = wflat[W_MSG_K + threadIdx.x];
+    __syncthreads();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < (int64_t)B * t.E) {
         const int b = (int)(i / t.E), e = (int)(i - (int64_t)b * t.E);
-        bwcap[i] = (float)(bw[b] / t.cap[e]);
+        const double cap = t.cap[e];
+        const float f0 = (float)(loads[i] / cap), f1 = t.capf[e], f2 = (float)(bw[b] / cap);
+        util[i] = f0;
+        bwcap[i] = f2;
+        float p0[H], p1[H];
+#pragma unroll
+        for (int j = 0; j < H; ++j) {
+            p0[j] = fmaf(f1, sw[H + j], fmaf(f0, sw[j], 0.f));
+            p1[j] = fmaf(f2, sw[2 * H + j], p0[j]);
+        }
+        store_row(ptab + i * (2 * H), p0);
+        store_row(ptab + i * (2 * H) + H, p1);
+        if (e == 0) nK[b] = candidate_count(t, sd, skip, b);
     }
     if (i < (int64_t)B * t.Kmax) {
         const int b = (int)(i / t.Kmax), k = (int)(i - (int64_t)b * t.Kmax);
         uint32_t* m = mask + i * W;
         for (int w = 0; w < W; ++w) m[w] = 0u;
-        if (k < nK[b]) {
+        if (k < candidate_count(t, sd, skip, b)) {
             const int s = sd[2 * b], d = sd[2 * b + 1];
             const int mid = t.mids[t.mid_off[s * t.N + d] + k];
             for (int q = t.sp_off[s * t.N + mid]; q < t.sp_off[s * t.N + mid + 1]; ++q) m[t.sp_edge[q] >> 5] |= 1u << (t.sp_edge[q] & 31);
@@ -332,17 +352,12 @@ __global__ void k_episode_begin(TopoView t, EpisodeView ep) {
 }
 
 // Env16.step (environment16.py:582-640), one warp per episode.
-__global__ void __launch_bounds__(128)
-k_env_step(TopoView t, EpisodeView ep, const int* __restrict__ action) {
-    const int lane = threadIdx.x & 31;
-    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (b >= ep.B || ep.done[b]) return;
+__device__ __forceinline__ void env_step_warp(const TopoView& t, const EpisodeView& ep, int b, int a, int lane) {
     const int NN = t.N * t.N;
     double* loads = ep.loads + (int64_t)b * t.E;
     int* mid_cur = ep.mid_cur + (int64_t)b * NN;
     const int s = ep.cur[2 * b], d = ep.cur[2 * b + 1];
     const double bw = ep.cur_bw[b];
-    const int a = action[b];
     const int mid = t.mids[t.mid_off[s * t.N + d] + a];
     warp_demand_add(t, loads, s, d, mid, bw, lane);
     if (mid != d && lane == 0) mid_cur[s * t.N + d] = mid;
@@ -375,6 +390,48 @@ k_env_step(TopoView t, EpisodeView ep, const int* __restrict__ action) {
         ep.it[b] = it; ep.cur[2 * b] = ns; ep.cur[2 * b + 1] = nd; ep.cur_bw[b] = nbw;
         ep.steps[b] = step + 1; ep.done[b] = fin ? 1 : 0;
     }
+}
+
+__global__ void __launch_bounds__(128)
+k_env_step(TopoView t, EpisodeView ep, const int* __restrict__ action) {
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= ep.B || ep.done[b]) return;
+    env_step_warp(t, ep, b, action[b], lane);
+}
+
+// Tail of one decision in one launch (one CTA per decision): read-out of the K' candidate graphs (a warp each),
+// soft-max + arg-max over their logits, and -- STEP -- Env16.step with the greedy action.  The arithmetic is that of
+// k_readout / k_policy / k_env_step, which stay for the callers that need the stages apart.
+constexpr int FIN_TPB = 512;
+template <bool STEP>
+__global__ void __launch_bounds__(FIN_TPB)
+k_decision_finish(GraphsTopo gr, const float* __restrict__ wflat, const float* __restrict__ h, float* logits,
+                  float* __restrict__ probs, int* __restrict__ action, TopoView t, EpisodeView ep) {
+    __shared__ float sr[W_R3_B + 1 - W_R1_K];
+    const int b = blockIdx.x;
+    const int n = gr.nK[b];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* x = logits + (int64_t)b * gr.Kmax;
+    if (n > 0) {
+        for (int i = threadIdx.x; i <= W_R3_B - W_R1_K; i += blockDim.x) sr[i] = wflat[W_R1_K + i];
+        __syncthreads();
+        for (int k = warp; k < gr.Kmax; k += blockDim.x >> 5) {
+            float y = 0.f;
+            if (k < n) {
+                const int64_t r0 = (int64_t)b * gr.RPD + (int64_t)k * gr.E;
+                y = readout_graph(sr, h, r0, r0 + gr.E, lane);
+            }
+            if (lane == 0) x[k] = y;
+        }
+        __syncthreads();                        // the CTA's logits are visible to warp 0
+    } else {
+        for (int k = threadIdx.x; k < gr.Kmax; k += blockDim.x) x[k] = 0.f;
+    }
+    if (warp != 0) return;
+    const int bi = policy_warp(x, n, gr.Kmax, probs ? probs + (int64_t)b * gr.Kmax : nullptr, lane);
+    if (lane == 0 && action) action[b] = bi;
+    if (STEP && !ep.done[b]) env_step_warp(t, ep, b, bi, lane);
 }
 
 // ---- sampled-action rollouts (train_Enero_3top_script.py:495-506) ---------------------------------------------

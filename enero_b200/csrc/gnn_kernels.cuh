@@ -68,6 +68,7 @@ struct RowRef {            // what k_mp_iter needs to know about one link-state 
     int pb, pe;            // its incoming pairs: list[pb..pe)
     const int* list;       // source rows (before `add`)
     int64_t add;
+    unsigned b, base;      // IdxTopo only: decision, and `add` within the decision (add = b * RPD + base)
 };
 // Explicit: arbitrary first/second of the signature-compatible path, as a CSR by
 // destination row built on device (stable in pair order).
@@ -83,7 +84,7 @@ struct IdxExplicit {
         b = seg_off[r]; e = seg_off[r + 1]; list = src; add = 0;
     }
     __device__ __forceinline__ void ref(int64_t r, RowRef& o) const {
-        o.ok = r < n; o.pb = o.pe = 0; o.list = src; o.add = 0;
+        o.ok = r < n; o.pb = o.pe = 0; o.list = src; o.add = 0; o.b = o.base = 0;
         if (o.ok) { o.pb = seg_off[r]; o.pe = seg_off[r + 1]; }
     }
 };
@@ -126,7 +127,7 @@ struct IdxTopo {
     // valid() + seg() in one go with 32-bit arithmetic (the host guarantees total < 2^31 for this path;
     // the 64-bit divisions of the separate calls cost ~7 % of the kernel, profiles/r01_v3_*)
     __device__ __forceinline__ void ref(int64_t r64, RowRef& o) const {
-        o.ok = false; o.pb = o.pe = 0; o.list = in_first; o.add = 0;
+        o.ok = false; o.pb = o.pe = 0; o.list = in_first; o.add = 0; o.b = o.base = 0;
         if (r64 >= total) return;
         const unsigned r = (unsigned)r64;
         const unsigned b = r / (unsigned)RPD;
@@ -136,7 +137,10 @@ struct IdxTopo {
         o.ok = true;
         if (off_s > 0) {
             const unsigned k = lr / (unsigned)off_s, x = lr - k * (unsigned)off_s;
-            if ((int)k < nk) { o.pb = in_off[x]; o.pe = in_off[x + 1]; o.add = (int64_t)(b * (unsigned)RPD + k * (unsigned)off_f); }
+            if ((int)k < nk) {
+                o.pb = in_off[x]; o.pe = in_off[x + 1]; o.b = b; o.base = k * (unsigned)off_f;
+                o.add = (int64_t)(b * (unsigned)RPD + k * (unsigned)off_f);
+            }
         }
     }
 };
@@ -629,16 +633,8 @@ __device__ __forceinline__ void graph_row_sum(float (&acc)[H], const float* __re
     for (int k = 0; k < H; ++k) acc[k] = __shfl_sync(0xffffffffu, s, k);
 }
 
-template <class GR>
-__global__ void __launch_bounds__(128)
-k_readout(const GR gr, const float* __restrict__ wflat, const float* __restrict__ h, float* __restrict__ out) {
-    __shared__ float sr[W_R3_B + 1 - W_R1_K];
-    for (int i = threadIdx.x; i <= W_R3_B - W_R1_K; i += blockDim.x) sr[i] = wflat[W_R1_K + i];
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    int64_t r0, r1, o;
-    if (!gr.range(g, r0, r1, o)) return;
+// sr: the readout weights W_R1_K..W_R3_B staged in shared memory; every lane returns the graph's scalar
+__device__ __forceinline__ float readout_graph(const float* sr, const float* __restrict__ h, int64_t r0, int64_t r1, int lane) {
     float acc[H];
     graph_row_sum(acc, h, r0, r1, lane);
     const float* R1 = sr; const float* B1 = sr + (W_R1_B - W_R1_K);
@@ -656,20 +652,27 @@ k_readout(const GR gr, const float* __restrict__ wflat, const float* __restrict_
     float y = 0.f;
 #pragma unroll
     for (int k = 0; k < H; ++k) y = fmaf(__shfl_sync(0xffffffffu, a2, k), R3[k], y);
-    if (lane == 0) out[o] = y + B3[0];
+    return y + B3[0];
+}
+
+template <class GR>
+__global__ void __launch_bounds__(128)
+k_readout(const GR gr, const float* __restrict__ wflat, const float* __restrict__ h, float* __restrict__ out) {
+    __shared__ float sr[W_R3_B + 1 - W_R1_K];
+    for (int i = threadIdx.x; i <= W_R3_B - W_R1_K; i += blockDim.x) sr[i] = wflat[W_R1_K + i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int64_t r0, r1, o;
+    if (!gr.range(g, r0, r1, o)) return;
+    const float y = readout_graph(sr, h, r0, r1, lane);
+    if (lane == 0) out[o] = y;
 }
 
 // ---- soft-max over the K' logits of each decision + greedy action --------------------
 // tf.nn.softmax (script_eval_on_single_topology.py:125-126): exp(x - max) * (1 / sum);
-// np.argmax (script :177): first maximum of the fp32 probabilities.
-__global__ void __launch_bounds__(128)
-k_policy(int B, int Kmax, const int* __restrict__ nK, const float* __restrict__ logits,
-         float* __restrict__ probs, int* __restrict__ action) {
-    const int lane = threadIdx.x & 31;
-    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (b >= B) return;
-    const int n = nK[b];
-    const float* x = logits + (int64_t)b * Kmax;
+// np.argmax (script :177): first maximum of the fp32 probabilities.  One warp; every lane returns the action.
+__device__ __forceinline__ int policy_warp(const float* x, int n, int Kmax, float* probs, int lane) {
     float m = -INFINITY;
     for (int i = lane; i < n; i += 32) m = fmaxf(m, x[i]);
 #pragma unroll
@@ -681,7 +684,7 @@ k_policy(int B, int Kmax, const int* __restrict__ nK, const float* __restrict__ 
     float best = -1.f; int bi = 0x7fffffff;
     for (int i = lane; i < Kmax; i += 32) {
         const float p = i < n ? expf(x[i] - m) * inv : 0.f;
-        if (probs) probs[(int64_t)b * Kmax + i] = p;
+        if (probs) probs[i] = p;
         if (i < n && p > best) { best = p; bi = i; }
     }
 #pragma unroll
@@ -690,6 +693,16 @@ k_policy(int B, int Kmax, const int* __restrict__ nK, const float* __restrict__ 
         const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
         if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
     }
+    return bi;
+}
+
+__global__ void __launch_bounds__(128)
+k_policy(int B, int Kmax, const int* __restrict__ nK, const float* __restrict__ logits,
+         float* __restrict__ probs, int* __restrict__ action) {
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= B) return;
+    const int bi = policy_warp(logits + (int64_t)b * Kmax, nK[b], Kmax, probs ? probs + (int64_t)b * Kmax : nullptr, lane);
     if (lane == 0 && action) action[b] = bi;
 }
 

@@ -46,7 +46,7 @@ constexpr int TC_W_F4 = (TC_N1 + TC_N2 + TC_N3) * TC_KC;          // float4 per 
 constexpr int TC_GROUPS = 2;                     // independent 128-thread tile pipelines per CTA (they share the weight images)
 constexpr int TC_TPB = TC_GROUPS * TC_ROWS;
 constexpr size_t TC_GROUP_BYTES = (size_t)2 * TC_KC * TC_ROWS * 16 + (size_t)TC_ROWS * H * 4 + 32;   // operands hi/lo, stage, 2 mbarriers
-constexpr size_t TC_SMEM_BYTES = (size_t)2 * TC_W_F4 * 16 + 832 + 16 + TC_GROUPS * TC_GROUP_BYTES;   // 208 floats: biases + Wm[0:3]
+constexpr size_t TC_SMEM_BYTES = (size_t)2 * TC_W_F4 * 16 + 832 + 16 + TC_GROUPS * TC_GROUP_BYTES;   // 208 floats: biases (140 used)
 
 __device__ __forceinline__ uint64_t tc_desc(const void* p, uint32_t lbo_bytes) {
     // K-major, no swizzle: 8 rows x 16 B core matrices, rows 16 B apart; SBO (next 8 rows) = 128 B, LBO (next
@@ -146,12 +146,16 @@ __device__ __forceinline__ void tc_stage_weights(float4* w_hi, float4* w_lo, int
 // decision b is [util(b,e), cap(e)/maxCap, on_path(b,k,e) ? bw(b)/cap(e) : 0, 0 x 17] (mark_action_sp + get_graph_features,
 // environment16.py:711-725, script_eval_on_single_topology.py:131-160), so both the tile's own rows and the operand
 // rows its gather needs are rebuilt from three small L1/L2-resident tables and one bit mask per candidate instead
-// of being written by a feature kernel (160 B per row) and read back (80 B per row + 80 B per pair).
+// of being written by a feature kernel (160 B per row) and read back (80 B per row + 80 B per pair).  The message
+// operand A_0 of a row takes one of two values per (decision, link) -- marked or not -- so those are tabulated
+// (`ptab`, 160 B per link and decision instead of 80 B per link, candidate and decision) and the gather reads the one
+// the mask bit selects.
 struct FeatSrc {
     const float* util;        // [B][E]   fp32(load / cap)
     const float* bwcap;       // [B][E]   fp32(bw / cap)
     const float* capf;        // [E]      fp32(cap / maxCap)
     const uint32_t* mask;     // [B][Kmax][W] bit e = link e is on path(s, mid_k) U path(mid_k, d)
+    const float* ptab;        // [B][E][2][20] A_0 of link e of decision b, unmarked / marked
     int W, Kmax;
 };
 __device__ __forceinline__ void tc_feature_row(const FeatSrc& f, const IdxTopo& idx, int64_t r, float& f0, float& f1, float& f2) {
@@ -188,7 +192,6 @@ k_mp_tc(const IDX idx, const float* __restrict__ wflat, const float* __restrict_
     float4* w3_hi = w2_lo + TC_KC * TC_N2;
     float4* w3_lo = w3_hi + TC_KC * TC_N3;
     float* sbias = reinterpret_cast<float*>(w3_lo + TC_KC * TC_N3);            // msg bias [20] | gru bias [2][60]
-    float* swm3 = sbias + 144;                                                 // Wm[0:3][0:20]: first message operand of a feature row
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(sbias + 208);
     const int g = threadIdx.x / TC_ROWS, t = threadIdx.x - g * TC_ROWS, wg = t >> 5;      // group, row in tile, warp in group
     unsigned char* gbase = reinterpret_cast<unsigned char*>(s_tmem + 4) + (size_t)g * TC_GROUP_BYTES;
@@ -211,7 +214,6 @@ k_mp_tc(const IDX idx, const float* __restrict__ wflat, const float* __restrict_
     tc_stage_weights(w2_hi, w2_lo, TC_N2, [&](int k, int n) { return (k >= H || n >= 60) ? 0.f : wflat[W_GRU_K + k * 60 + n]; });
     tc_stage_weights(w3_hi, w3_lo, TC_N3, [&](int k, int n) { return (k >= H || n >= H) ? 0.f : wflat[W_MSG_K + k * H + n]; });
     for (int i = threadIdx.x; i < 140; i += TC_TPB) sbias[i] = i < H ? wflat[W_MSG_B + i] : wflat[W_GRU_B + i - H];
-    for (int i = threadIdx.x; i < 3 * H; i += TC_TPB) swm3[i] = wflat[W_MSG_K + i];
     a_hi[5 * TC_ROWS + t] = make_float4(0.f, 0.f, 0.f, 0.f);                   // k = 20..23: never written again
     a_lo[5 * TC_ROWS + t] = make_float4(0.f, 0.f, 0.f, 0.f);
     fence_proxy_async();
@@ -291,12 +293,31 @@ k_mp_tc(const IDX idx, const float* __restrict__ wflat, const float* __restrict_
         for (int j = 0; j < H / 2; ++j) { t2[j] = pack2(B[2 * j] + sbias[2 * j], B[2 * j + 1] + sbias[2 * j + 1]); agg2[j] = 0ull; }
         // ---- agg = sum over incoming pairs (ascending pair index) of selu(A[first] + B); two operand rows in flight
         if (FUSED0) {
-            for (int p = cur.pb; p < cur.pe; ++p) {
-                float f0 = 0.f, f1 = 0.f, f2 = 0.f, a[H];
-                if constexpr (FUSED0) tc_feature_row(feat, idx, (int64_t)cur.list[p] + cur.add, f0, f1, f2);
-#pragma unroll
-                for (int j = 0; j < H; ++j) a[j] = fmaf(f2, swm3[2 * H + j], fmaf(f1, swm3[H + j], fmaf(f0, swm3[j], 0.f)));   // = k_features' A_0
-                mp_accumulate<ACC>(agg2, a, t2);
+            if constexpr (FUSED0) {
+                // source row = link e of candidate k of the row's own decision: A_0 from the decision's table
+                const float* ptab = feat.ptab + (size_t)cur.b * idx.E * (2 * H);
+                const uint32_t* mrow = feat.mask + (size_t)cur.b * feat.Kmax * feat.W;
+                const bool aligned = idx.off_f == idx.E;            // (else the old_cummax quirk moves sources across graphs)
+                const unsigned k0 = aligned ? cur.base / (unsigned)idx.E : 0u;
+                auto src = [&](int p) {
+                    unsigned k = k0, e = (unsigned)cur.list[p];
+                    if (!aligned) { const unsigned lr = cur.base + e; k = lr / (unsigned)idx.E; e = lr - k * (unsigned)idx.E; }
+                    const uint32_t bit = (mrow[k * feat.W + (e >> 5)] >> (e & 31)) & 1u;
+                    return ptab + (e * 2u + bit) * H;
+                };
+                int p = cur.pb;
+                for (; p + 1 < cur.pe; p += 2) {
+                    float a0[H], a1[H];
+                    const float* s0 = src(p); const float* s1 = src(p + 1);
+                    load_row(a0, s0); load_row(a1, s1);
+                    mp_accumulate<ACC>(agg2, a0, t2);
+                    mp_accumulate<ACC>(agg2, a1, t2);
+                }
+                if (p < cur.pe) {
+                    float a0[H];
+                    load_row(a0, src(p));
+                    mp_accumulate<ACC>(agg2, a0, t2);
+                }
             }
         } else {
             // two operand rows in flight.  Tried and dropped at the 128-register budget of two CTAs per SM: resolving the

@@ -403,3 +403,42 @@ def test_caller_stream_and_engines_agree(ctx, weights, tmp_path_factory):
         assert np.array_equal(out["tc"][3], out["ffma"][3]) and np.array_equal(out["tc"][2], out["ffma"][2])
     finally:
         ctx.engine = before
+
+
+def test_decision_tail_variants_identical(weights, tmp_path_factory, monkeypatch):
+    """The tail of a decision runs either as one launch (k_decision_finish: read-out + soft-max + arg-max + Env16.step,
+    picked below 512 decisions in flight) or as k_readout + k_policy + k_env_step (picked above): same arithmetic, so
+    logits, probabilities, greedy histories and best routings must be bit-identical, whichever the batch size picks."""
+    from enero_b200.runtime import Context
+    from enero_b200.engine import EpisodeBatch
+    from enero_b200 import datasets as ds
+    case, topo, _ = _topos("tiny12", tmp_path_factory)
+    gf = case_graph_file(case, tmp_path_factory.mktemp("tail"))
+    sigma = ds.sigma_for_mean_utilisation(gf)
+    B = 24
+    tms = np.stack([ds.uniform_tm(gf.num_nodes, sigma, 300 + j) for j in range(B)])
+    got = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("ENERO_FUSED_TAIL", mode)
+        c = Context(0)
+        try:
+            c.upload_weights(0, [weights[k] for k in orc.WEIGHT_NAMES])
+            eb = EpisodeBatch(c, topo, B)
+            eb.reset(tms)
+            st = eb.state()
+            dec = c.decide_batch(topo, st["loads"], st["cur"], st["bw"])
+            eb.run_greedy()
+            got[mode] = (dec, eb.history(), eb.best_arrays(), eb.state())
+            eb.close()
+        finally:
+            c.close()
+    monkeypatch.delenv("ENERO_FUSED_TAIL")
+    d0, h0, b0, s0 = got["0"]
+    d1, h1, b1, s1 = got["1"]
+    for a, b in zip(d0, d1):
+        assert np.array_equal(a, b)
+    for a, b in zip(h0 + b0, h1 + b1):
+        assert np.array_equal(a, b)
+    for k in s0:
+        assert np.array_equal(s0[k], s1[k]), k
+    assert int(s0["steps"].sum()) > B
