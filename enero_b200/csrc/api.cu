@@ -145,7 +145,7 @@ extern "C" int enero_ctx_sync(enero_ctx* c) {
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return ENERO_OK;
 }
-extern "C" int64_t enero_ctx_launch_count(enero_ctx* c) { return c ? c->launches : -1; }
+extern "C" int64_t enero_ctx_launch_count(enero_ctx* c) { return c ? c->launches.load() : (int64_t)-1; }
 extern "C" void* enero_ctx_stream(enero_ctx* c) { return c ? (void*)c->stream : nullptr; }
 extern "C" int enero_ctx_set_stream(enero_ctx* c, void* stream) {
     if (!c) return fail(ENERO_ERR_INVALID, "enero_ctx_set_stream: null ctx");

@@ -3,7 +3,12 @@
 #include <cuda_runtime.h>
 #include <nvtx3/nvToolsExt.h>
 
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -62,14 +67,61 @@ struct TrainGroup {                          // the samples of one topology in t
 };
 constexpr int TRAIN_GROUPS = 3;
 
+// One helper thread per ctx that enqueues the critic lane of a training group while the calling thread enqueues the
+// actor lane: an Adam step is ~175 small launches, and the host's 5.5 us per launch (0.96 ms) was level with the GPU's
+// time per step.  run() hands a job over, wait() returns its status (and the error text, which is thread local).
+struct LaneWorker {
+    std::thread th;
+    std::mutex m;
+    std::condition_variable cv;
+    std::function<int()> job;
+    bool has_job = false, finished = true, stop = false;
+    int rc = 0;
+    std::string err;
+    explicit LaneWorker(int device) {
+        th = std::thread([this, device] {
+            cudaSetDevice(device);
+            std::unique_lock<std::mutex> lk(m);
+            for (;;) {
+                cv.wait(lk, [this] { return has_job || stop; });
+                if (stop) return;
+                std::function<int()> f = std::move(job);
+                has_job = false;
+                lk.unlock();
+                const int r = f();
+                const std::string e = r ? enero_last_error() : "";
+                lk.lock();
+                rc = r; err = e; finished = true;
+                cv.notify_all();
+            }
+        });
+    }
+    void run(std::function<int()> f) {
+        std::lock_guard<std::mutex> lk(m);
+        job = std::move(f); has_job = true; finished = false;
+        cv.notify_all();
+    }
+    int wait() {
+        std::unique_lock<std::mutex> lk(m);
+        cv.wait(lk, [this] { return finished; });
+        if (rc) enero_set_error(err);
+        return rc;
+    }
+    ~LaneWorker() {
+        { std::lock_guard<std::mutex> lk(m); stop = true; cv.notify_all(); }
+        if (th.joinable()) th.join();
+    }
+};
+
 struct enero_ctx {
     int device = 0;
     int num_sms = 0;
     cudaStream_t stream = nullptr;           // stream every launch / copy of this ctx goes to (enero_ctx_set_stream)
     cudaStream_t own_stream = nullptr;       // the non-blocking stream the ctx created for itself
     float* w[2] = {nullptr, nullptr};
-    int64_t launches = 0;
+    std::atomic<int64_t> launches{0};         // (the two lanes of a training group are enqueued from two host threads)
     // scratch of the GNN engine
+    LaneWorker* lane_worker = nullptr;       // created with the lanes unless ENERO_TRAIN_THREADS=0
     DevBuf bwcap, marks, ptab;                      // tables of the fused first iteration (k_decision_tables)
     int tail_mode = -1;                      // decision tail: 1 = k_decision_finish, 0 = k_readout + k_policy + k_env_step, -1 = by batch
                                              // size (ENERO_FUSED_TAIL=0/1 forces one; measured cross-over in DESIGN.md)

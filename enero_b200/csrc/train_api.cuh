@@ -37,6 +37,8 @@ int ensure_lanes(enero_ctx* c) {
             CUDA_TRY(cudaMalloc(&L.tile_ctr, 16 * sizeof(int)));
         }
     }
+    const char* e = std::getenv("ENERO_TRAIN_THREADS");
+    if (!(e && std::atoi(e) == 0)) c->lane_worker = new LaneWorker(c->device);
     return ENERO_OK;
 }
 
@@ -96,10 +98,10 @@ int train_backward(enero_ctx* c, TrainLane& L, enero_topo* t, const TrainTopo& g
         }
         LAUNCH_CHECK(c);
         WgradIter wi{ht, L.t_agg.as<float>(), L.t_G.as<float>(), L.t_dB.as<float>(), L.t_dA.as<float>()};
-        k_wgrad<<<wg_grid, WG_TPB, 0, st>>>(idx, wi, (rows + WG_ROWS - 1) / WG_ROWS, L.t_partials.as<float>()); LAUNCH_CHECK(c);
-        k_reduce_partials<<<(W_MP_FLOATS + 255) / 256, 256, 0, st>>>(wg_grid, L.t_partials.as<float>(), grad); LAUNCH_CHECK(c);
+        k_wgrad<<<wg_grid, WG_TPB, 0, st>>>(idx, wi, (rows + WG_ROWS - 1) / WG_ROWS, L.t_partials.as<float>(), it < T - 1 ? 1 : 0); LAUNCH_CHECK(c);
         cur ^= 1;
     }
+    k_reduce_partials<<<(W_MP_FLOATS + 255) / 256, 256, 0, st>>>(wg_grid, L.t_partials.as<float>(), grad); LAUNCH_CHECK(c);
     return ENERO_OK;
 }
 
@@ -153,6 +155,8 @@ int join_lanes(enero_ctx* c) {
 }  // namespace
 
 void train_release_lanes(enero_ctx* c) {
+    delete c->lane_worker;
+    c->lane_worker = nullptr;
     if (!c->groups) return;
     for (int g = 0; g < TRAIN_GROUPS; ++g) {
         cudaEventDestroy(c->groups[g].ready);
@@ -342,8 +346,8 @@ static int accumulate_dev(enero_ctx* c, TrainGroup& G, enero_topo* t, int n, con
     TopoView tv = view_of(t);
     TRY(ensure_ones(c, n));
     CUDA_TRY(cudaEventRecord(G.ready, c->stream));               // the group's samples are in place after this point
-    // ---- actor lane: K' candidate graphs per sample
-    {
+    // ---- actor lane: K' candidate graphs per sample (enqueued by the calling thread)
+    auto actor_lane = [&]() -> int {
         TrainLane& L = G.lane[ENERO_ACTOR];
         cudaStream_t st = L.st;
         CUDA_TRY(cudaStreamWaitEvent(st, G.ready, 0));
@@ -366,15 +370,15 @@ static int accumulate_dev(enero_ctx* c, TrainGroup& G, enero_topo* t, int n, con
         k_ppo_actor_head<<<(n + 3) / 4, 128, 0, st>>>(n, Kmax, nK, L.t_logits.as<float>(), action, old_prob, advantage, inv_m,
                                                       entropy_beta, clipping_val, L.t_dlogit.as<float>(), L.t_loss.as<float>(),
                                                       L.t_ent.as<float>()); LAUNCH_CHECK(c);
-        k_sum_into<<<1, 32, 0, st>>>(n, L.t_loss.as<float>(), sums + 0); LAUNCH_CHECK(c);
-        k_sum_into<<<1, 32, 0, st>>>(n, L.t_ent.as<float>(), sums + 1); LAUNCH_CHECK(c);
+        k_sum_into<<<1, 64, 0, st>>>(n, L.t_loss.as<float>(), L.t_ent.as<float>(), sums); LAUNCH_CHECK(c);
         TrainTopo g{n, Kmax, E, RPD, rows, nK};
         TRY(train_backward(c, L, t, g, ENERO_ACTOR, T, L.t_dlogit.as<float>()));
         CUDA_TRY(cudaEventRecord(L.done, st));
         L.busy = true;
-    }
-    // ---- critic lane: one graph per sample, concurrently with the actor lane
-    {
+        return ENERO_OK;
+    };
+    // ---- critic lane: one graph per sample, concurrently with the actor lane (enqueued by the helper thread)
+    auto critic_lane = [&]() -> int {
         TrainLane& L = G.lane[ENERO_CRITIC];
         cudaStream_t st = L.st;
         CUDA_TRY(cudaStreamWaitEvent(st, G.ready, 0));
@@ -393,11 +397,22 @@ static int accumulate_dev(enero_ctx* c, TrainGroup& G, enero_topo* t, int n, con
         k_readout<GraphsTopo><<<(n + 3) / 4, 128, 0, st>>>(gr, c->w[ENERO_CRITIC], L.t_h[T].as<float>(), L.t_logits.as<float>()); LAUNCH_CHECK(c);
         k_ppo_critic_head<<<(n + 127) / 128, 128, 0, st>>>(n, L.t_logits.as<float>(), ret, inv_m, L.t_dlogit.as<float>(), L.t_loss.as<float>());
         LAUNCH_CHECK(c);
-        k_sum_into<<<1, 32, 0, st>>>(n, L.t_loss.as<float>(), sums + 0); LAUNCH_CHECK(c);
+        k_sum_into<<<1, 32, 0, st>>>(n, L.t_loss.as<float>(), nullptr, sums); LAUNCH_CHECK(c);
         TrainTopo g{n, 1, E, E, rows, ones};
         TRY(train_backward(c, L, t, g, ENERO_CRITIC, T, L.t_dlogit.as<float>()));
         CUDA_TRY(cudaEventRecord(L.done, st));
         L.busy = true;
+        return ENERO_OK;
+    };
+    if (c->lane_worker) {
+        c->lane_worker->run(critic_lane);
+        const int ra = actor_lane();
+        const int rc = c->lane_worker->wait();                   // always collected: the job refers to this frame
+        if (ra != ENERO_OK) return ra;
+        if (rc != ENERO_OK) return rc;
+    } else {
+        TRY(actor_lane());
+        TRY(critic_lane());
     }
     // no synchronisation: H2D copies from pageable host memory have left the caller's buffers when
     // cudaMemcpyAsync returns, and the device staging buffers are reused in stream order

@@ -315,7 +315,7 @@ k_readout_bwd(const GraphsTopo gr, const float* __restrict__ wflat, const float*
 
 // readout weight gradients: thread o owns output o of the 861 readout parameters and walks the graphs in ascending
 // order (deterministic), reading the per-graph vectors V = [g | a1 | a2 | dp1 | dp2 | dy] straight from global memory
-// (warp-uniform or warp-contiguous addresses); four graphs in flight.  The previous version (32 graphs per CTA with two
+// (warp-uniform or warp-contiguous addresses).  The previous version (32 graphs per CTA with two
 // block barriers each, partial vectors, a second reduction kernel) took 107 us per call -- 15 % of a PPO update.
 constexpr int RW_NOUT = W_R3_B + 1 - W_R1_K;     // 861
 __global__ void __launch_bounds__(128)
@@ -329,12 +329,25 @@ k_readout_wgrad(int n_graphs, int Kmax, const int* __restrict__ nK, const float*
     else if (o < 840) { ia = 4 * H + o - 820; ib = -1; }                          // db2
     else if (o < 860) { ia = 2 * H + o - 840; ib = 5 * H; }                       // dR3 = a2[k] * dy
     else { ia = 5 * H; ib = -1; }                                                 // db3
+    // eight graphs in flight: the loads and products are independent, only the adds are ordered; a padded graph
+    // (k >= nK) contributes an exact zero
     float acc = 0.f;
-    for (int g = 0; g < n_graphs; ++g) {
-        const int b = g / Kmax, k = g - b * Kmax;
-        if (k >= nK[b]) continue;
-        const float* v = V + (int64_t)g * 6 * H;
-        acc += ib >= 0 ? v[ia] * v[ib] : v[ia];
+    const int ib2 = ib >= 0 ? ib : ia;
+    for (int g0 = 0; g0 < n_graphs; g0 += 8) {
+        float term[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int g = g0 + i;
+            term[i] = 0.f;
+            if (g < n_graphs) {
+                const int b = g / Kmax, k = g - b * Kmax;
+                const float* v = V + (int64_t)g * 6 * H;
+                const float x = v[ia], y = v[ib2];
+                if (k < nK[b]) term[i] = ib >= 0 ? x * y : x;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc += term[i];
     }
     grad_out[o] += acc;
 }
@@ -362,7 +375,7 @@ __device__ __forceinline__ void wgrad_cols(int o, int& xc, int& dc) {
 // broadcast) and one float4 of D and issues 24 FMAs.  The previous version looked its 14 scattered
 // (x, d) pairs up in shared memory row by row (2 LDS per FMA) and took 36 % of the PPO step.
 __global__ void __launch_bounds__(WG_TPB)
-k_wgrad(const IdxTopo idx, const WgradIter it, int64_t ntiles, float* __restrict__ partials) {
+k_wgrad(const IdxTopo idx, const WgradIter it, int64_t ntiles, float* __restrict__ partials, int accumulate) {
     __shared__ __align__(16) float sx[WG_ROWS * WG_XP];
     __shared__ __align__(16) float sd[WG_ROWS * WG_DP];
     __shared__ unsigned char s_ok[WG_ROWS];
@@ -377,20 +390,37 @@ k_wgrad(const IdxTopo idx, const WgradIter it, int64_t ntiles, float* __restrict
         __syncthreads();
         if (threadIdx.x < WG_ROWS) s_ok[threadIdx.x] = idx.valid(r0 + threadIdx.x) ? 1 : 0;
         __syncthreads();
-        for (int i = threadIdx.x; i < WG_ROWS * (WG_XP + WG_DP); i += WG_TPB) {
-            const int row = i / (WG_XP + WG_DP), c = i - row * (WG_XP + WG_DP);
+        // stage the tile: 40 float4 per row (h 5 | agg 5 | G 20 | dB 5 | dA 5), ten per thread, all requested before the
+        // first is stored (a scalar element loop exposed one load latency per element: 105 us per launch, half of a
+        // backward pass)
+        constexpr int WG_V4 = 40, WG_LD = WG_ROWS * WG_V4 / WG_TPB;
+        float4 v[WG_LD];
+#pragma unroll
+        for (int u = 0; u < WG_LD; ++u) {
+            const int i = threadIdx.x + u * WG_TPB;
+            const int row = i / WG_V4, q = i - row * WG_V4;
             const int64_t r = r0 + row;
-            float v = 0.f;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (s_ok[row]) {
-                if (c < 20) v = it.h[r * H + c];
-                else if (c < 40) v = it.agg[r * H + c - 20];
-                else if (c == 40) v = 1.f;
-                else if (c < WG_XP) v = 0.f;
-                else if (c < WG_XP + 80) v = it.G[r * 4 * H + c - WG_XP];
-                else if (c < WG_XP + 100) v = it.dB[r * H + c - WG_XP - 80];
-                else if (c < WG_XP + 120) v = it.dA[r * H + c - WG_XP - 100];
+                const float* src = q < 5 ? it.h + r * H + 4 * q : q < 10 ? it.agg + r * H + 4 * (q - 5)
+                                 : q < 30 ? it.G + r * 4 * H + 4 * (q - 10) : q < 35 ? it.dB + r * H + 4 * (q - 30)
+                                 : it.dA + r * H + 4 * (q - 35);
+                v[u] = *reinterpret_cast<const float4*>(src);
             }
-            if (c < WG_XP) sx[row * WG_XP + c] = v; else sd[row * WG_DP + c - WG_XP] = v;
+        }
+#pragma unroll
+        for (int u = 0; u < WG_LD; ++u) {
+            const int i = threadIdx.x + u * WG_TPB;
+            const int row = i / WG_V4, q = i - row * WG_V4;
+            float* dst = q < 10 ? sx + row * WG_XP + 4 * q : sd + row * WG_DP + 4 * (q - 10);
+            *reinterpret_cast<float4*>(dst) = v[u];
+        }
+        if (threadIdx.x < WG_ROWS) {                      // the constant column of X, the padding of X and D
+            const int row = threadIdx.x;
+            *reinterpret_cast<float4*>(sx + row * WG_XP + 40) = make_float4(s_ok[row] ? 1.f : 0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(sx + row * WG_XP + 44) = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(sd + row * WG_DP + 120) = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(sd + row * WG_DP + 124) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         __syncthreads();
 #pragma unroll 4
@@ -406,10 +436,16 @@ k_wgrad(const IdxTopo idx, const WgradIter it, int64_t ntiles, float* __restrict
             }
         }
     }
+    // the CTA's slot collects the iterations of one backward pass (same grid every iteration, newest iteration first);
+    // k_reduce_partials runs once per pass
     float* out = partials + (int64_t)blockIdx.x * WG_PART;
 #pragma unroll
-    for (int i = 0; i < 6; ++i)
-        *reinterpret_cast<float4*>(out + (6 * xg + i) * WG_DP + 4 * dg) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    for (int i = 0; i < 6; ++i) {
+        float4* o4 = reinterpret_cast<float4*>(out + (6 * xg + i) * WG_DP + 4 * dg);
+        float4 v = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        if (accumulate) { const float4 p = *o4; v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w; }
+        *o4 = v;
+    }
 }
 
 // grad[o] += sum over CTAs (ascending) of the (x, d) entry of parameter o
@@ -488,11 +524,14 @@ __global__ void k_ppo_critic_head(int n, const float* __restrict__ value, const 
 }
 
 // dst += sum(x[0..n)) in a fixed order (one warp: lane-strided partial sums, then the shuffle tree)
-__global__ void k_sum_into(int n, const float* __restrict__ x, float* __restrict__ dst) {
+// (warp w of the CTA: dst[w] += sum(x_w); x1 may be null with a one-warp launch)
+__global__ void k_sum_into(int n, const float* __restrict__ x0, const float* __restrict__ x1, float* __restrict__ dst) {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* x = w ? x1 : x0;
     float s = 0.f;
-    for (int i = threadIdx.x; i < n; i += 32) s += x[i];
+    for (int i = lane; i < n; i += 32) s += x[i];
     s = warp_sum(s);
-    if (threadIdx.x == 0) *dst += s;
+    if (lane == 0) dst[w] += s;
 }
 
 // ---- clip_by_global_norm + Adam for both models (single CTA) ----------------------------------------------------
