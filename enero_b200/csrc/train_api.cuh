@@ -73,7 +73,7 @@ int train_backward(enero_ctx* c, TrainLane& L, enero_topo* t, const TrainTopo& g
     const float* w = c->w[which];
     k_readout_bwd<<<(n_graphs + 3) / 4, 128, 0, st>>>(gr, w, L.t_h[T].as<float>(), dlogit, L.t_dh[0].as<float>(), L.t_V.as<float>());
     LAUNCH_CHECK(c);
-    k_readout_wgrad<<<(RW_NOUT + 127) / 128, 128, 0, st>>>(n_graphs, g.Kmax, g.nK, L.t_V.as<float>(), grad + W_R1_K); LAUNCH_CHECK(c);
+    k_readout_wgrad<<<(RW_NOUT + RW_OUT_PER_CTA - 1) / RW_OUT_PER_CTA, RW_TPB, 0, st>>>(n_graphs, g.Kmax, g.nK, L.t_V.as<float>(), grad + W_R1_K); LAUNCH_CHECK(c);
     const int bgrid = (int)((rows + BW_TPB - 1) / BW_TPB);
     int cur = 0;
     for (int it = T - 1; it >= 0; --it) {

@@ -313,31 +313,32 @@ k_readout_bwd(const GraphsTopo gr, const float* __restrict__ wflat, const float*
     }
 }
 
-// readout weight gradients: thread o owns output o of the 861 readout parameters and walks the graphs in ascending
-// order (deterministic), reading the per-graph vectors V = [g | a1 | a2 | dp1 | dp2 | dy] straight from global memory
-// (warp-uniform or warp-contiguous addresses).  The previous version (32 graphs per CTA with two
-// block barriers each, partial vectors, a second reduction kernel) took 107 us per call -- 15 % of a PPO update.
+// readout weight gradients: eight threads share output o of the 861 readout parameters; thread s of the eight walks
+// the graphs g = s, s + 8, ... in ascending order (four in flight) reading the per-graph vectors V = [g | a1 | a2 | dp1 |
+// dp2 | dy] straight from global memory, and the eight partial sums meet in a fixed shuffle tree (deterministic).  A
+// padded graph (k >= nK) contributes an exact zero.  History: 32 graphs per CTA with two block barriers each, partial
+// vectors and a second reduction kernel took 107 us per call; one thread per output still 160 us for an actor lane
+// (400 dependent iterations on seven CTAs).
 constexpr int RW_NOUT = W_R3_B + 1 - W_R1_K;     // 861
-__global__ void __launch_bounds__(128)
+constexpr int RW_TPB = 128, RW_SPLIT = 8, RW_OUT_PER_CTA = RW_TPB / RW_SPLIT;
+__global__ void __launch_bounds__(RW_TPB)
 k_readout_wgrad(int n_graphs, int Kmax, const int* __restrict__ nK, const float* __restrict__ V, float* __restrict__ grad_out) {
-    const int o = blockIdx.x * blockDim.x + threadIdx.x;
-    if (o >= RW_NOUT) return;
-    int ia, ib;                                   // value = V[ia] * V[ib]  (ib < 0: V[ia] alone)
+    const int o = blockIdx.x * RW_OUT_PER_CTA + (threadIdx.x / RW_SPLIT), sl = threadIdx.x % RW_SPLIT;
+    const bool live = o < RW_NOUT;
+    int ia = 0, ib = -1;                          // value = V[ia] * V[ib]  (ib < 0: V[ia] alone)
     if (o < 400) { ia = o / H; ib = 3 * H + o % H; }                              // dR1[k][j] = g[k] * dp1[j]
     else if (o < 420) { ia = 3 * H + o - 400; ib = -1; }                          // db1
     else if (o < 820) { ia = H + (o - 420) / H; ib = 4 * H + (o - 420) % H; }     // dR2 = a1[k] * dp2[j]
     else if (o < 840) { ia = 4 * H + o - 820; ib = -1; }                          // db2
     else if (o < 860) { ia = 2 * H + o - 840; ib = 5 * H; }                       // dR3 = a2[k] * dy
-    else { ia = 5 * H; ib = -1; }                                                 // db3
-    // eight graphs in flight: the loads and products are independent, only the adds are ordered; a padded graph
-    // (k >= nK) contributes an exact zero
-    float acc = 0.f;
+    else if (live) { ia = 5 * H; ib = -1; }                                       // db3
     const int ib2 = ib >= 0 ? ib : ia;
-    for (int g0 = 0; g0 < n_graphs; g0 += 8) {
-        float term[8];
+    float acc = 0.f;
+    for (int g0 = sl; g0 < n_graphs && live; g0 += 4 * RW_SPLIT) {
+        float term[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int g = g0 + i;
+        for (int i = 0; i < 4; ++i) {
+            const int g = g0 + i * RW_SPLIT;
             term[i] = 0.f;
             if (g < n_graphs) {
                 const int b = g / Kmax, k = g - b * Kmax;
@@ -347,9 +348,11 @@ k_readout_wgrad(int n_graphs, int Kmax, const int* __restrict__ nK, const float*
             }
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc += term[i];
+        for (int i = 0; i < 4; ++i) acc += term[i];
     }
-    grad_out[o] += acc;
+#pragma unroll
+    for (int d = RW_SPLIT / 2; d > 0; d >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, d, RW_SPLIT);
+    if (live && sl == 0) grad_out[o] += acc;
 }
 
 // ---- message / GRU weight gradients -----------------------------------------------------------------------------
