@@ -243,8 +243,11 @@ def _ncu_traffic(B, engine):
             continue
         rows = {r[0]: r for r in csv.reader(open(prof)) if r}
         try:
-            mb = float(rows["dram__bytes_read.sum"][2]) + float(rows["dram__bytes_write.sum"][2])
-            return mb * 1e6 * B / 1024.0, rel + " (dram__bytes_read.sum + dram__bytes_write.sum, launch 1, x B/1024)"
+            unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            rd = [float(x) * unit[rows["dram__bytes_read.sum"][1]] for x in rows["dram__bytes_read.sum"][2:] if x]
+            wr = [float(x) * unit[rows["dram__bytes_write.sum"][1]] for x in rows["dram__bytes_write.sum"][2:] if x]
+            mb = (sum(rd) + sum(wr)) / len(rd) / 1e6
+            return mb * 1e6 * B / 1024.0, rel + " (dram__bytes_read.sum + dram__bytes_write.sum, mean of the %d launches captured, x B/1024)" % len(rd)
         except Exception:
             continue
     return None, None
@@ -352,7 +355,7 @@ def run_ours(args, rank, world, local_rank):
                   "note": "the tensor pipe is not the limit (ncu: 16 % active); gather / gate latency and instruction issue are"}
     roofline = {
         "bound": "fp32",
-        "kernel": ("k_mp_tc<IdxTopo> (tcgen05 3xTF32; 5 launches per decision step, ~92 % of it)" if tc
+        "kernel": ("k_mp_tc<IdxTopo> (tcgen05 3xTF32; 5 launches per decision step, ~97 % of its kernel time)" if tc
                    else "k_mp_iter<IdxTopo> (5 launches per decision step, ~94 % of it)"),
         "engine": ctx.engine, "tensor": tensor,
         "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak if fp32_peak else None,
