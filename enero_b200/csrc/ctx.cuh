@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <nvtx3/nvToolsExt.h>
 
+#include <algorithm>
 #include <atomic>
 #include <condition_variable>
 #include <functional>
@@ -26,6 +27,17 @@
 
 static inline int fail(int code, const std::string& m) { enero_set_error(m); return code; }
 
+// Growth head-room of DevBuf::ensure on this thread.  A re-allocation is a cudaFree (device-wide synchronisation) plus a
+// cudaMalloc, ~1.5 ms each: the ~30 scratch buffers of a training lane re-allocating because a minibatch holds a few
+// more samples of a topology than any before stalled single PPO updates by 80 ms .. seconds.  The training path
+// reserves for the largest share of the minibatch it can expect (ReserveScope) so the buffers settle at the first step.
+inline double& devbuf_reserve() { static thread_local double r = 1.0; return r; }
+struct ReserveScope {
+    double prev;
+    explicit ReserveScope(double r) : prev(devbuf_reserve()) { devbuf_reserve() = r; }
+    ~ReserveScope() { devbuf_reserve() = prev; }
+};
+
 struct DevBuf {
     void* p = nullptr; size_t cap = 0;
     int ensure(size_t bytes) {
@@ -33,6 +45,7 @@ struct DevBuf {
         if (p) cudaFree(p);
         p = nullptr; cap = 0;
         size_t want = bytes + bytes / 4 + 256;
+        want = std::max(want, (size_t)((double)bytes * devbuf_reserve()) + 256);
         cudaError_t e = cudaMalloc(&p, want);
         if (e != cudaSuccess) { enero_set_error(std::string("cudaMalloc: ") + cudaGetErrorString(e)); return ENERO_ERR_CUDA; }
         cap = want;

@@ -215,6 +215,7 @@ static int acquire_group(enero_ctx* c, TrainGroup** out) {
     return ENERO_OK;
 }
 static int ensure_group_inputs(TrainGroup& G, int n, int E) {
+    ReserveScope rs(2.0);
     TRY(G.t_loads.ensure((size_t)n * E * 8)); TRY(G.t_sd.ensure((size_t)n * 8)); TRY(G.t_bw.ensure((size_t)n * 8));
     TRY(G.t_action.ensure((size_t)n * 4)); TRY(G.t_oldp.ensure((size_t)n * 4)); TRY(G.t_adv.ensure((size_t)n * 4));
     TRY(G.t_ret.ensure((size_t)n * 4));
@@ -347,7 +348,11 @@ static int accumulate_dev(enero_ctx* c, TrainGroup& G, enero_topo* t, int n, con
     TRY(ensure_ones(c, n));
     CUDA_TRY(cudaEventRecord(G.ready, c->stream));               // the group's samples are in place after this point
     // ---- actor lane: K' candidate graphs per sample (enqueued by the calling thread)
+    // scratch sized for up to twice this share of the minibatch (never more than the whole minibatch)
+    const int m_all = inv_m > 0.f ? std::max(n, (int)std::lround(1.0 / inv_m)) : n;
+    const double reserve = (double)std::min(m_all, 2 * n) / n;
     auto actor_lane = [&]() -> int {
+        ReserveScope rs(reserve);
         TrainLane& L = G.lane[ENERO_ACTOR];
         cudaStream_t st = L.st;
         CUDA_TRY(cudaStreamWaitEvent(st, G.ready, 0));
@@ -379,6 +384,7 @@ static int accumulate_dev(enero_ctx* c, TrainGroup& G, enero_topo* t, int n, con
     };
     // ---- critic lane: one graph per sample, concurrently with the actor lane (enqueued by the helper thread)
     auto critic_lane = [&]() -> int {
+        ReserveScope rs(reserve);
         TrainLane& L = G.lane[ENERO_CRITIC];
         cudaStream_t st = L.st;
         CUDA_TRY(cudaStreamWaitEvent(st, G.ready, 0));

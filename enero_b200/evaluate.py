@@ -47,11 +47,14 @@ def evaluate_tms(ctx: Context, topo: Topology, tms, percentage_demands: float = 
     out["ls_moves"] = np.zeros(n, dtype=np.int64)
     out["drl_steps"] = [None] * n
     out["ls_steps"] = [None] * n
-    for b0 in range(0, n, batch):
-        chunk = tms[b0:b0 + batch]
-        B = chunk.shape[0]
-        eb = EpisodeBatch(ctx, topo, B, percentage_demands)
-        try:
+    batches = {}                                  # one device-resident batch per chunk size, reused by every chunk
+    try:
+        for b0 in range(0, n, batch):
+            chunk = tms[b0:b0 + batch]
+            B = chunk.shape[0]
+            if B not in batches:
+                batches[B] = EpisodeBatch(ctx, topo, B, percentage_demands)
+            eb = batches[B]
             t0 = tt.perf_counter()
             eb.reset(chunk)
             eb.run_greedy()
@@ -80,7 +83,8 @@ def evaluate_tms(ctx: Context, topo: Topology, tms, percentage_demands: float = 
                 t4 = tt.perf_counter()
                 out["sap"][sl] = eb.sap(None)
                 out["cost_sap"][sl] = (tt.perf_counter() - t4) / B
-        finally:
+    finally:
+        for eb in batches.values():
             eb.close()
     return out
 

@@ -73,6 +73,9 @@ def allreduce_sum_(tensor, group=None):
 
 def max_over_ranks(value, device=None, group=None):
     """max of a python float over ranks (device timings are reported as the slowest rank's)"""
+    import sys
+    if "torch" not in sys.modules:                  # no torch, no process group: a single rank
+        return float(value)
     import torch
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
@@ -84,6 +87,9 @@ def max_over_ranks(value, device=None, group=None):
 
 def gather_records(records, group=None):
     """rank 0 receives the concatenation of every rank's result records in rank order; others get None"""
+    import sys
+    if "torch" not in sys.modules:
+        return list(records)
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return list(records)
