@@ -84,6 +84,13 @@ class TrainingRun:
         self.training_tm_ids = list(range(100))
         self.rollout_mode = rollout_mode
         self._tm_cache = {}
+        self._eval_tms = {}
+        # rollouts / greedy evaluation of the topologies run side by side: one helper context (stream + scratch) per
+        # topology on the same device, driven from one host thread each -- a batch of 4-6 episodes is bound by launch
+        # latency, not by the GPU (ENERO_ROLLOUT_THREADS=0: one after the other on the training context)
+        self._helpers = None
+        self._pool = None
+        self._use_helpers = os.environ.get("ENERO_ROLLOUT_THREADS", "1") != "0"
         self.checkpoint_actor = Checkpoint(model=self.agent.actor, optimizer=self.agent.optimizer)
         self.checkpoint_critic = Checkpoint(model=self.agent.critic, optimizer=self.agent.optimizer)
         random.seed(SEED)
@@ -156,6 +163,43 @@ class TrainingRun:
                                                                      % (env.graph_topology_name, tm_id)), env.numNodes)
         return self._tm_cache[key]
 
+    def _side_contexts(self, n):
+        """n contexts holding the agent's current weights (None when running on the training context alone)"""
+        self.agent._bind()
+        if not self._use_helpers or n < 2:
+            return None
+        from .runtime import Context
+        from concurrent.futures import ThreadPoolExecutor
+        if self._helpers is None:
+            self._helpers = []
+        while len(self._helpers) < n:
+            h = Context(self.ctx.device)
+            h.math, h.engine = self.ctx.math, self.ctx.engine
+            self._helpers.append(h)
+        if self._pool is None:
+            self._pool = ThreadPoolExecutor(max_workers=8)
+        self.ctx.sync()
+        for which in (0, 1):
+            w = self.ctx.download_weights(which)
+            for h in self._helpers[:n]:
+                h.upload_weights(which, w)
+        return self._helpers[:n]
+
+    def _map_topologies(self, fn, items):
+        """fn(context, item) for every item, concurrently on the helper contexts when there are any"""
+        helpers = self._side_contexts(len(items))
+        if helpers is None:
+            return [fn(self.ctx, it) for it in items]
+        return list(self._pool.map(lambda hi: fn(hi[0], hi[1]), zip(helpers, items)))
+
+    def close(self):
+        if self._pool is not None:
+            self._pool.shutdown()
+            self._pool = None
+        for h in self._helpers or []:
+            h.close()
+        self._helpers = None
+
     def collect_device(self):
         """The rollouts of train script :483-625 as device-resident batches: every topology runs `episodes per quota`
         episodes (quota / episode length = 5, 4, 6 with the reference's multipliers) at once through
@@ -181,20 +225,26 @@ class TrainingRun:
             slots = [(i, rounds * per_topo[i] + j) for i in range(len(self.train_envs)) if need[i] for j in range(per_topo[i])]
             mine = slots[rank::world]
             out = {}
-            for i in sorted({s[0] for s in mine}):
+
+            def roll(ctx, i):
                 env = self.train_envs[i]
                 js = [j for (ii, j) in mine if ii == i]
                 tm_ids = [int(np.random.RandomState((SEED, self.counter, i, j)).choice(self.training_tm_ids)) for j in js]
-                eb = EpisodeBatch(self.ctx, env.topology, len(js), self.pct)
+                eb = EpisodeBatch(ctx, env.topology, len(js), self.pct)
                 try:
                     eb.reset(np.stack([self._tm(env, t) for t in tm_ids]))
                     r = eb.rollout(seed=(SEED << 40) ^ (self.counter << 20) ^ (i << 12) ^ js[0])
                 finally:
                     eb.close()
+                res = {}
                 for b, j in enumerate(js):
                     n = int(r["steps"][b])
-                    out[(i, j)] = {k: np.array(r[k][b, :n]) for k in ("loads", "sd", "bw", "action", "prob", "value", "reward")}
-                    out[(i, j)]["last_value"] = float(r["last_value"][b])
+                    res[(i, j)] = {k: np.array(r[k][b, :n]) for k in ("loads", "sd", "bw", "action", "prob", "value", "reward")}
+                    res[(i, j)]["last_value"] = float(r["last_value"][b])
+                return res
+
+            for res in self._map_topologies(roll, sorted({s[0] for s in mine})):
+                out.update(res)
             if world > 1:
                 import torch.distributed as dist
                 gathered = [None] * world
@@ -283,27 +333,34 @@ class TrainingRun:
 
     # ---- greedy evaluation (train script :633-693), batched --------------------------------------------
     def evaluate(self):
-        rewards, max_uti, uti_std = [], [], []
-        self.agent._bind()                       # the batches below run with whatever weights the context holds
-        for env in self.eval_envs:
-            tms = np.stack([ds.parse_demands_file(os.path.join(env.dataset_folder_name, "TM", "%s.%d.demands"
-                                                               % (env.graph_topology_name, t)), env.numNodes)
-                            for t in range(self.eval_episodes)])
-            eb = EpisodeBatch(self.ctx, env.topology, tms.shape[0], self.pct)
+        def greedy(ctx, env):
+            key = id(env)
+            if key not in self._eval_tms:             # the evaluation matrices are fixed: parsed once
+                self._eval_tms[key] = np.stack([ds.parse_demands_file(os.path.join(env.dataset_folder_name, "TM", "%s.%d.demands"
+                                                                                     % (env.graph_topology_name, t)), env.numNodes)
+                                                for t in range(self.eval_episodes)])
+            tms = self._eval_tms[key]
+            eb = EpisodeBatch(ctx, env.topology, tms.shape[0], self.pct)
             try:
                 eb.reset(tms)
                 eb.run_greedy()
                 st = eb.state()
                 _, r, _ = eb.history()
-                for i in range(tms.shape[0]):
-                    rew = 0
-                    for v in r[i, :st["steps"][i]]:     # rewardAddTest += reward, in step order
-                        rew += v
-                    rewards.append(rew)
-                max_uti += list(st["max_uti"])
-                uti_std += [float(np.std(st["loads"][i])) for i in range(tms.shape[0])]
             finally:
                 eb.close()
+            rewards = []
+            for i in range(tms.shape[0]):
+                rew = 0
+                for v in r[i, :st["steps"][i]]:         # rewardAddTest += reward, in step order
+                    rew += v
+                rewards.append(rew)
+            return rewards, list(st["max_uti"]), [float(np.std(st["loads"][i])) for i in range(tms.shape[0])]
+
+        rewards, max_uti, uti_std = [], [], []
+        for a, b, c in self._map_topologies(greedy, list(self.eval_envs)):     # (with whatever weights the agent holds)
+            rewards += a
+            max_uti += b
+            uti_std += c
         return np.array(rewards), np.array(max_uti), np.array(uti_std)
 
     # ---- one PPO episode ---------------------------------------------------------------------------

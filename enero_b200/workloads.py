@@ -113,8 +113,11 @@ def run_cfg4(ctx, ppo_episodes=1, process_group=None, specs=((20, 31, 1003), (23
     decisions (285 / 304 / 246 per topology), GAE, 8 epochs x 16 minibatches of clip + Adam."""
     from .train import TrainingRun
     run = TrainingRun.synthetic(ctx, specs, process_group=process_group)
-    run.ppo_episode()                       # warm-up: first-touch allocations of the training buffers
-    return run.run(1, ppo_episodes)
+    try:
+        run.ppo_episode()                   # warm-up: first-touch allocations of the training buffers
+        return run.run(1, ppo_episodes)
+    finally:
+        run.close()
 
 
 def _main():
