@@ -348,9 +348,10 @@ static int accumulate_dev(enero_ctx* c, TrainGroup& G, enero_topo* t, int n, con
     TRY(ensure_ones(c, n));
     CUDA_TRY(cudaEventRecord(G.ready, c->stream));               // the group's samples are in place after this point
     // ---- actor lane: K' candidate graphs per sample (enqueued by the calling thread)
-    // scratch sized for up to twice this share of the minibatch (never more than the whole minibatch)
+    // scratch sized for up to twice this share of the minibatch, at least 24 samples (a rank of a sharded step sees
+    // small, uneven shares), never more than the whole minibatch
     const int m_all = inv_m > 0.f ? std::max(n, (int)std::lround(1.0 / inv_m)) : n;
-    const double reserve = (double)std::min(m_all, 2 * n) / n;
+    const double reserve = (double)std::min(m_all, std::max(2 * n, 24)) / n;
     auto actor_lane = [&]() -> int {
         ReserveScope rs(reserve);
         TrainLane& L = G.lane[ENERO_ACTOR];
