@@ -117,3 +117,50 @@ def test_training_loop_runs_and_checkpoints(ctx, tmp_path, mode):
                                   np.concatenate([x.reshape(-1) for x in b.adam_slots("m")]))
     st2 = run2.ppo_episode()
     assert os.path.isfile(os.path.join(cdir, "ckpt_ACT-2.index")) and np.isfinite(st2["actor_loss"])
+
+
+def test_evaluate_tms_independent_of_chunking(ctx, tmp_path):
+    """evaluate_tms walks the matrices in chunks on ONE device batch per chunk size (re-used, reset per chunk): the
+    per-TM results do not depend on the chunk size, including a ragged last chunk"""
+    from enero_b200 import datasets as ds
+    from enero_b200.evaluate import evaluate_tms
+    from enero_b200.topology import Topology
+    case = load_case("tiny12")
+    folder = _dataset(case, tmp_path)
+    gf = ds.parse_graph_file(os.path.join(folder, "tiny12.graph"))
+    topo = Topology(gf, K=100)
+    sigma = ds.sigma_for_mean_utilisation(gf)
+    tms = np.stack([ds.uniform_tm(gf.num_nodes, sigma, 700 + j) for j in range(7)])
+    whole = evaluate_tms(ctx, topo, tms, batch=1024)
+    pieces = evaluate_tms(ctx, topo, tms, batch=3)               # chunks of 3, 3, 1
+    for k in ("ospf", "drl", "enero", "decisions", "ls_moves"):
+        assert np.array_equal(whole[k], pieces[k]), k
+    for a, b in zip(whole["drl_steps"] + whole["ls_steps"], pieces["drl_steps"] + pieces["ls_steps"]):
+        assert np.array_equal(a, b)
+    topo.close()
+
+
+def test_rollouts_side_by_side_equal_one_after_the_other(ctx, tmp_path, monkeypatch):
+    """TrainingRun rolls the topologies out on helper contexts from one host thread each; the buffer (Philox streams
+    keyed by seed / episode / topology / slot) and the greedy evaluation are those of the sequential run"""
+    from enero_b200.train import TrainingRun
+    specs = ((8, 11, 1003), (9, 12, 1004), (7, 10, 1005))
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("ENERO_ROLLOUT_THREADS", mode)
+        run = TrainingRun.synthetic(ctx, specs, n_train_tms=6, n_eval_tms=3, folder=os.path.join(str(tmp_path), "data" + mode),
+                                    eval_episodes=3)
+        try:
+            buf = run.collect()
+            ev = run.evaluate()
+        finally:
+            run.close()
+        out[mode] = (buf, ev)
+    a, b = out["1"][0], out["0"][0]
+    assert len(a["tensors"]) == len(b["tensors"]) > 0
+    for x, y in zip(a["tensors"], b["tensors"]):
+        assert x["sd"] == y["sd"] and x["bw"] == y["bw"] and np.array_equal(x["loads"], y["loads"]) and x["old_prob"] == y["old_prob"]
+    assert a["actions"] == b["actions"] and a["rewards"] == b["rewards"] and a["masks"] == b["masks"]
+    assert np.array_equal(np.asarray(a["values"]), np.asarray(b["values"]))
+    for x, y in zip(out["1"][1], out["0"][1]):
+        assert np.array_equal(x, y)
